@@ -1,0 +1,1025 @@
+// engine.cu — host side of the B200 decode engine: model load, paged-KV bookkeeping, CUDA-graph'd decode loop.
+//
+// Stands in for the model-load + generate path of the external serving image the reference's ServerReconciler
+// launches (internal/controller/server_controller.go:114-205; container contract docs/container-contract.md:25-55).
+// Forward structure = HF LlamaModel.forward / LlamaDecoderLayer.forward (HF:models/llama/modeling_llama.py:292-332,
+// 355-500); greedy loop = HF:generation/utils.py:2658-2800.  No CPU fallback anywhere: init() fails with
+// SSB_ENODEV when there is no sm_100 device.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ssb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+const char* get_error() { return g_err.c_str(); }
+
+#define CK(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return SSB_ECUDA;                                                                                  \
+    }                                                                                                    \
+  } while (0)
+#define RET(code, msg)   \
+  do {                   \
+    set_error(msg);      \
+    return (code);       \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != SSB_OK) return _r; \
+  } while (0)
+
+// synthetic-weight conventions; twins of oracle/synth.py (W_AMP, LMHEAD_GAIN, NORM_AMP, tensor ids)
+static const float kWAmp = 0.02f * 1.7320508075688772f;
+static const float kLmHeadGain = 4.0f;
+static const float kNormAmp = 0.1f;
+enum { K_Q = 0, K_K, K_V, K_O, K_GATE, K_UP, K_DOWN, K_LN1, K_LN2 };
+static const uint32_t kGlobal = 1u << 20;
+
+Engine::~Engine() {
+  if (device_ >= 0) cudaSetDevice(device_);
+  for (auto& g : graphs_) cudaGraphExecDestroy(g.second);
+  for (void* p : allocs_) cudaFree(p);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+template <typename T>
+int Engine::dmalloc(T** p, size_t n) {
+  void* v = nullptr;
+  size_t bytes = std::max<size_t>(n * sizeof(T), 256);
+  cudaError_t e = cudaMalloc(&v, bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return SSB_ENOMEM;
+  }
+  allocs_.push_back(v);
+  hbm_bytes_ += bytes;
+  *p = (T*)v;
+  return SSB_OK;
+}
+
+int Engine::load_config(const std::string& dir, const Json& params) {
+  std::string txt;
+  if (!read_text_file(dir + "/config.json", &txt)) RET(SSB_EIO, "cannot read " + dir + "/config.json");
+  Json c;
+  try {
+    c = json_parse(txt);
+  } catch (std::exception& e) {
+    RET(SSB_EINVAL, std::string("config.json: ") + e.what());
+  }
+  cfg_.model_type = c.get_str("model_type", "llama");
+  if (cfg_.model_type != "llama") RET(SSB_EINVAL, "unsupported model_type '" + cfg_.model_type + "' (llama family only in this build)");
+  cfg_.hidden = (int)c.get_int("hidden_size", 0);
+  cfg_.inter = (int)c.get_int("intermediate_size", 0);
+  cfg_.layers = (int)c.get_int("num_hidden_layers", 0);
+  cfg_.heads = (int)c.get_int("num_attention_heads", 0);
+  cfg_.kv_heads = (int)c.get_int("num_key_value_heads", cfg_.heads);
+  cfg_.head_dim = (int)c.get_int("head_dim", cfg_.heads ? cfg_.hidden / cfg_.heads : 0);
+  cfg_.vocab = (int)c.get_int("vocab_size", 0);
+  cfg_.max_pos = (int)c.get_int("max_position_embeddings", 2048);
+  cfg_.eps = (float)c.get_num("rms_norm_eps", 1e-6);
+  cfg_.theta = (float)c.get_num("rope_theta", 10000.0);
+  if (const Json* rp = c.find("rope_parameters"))
+    if (rp->kind == Json::Obj) cfg_.theta = (float)rp->get_num("rope_theta", cfg_.theta);
+  if (const Json* rs = c.find("rope_scaling"))
+    if (rs->kind == Json::Obj && rs->get_str("rope_type", rs->get_str("type", "default")) != "default")
+      RET(SSB_EINVAL, "rope_scaling other than 'default' is not supported");
+  cfg_.tie_embeddings = c.get_num("tie_word_embeddings", 0) != 0;
+  if (cfg_.hidden <= 0 || cfg_.inter <= 0 || cfg_.layers <= 0 || cfg_.heads <= 0 || cfg_.vocab <= 0)
+    RET(SSB_EINVAL, "config.json: missing model dimensions");
+  if (cfg_.head_dim != 64 && cfg_.head_dim != 128) RET(SSB_EINVAL, "head_dim must be 64 or 128");
+  if (cfg_.hidden % 8 || cfg_.inter % 8 || cfg_.vocab % 2) RET(SSB_EINVAL, "hidden/intermediate must be multiples of 8, vocab even");
+  if (cfg_.heads % cfg_.kv_heads) RET(SSB_EINVAL, "num_attention_heads must be a multiple of num_key_value_heads");
+  const int group = cfg_.heads / cfg_.kv_heads;
+  if (group > 8 && group % 8) RET(SSB_EINVAL, "GQA group must be <= 8 or a multiple of 8");
+  tp_size_ = (int)params.get_int("tp_size", 1);
+  tp_rank_ = (int)params.get_int("tp_rank", 0);
+  if (tp_size_ < 1 || tp_rank_ < 0 || tp_rank_ >= tp_size_) RET(SSB_EINVAL, "bad tp_size/tp_rank");
+  if (cfg_.kv_heads % tp_size_ || cfg_.inter % (8 * tp_size_)) RET(SSB_EINVAL, "tp_size must divide kv heads and intermediate_size/8");
+  Hl_ = cfg_.heads / tp_size_;
+  KVHl_ = cfg_.kv_heads / tp_size_;
+  Il_ = cfg_.inter / tp_size_;
+  return SSB_OK;
+}
+
+int Engine::alloc_weights() {
+  const size_t h = cfg_.hidden, D = cfg_.head_dim;
+  const size_t qkv_rows = (size_t)(Hl_ + 2 * KVHl_) * D;
+  lw_.resize(cfg_.layers);
+  for (auto& w : lw_) {
+    TRY(dmalloc(&w.wqkv, qkv_rows * h));
+    TRY(dmalloc(&w.wo, h * (size_t)Hl_ * D));
+    TRY(dmalloc(&w.wgu, 2 * (size_t)Il_ * h));
+    TRY(dmalloc(&w.wdown, h * (size_t)Il_));
+    TRY(dmalloc(&w.ln1, h));
+    TRY(dmalloc(&w.ln2, h));
+  }
+  TRY(dmalloc(&embed_, (size_t)cfg_.vocab * h));
+  if (cfg_.tie_embeddings)
+    lm_head_ = embed_;
+  else
+    TRY(dmalloc(&lm_head_, (size_t)cfg_.vocab * h));
+  TRY(dmalloc(&final_norm_, h));
+  weight_bytes_step_ = 2 * ((int64_t)cfg_.layers * (int64_t)(qkv_rows * h + h * Hl_ * D + 3 * (size_t)Il_ * h) + (int64_t)cfg_.vocab * h);
+  return SSB_OK;
+}
+
+// One destination matrix region filled either from a checkpoint tensor or from the synthetic generator.
+struct FillJob {
+  bf16* dst;            // destination (row r at dst + r*dst_ld)
+  int64_t dst_ld;
+  std::vector<int> rows;  // logical source rows (empty => identity 0..n_rows-1)
+  int n_rows;
+  int col0, cols;
+  int64_t full_cols;    // logical columns of the HF tensor
+  std::string name;     // HF tensor name
+  uint32_t tid;
+  float amp, base;
+};
+
+int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) {
+  const int h = cfg_.hidden, D = cfg_.head_dim, half = D / 2;
+  const int h0 = tp_rank_ * Hl_, kv0 = tp_rank_ * KVHl_, i0 = tp_rank_ * Il_;
+  std::vector<FillJob> jobs;
+  auto ident = [](int start, int n) {
+    std::vector<int> v(n);
+    for (int i = 0; i < n; ++i) v[i] = start + i;
+    return v;
+  };
+  // pair-interleave so that physical rows (2p, 2p+1) = logical (head*D + j, head*D + j + D/2): RoPE partners adjacent
+  auto rope_rows = [&](int head0, int nheads) {
+    std::vector<int> v((size_t)nheads * D);
+    for (int r = 0; r < nheads * D; ++r) {
+      int p = r >> 1, hd = p / half, j = p % half;
+      v[r] = (head0 + hd) * D + j + (r & 1) * half;
+    }
+    return v;
+  };
+  for (int l = 0; l < cfg_.layers; ++l) {
+    const std::string p = "model.layers." + std::to_string(l) + ".";
+    const uint32_t t = (uint32_t)l * 16;
+    LayerW& w = lw_[l];
+    jobs.push_back({w.wqkv, h, rope_rows(h0, Hl_), Hl_ * D, 0, h, h, p + "self_attn.q_proj.weight", t + K_Q, kWAmp, 0.f});
+    jobs.push_back({w.wqkv + (size_t)Hl_ * D * h, h, rope_rows(kv0, KVHl_), KVHl_ * D, 0, h, h, p + "self_attn.k_proj.weight", t + K_K, kWAmp, 0.f});
+    jobs.push_back({w.wqkv + (size_t)(Hl_ + KVHl_) * D * h, h, ident(kv0 * D, KVHl_ * D), KVHl_ * D, 0, h, h, p + "self_attn.v_proj.weight", t + K_V, kWAmp, 0.f});
+    jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, (int64_t)cfg_.heads * D, p + "self_attn.o_proj.weight", t + K_O, kWAmp, 0.f});
+    // gate/up interleaved row-wise: physical row 2i = gate_i, 2i+1 = up_i (SwiGLU partners adjacent)
+    jobs.push_back({w.wgu, 2 * (int64_t)h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.gate_proj.weight", t + K_GATE, kWAmp, 0.f});
+    jobs.push_back({w.wgu + h, 2 * (int64_t)h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.up_proj.weight", t + K_UP, kWAmp, 0.f});
+    jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, cfg_.inter, p + "mlp.down_proj.weight", t + K_DOWN, kWAmp, 0.f});
+    jobs.push_back({w.ln1, h, {}, 1, 0, h, h, p + "input_layernorm.weight", t + K_LN1, kNormAmp, 1.f});
+    jobs.push_back({w.ln2, h, {}, 1, 0, h, h, p + "post_attention_layernorm.weight", t + K_LN2, kNormAmp, 1.f});
+  }
+  jobs.push_back({embed_, h, {}, cfg_.vocab, 0, h, h, "model.embed_tokens.weight", kGlobal + 0, kWAmp, 0.f});
+  if (!cfg_.tie_embeddings) jobs.push_back({lm_head_, h, {}, cfg_.vocab, 0, h, h, "lm_head.weight", kGlobal + 2, kWAmp * kLmHeadGain, 0.f});
+  jobs.push_back({final_norm_, h, {}, 1, 0, h, h, "model.norm.weight", kGlobal + 1, kNormAmp, 1.f});
+
+  ModelFiles files;
+  size_t max_src = 0;
+  if (!synthetic) {
+    std::string err;
+    if (!files.open(dir, &err)) RET(SSB_EIO, err);
+    if (files.is_gguf()) RET(SSB_EINVAL, "GGUF checkpoints are handled by the gguf path (not in this build step)");
+    for (auto& j : jobs) {
+      const TensorView* tv = files.find(j.name);
+      if (!tv) RET(SSB_EIO, "checkpoint is missing tensor " + j.name);
+      if (tv->dtype > DT_F32) RET(SSB_EINVAL, "unsupported dtype for " + j.name);
+      if (tv->cols() != j.full_cols) RET(SSB_EINVAL, "unexpected shape for " + j.name);
+      max_src = std::max(max_src, tv->nbytes);
+    }
+  }
+  int* d_rows = nullptr;
+  size_t max_rows = 0;
+  for (auto& j : jobs) max_rows = std::max(max_rows, j.rows.size());
+  CK(cudaMalloc(&d_rows, std::max<size_t>(max_rows, 1) * sizeof(int)));
+  void* d_src = nullptr;
+  if (max_src) CK(cudaMalloc(&d_src, max_src));
+  int rc = SSB_OK;
+  for (auto& j : jobs) {
+    const int* rows = nullptr;
+    if (!j.rows.empty()) {
+      cudaMemcpyAsync(d_rows, j.rows.data(), j.rows.size() * sizeof(int), cudaMemcpyHostToDevice, stream_);
+      rows = d_rows;
+    }
+    cudaError_t e;
+    if (synthetic) {
+      e = launch_synth_fill(j.dst, j.dst_ld, rows, j.n_rows, j.col0, j.cols, j.full_cols, seed, j.tid, j.amp, j.base, stream_);
+    } else {
+      const TensorView* tv = files.find(j.name);
+      cudaMemcpyAsync(d_src, tv->data, tv->nbytes, cudaMemcpyHostToDevice, stream_);
+      timing_.h2d_bytes += (int64_t)tv->nbytes;
+      e = launch_gather_rows(j.dst, j.dst_ld, d_src, tv->dtype, tv->cols(), rows, j.n_rows, j.col0, j.cols, stream_);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);  // d_rows / d_src are reused by the next job
+    if (e != cudaSuccess) {
+      set_error(std::string("weight fill ") + j.name + ": " + cudaGetErrorString(e));
+      rc = SSB_ECUDA;
+      break;
+    }
+  }
+  cudaFree(d_rows);
+  if (d_src) cudaFree(d_src);
+  return rc;
+}
+
+int Engine::decode_splits_(int M) const {
+  const int group = cfg_.heads / cfg_.kv_heads;
+  const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
+  const int ctas = M * (Hl_ / gc);
+  int s = (2 * n_sm_ + ctas - 1) / ctas;
+  return std::max(1, std::min(s, 16));
+}
+
+int Engine::alloc_runtime(const Json& params) {
+  const int h = cfg_.hidden, D = cfg_.head_dim;
+  max_batch_ = (int)params.get_int("max_batch", 32);
+  max_seq_ = (int)params.get_int("max_seq_len", cfg_.max_pos);
+  block_size_ = (int)params.get_int("kv_block_size", 16);
+  if (max_batch_ < 1 || max_seq_ < 1 || (block_size_ != 8 && block_size_ != 16 && block_size_ != 32 && block_size_ != 64))
+    RET(SSB_EINVAL, "bad max_batch / max_seq_len / kv_block_size (8|16|32|64)");
+  max_blocks_per_seq_ = (max_seq_ + block_size_ - 1) / block_size_;
+  m_max_ = std::max(max_batch_, (int)params.get_int("prefill_chunk", 1024));
+  max_steps_ = max_seq_;
+  // rope table
+  {
+    const int half = D / 2;
+    std::vector<uint32_t> cs((size_t)max_seq_ * half);
+    std::vector<float> inv(half);
+    // HF: inv_freq = 1 / theta^(2j/d) in fp32; freqs = pos * inv_freq (fp32); cos/sin fp32 -> bf16
+    for (int j = 0; j < half; ++j) inv[j] = 1.0f / powf(cfg_.theta, (float)(2 * j) / (float)D);
+    for (int p = 0; p < max_seq_; ++p)
+      for (int j = 0; j < half; ++j) {
+        const float f = (float)p * inv[j];
+        __nv_bfloat16 c = __float2bfloat16_rn(cosf(f)), s = __float2bfloat16_rn(sinf(f));
+        uint16_t cb, sb;
+        memcpy(&cb, &c, 2);
+        memcpy(&sb, &s, 2);
+        cs[(size_t)p * half + j] = (uint32_t)cb | ((uint32_t)sb << 16);
+      }
+    TRY(dmalloc(&rope_cs_, cs.size()));
+    CK(cudaMemcpy(rope_cs_, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+  }
+  TRY(dmalloc(&h_, (size_t)m_max_ * h));
+  TRY(dmalloc(&q_, (size_t)m_max_ * Hl_ * D));
+  TRY(dmalloc(&attn_, (size_t)m_max_ * Hl_ * D));
+  TRY(dmalloc(&act_, (size_t)m_max_ * Il_));
+  TRY(dmalloc(&logits_, (size_t)max_batch_ * cfg_.vocab));
+  const int max_splits = 16;
+  TRY(dmalloc(&part_o_, (size_t)max_batch_ * Hl_ * max_splits * D));
+  TRY(dmalloc(&part_ml_, (size_t)max_batch_ * Hl_ * max_splits * 2));
+  TRY(dmalloc(&counters_, (size_t)m_max_ * Hl_));
+  CK(cudaMemset(counters_, 0, (size_t)m_max_ * Hl_ * sizeof(int)));
+  TRY(dmalloc(&row_tok_, (size_t)m_max_));
+  TRY(dmalloc(&row_slot_, (size_t)m_max_));
+  TRY(dmalloc(&row_pos_, (size_t)m_max_));
+  TRY(dmalloc(&logit_rows_, (size_t)max_batch_));
+  TRY(dmalloc(&next_tok_, (size_t)max_batch_));
+  TRY(dmalloc(&hist_, (size_t)max_steps_ * max_batch_));
+  TRY(dmalloc(&step_, 1));
+  TRY(dmalloc(&block_table_, (size_t)max_batch_ * max_blocks_per_seq_));
+  CK(cudaMemset(block_table_, 0, (size_t)max_batch_ * max_blocks_per_seq_ * sizeof(int)));
+  host_bt_.assign((size_t)max_batch_ * max_blocks_per_seq_, 0);
+  taps_ = params.get_int("debug_taps", 0) != 0;
+  if (taps_) {
+    TRY(dmalloc(&tap_q0_, (size_t)m_max_ * Hl_ * D));
+    TRY(dmalloc(&tap_attn0_, (size_t)m_max_ * Hl_ * D));
+    TRY(dmalloc(&tap_h0_, (size_t)m_max_ * h));
+  }
+  // KV pool
+  const size_t block_elems = (size_t)KVHl_ * block_size_ * D;
+  const size_t block_bytes_all_layers = block_elems * 2 /*bf16*/ * 2 /*K,V*/ * cfg_.layers;
+  int64_t want = params.get_int("kv_blocks", (int64_t)max_batch_ * max_blocks_per_seq_);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const int64_t fit = (int64_t)((double)free_b * 0.92 / (double)block_bytes_all_layers);
+  n_blocks_ = (int)std::min<int64_t>(want, fit);
+  if (n_blocks_ < max_blocks_per_seq_ && n_blocks_ < want) RET(SSB_ENOMEM, "not enough HBM for the KV block pool");
+  kv_layer_elems_ = (size_t)n_blocks_ * block_elems;
+  TRY(dmalloc(&kpool_, kv_layer_elems_ * cfg_.layers));
+  TRY(dmalloc(&vpool_, kv_layer_elems_ * cfg_.layers));
+  free_blocks_.resize(n_blocks_);
+  for (int i = 0; i < n_blocks_; ++i) free_blocks_[i] = n_blocks_ - 1 - i;
+  slots_.assign(max_batch_, SeqSlot());
+  return SSB_OK;
+}
+
+int Engine::init(const std::string& model_dir, const std::string& params_json) {
+  Json params;
+  try {
+    params = json_parse(params_json.empty() ? "{}" : params_json);
+  } catch (std::exception& e) {
+    RET(SSB_EINVAL, std::string("params.json: ") + e.what());
+  }
+  if (params.kind != Json::Obj) RET(SSB_EINVAL, "params.json must be a JSON object");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    device_ = -1;
+    RET(SSB_ENODEV, "no CUDA device: libsubstratus_b200 has no CPU fallback");
+  }
+  TRY(load_config(model_dir, params));
+  device_ = (int)params.get_int("device", tp_rank_ % ndev);
+  if (device_ < 0 || device_ >= ndev) RET(SSB_EINVAL, "bad device index");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major != 10) {
+    RET(SSB_ENODEV, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                        "; this library contains sm_100a code only");
+  }
+  CK(cudaSetDevice(device_));
+  n_sm_ = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0_));
+  CK(cudaEventCreate(&ev1_));
+  use_pdl_ = params.get_int("use_pdl", 1) != 0;
+  use_graph_ = params.get_int("use_graph", 1) != 0;
+  if (tp_size_ > 1) RET(SSB_EINVAL, "tensor parallel engines need ssb_tp_connect (not available in this build step)");
+  TRY(alloc_weights());
+  const std::string wmode = params.get_str("weights", "file");
+  if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
+  TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0)));
+  TRY(alloc_runtime(params));
+  CK(cudaStreamSynchronize(stream_));
+  timing_reset();
+  return SSB_OK;
+}
+
+int Engine::info(ssb_info* o) const {
+  memset(o, 0, sizeof(*o));
+  o->vocab_size = cfg_.vocab;
+  o->hidden_size = cfg_.hidden;
+  o->n_layers = cfg_.layers;
+  o->n_heads = cfg_.heads;
+  o->n_kv_heads = cfg_.kv_heads;
+  o->head_dim = cfg_.head_dim;
+  o->intermediate_size = cfg_.inter;
+  o->max_seq_len = max_seq_;
+  o->max_batch = max_batch_;
+  o->kv_block_size = block_size_;
+  o->tp_size = tp_size_;
+  o->tp_rank = tp_rank_;
+  o->n_sm = n_sm_;
+  o->device = device_;
+  o->weight_bytes_per_step = weight_bytes_step_;
+  o->kv_bytes_per_token = (int64_t)2 * cfg_.layers * KVHl_ * cfg_.head_dim * 2;
+  o->hbm_bytes_allocated = (int64_t)hbm_bytes_;
+  snprintf(o->model_type, sizeof o->model_type, "%s", cfg_.model_type.c_str());
+  snprintf(o->dtype, sizeof o->dtype, "bf16");
+  return SSB_OK;
+}
+
+int Engine::seq_create(int* id) {
+  for (int i = 0; i < max_batch_; ++i)
+    if (!slots_[i].used) {
+      slots_[i].used = true;
+      slots_[i].len = 0;
+      slots_[i].blocks.clear();
+      *id = i;
+      return SSB_OK;
+    }
+  RET(SSB_ENOMEM, "all sequence slots are in use (max_batch)");
+}
+
+int Engine::seq_free(int id) {
+  if (id < 0 || id >= max_batch_ || !slots_[id].used) RET(SSB_EINVAL, "bad seq_id");
+  for (int b : slots_[id].blocks) free_blocks_.push_back(b);
+  slots_[id] = SeqSlot();
+  return SSB_OK;
+}
+
+int Engine::seq_len(int id, int* len) const {
+  if (id < 0 || id >= max_batch_ || !slots_[id].used) RET(SSB_EINVAL, "bad seq_id");
+  *len = slots_[id].len;
+  return SSB_OK;
+}
+
+int Engine::ensure_blocks(int slot, int new_len) {
+  if (new_len > max_seq_) RET(SSB_EINVAL, "sequence would exceed max_seq_len");
+  SeqSlot& s = slots_[slot];
+  const int need = (new_len + block_size_ - 1) / block_size_;
+  while ((int)s.blocks.size() < need) {
+    if (free_blocks_.empty()) RET(SSB_ENOMEM, "KV block pool exhausted");
+    const int b = free_blocks_.back();
+    free_blocks_.pop_back();
+    host_bt_[(size_t)slot * max_blocks_per_seq_ + s.blocks.size()] = b;
+    s.blocks.push_back(b);
+  }
+  return SSB_OK;
+}
+
+int Engine::upload_block_rows(const std::vector<int>& slots) {
+  for (int s : slots) {
+    const size_t n = slots_[s].blocks.size();
+    if (!n) continue;
+    CK(cudaMemcpyAsync(block_table_ + (size_t)s * max_blocks_per_seq_, host_bt_.data() + (size_t)s * max_blocks_per_seq_,
+                       n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    timing_.h2d_bytes += (int64_t)(n * sizeof(int));
+  }
+  return SSB_OK;
+}
+
+// Enqueue one forward pass over the M staged rows (row_tok_/row_slot_/row_pos_).  The last-position logits of the
+// n_logit_rows rows listed in logit_rows_ go to logits_; greedy picks to next_tok_.  decode_mode: rows == batch,
+// argmax feeds row_tok_ back, appends to hist_ and advances row_pos_ (device-resident loop, graph-capturable).
+int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
+  const int h = cfg_.hidden, D = cfg_.head_dim;
+  const int group = cfg_.heads / cfg_.kv_heads;
+  int launches = 0;
+  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, lc(true)));
+  ++launches;
+  const int n_splits = (M <= max_batch_) ? decode_splits_(M) : 1;
+  for (int l = 0; l < cfg_.layers; ++l) {
+    const LayerW& w = lw_[l];
+    GemvArgs g = {};
+    g.W = w.wqkv;
+    g.N = (Hl_ + 2 * KVHl_) * D;
+    g.K = h;
+    g.x = h_;
+    g.ldx = h;
+    g.M = M;
+    g.norm_w = w.ln1;
+    g.eps = cfg_.eps;
+    g.q_out = q_;
+    g.q_rows = Hl_ * D;
+    g.kv_rows = KVHl_ * D;
+    g.head_dim = D;
+    g.kcache = kpool_ + (size_t)l * kv_layer_elems_;
+    g.vcache = vpool_ + (size_t)l * kv_layer_elems_;
+    g.block_table = block_table_;
+    g.bt_stride = max_blocks_per_seq_;
+    g.row_slot = row_slot_;
+    g.row_pos = row_pos_;
+    g.rope_cs = rope_cs_;
+    g.block_size = block_size_;
+    g.kvh = KVHl_;
+    CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
+
+    AttnArgs a = {};
+    a.q = q_;
+    a.kcache = g.kcache;
+    a.vcache = g.vcache;
+    a.block_table = block_table_;
+    a.bt_stride = max_blocks_per_seq_;
+    a.row_slot = row_slot_;
+    a.row_pos = row_pos_;
+    a.out = attn_;
+    a.part_o = part_o_;
+    a.part_ml = part_ml_;
+    a.counters = counters_;
+    a.M = M;
+    a.n_heads = Hl_;
+    a.kvh = KVHl_;
+    a.group = group;
+    a.head_dim = D;
+    a.block_size = block_size_;
+    a.n_splits = n_splits;
+    a.scale = 1.0f / sqrtf((float)D);
+    CK(launch_attn_decode(a, lc(true)));
+    if (taps_ && l == 0) {
+      CK(cudaMemcpyAsync(tap_q0_, q_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
+      CK(cudaMemcpyAsync(tap_attn0_, attn_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
+    }
+
+    GemvArgs o = {};
+    o.W = w.wo;
+    o.N = h;
+    o.K = Hl_ * D;
+    o.x = attn_;
+    o.ldx = Hl_ * D;
+    o.M = M;
+    o.out_bf16 = h_;
+    o.resid = h_;
+    o.ld_out = h;
+    CK(launch_gemv(o, EPI_RESID, NORM_NONE, lc(true)));
+
+    GemvArgs u = {};
+    u.W = w.wgu;
+    u.N = 2 * Il_;
+    u.K = h;
+    u.x = h_;
+    u.ldx = h;
+    u.M = M;
+    u.norm_w = w.ln2;
+    u.eps = cfg_.eps;
+    u.out_bf16 = act_;
+    u.ld_out = Il_;
+    CK(launch_gemv(u, EPI_SWIGLU, NORM_RMS, lc(true)));
+
+    GemvArgs d = {};
+    d.W = w.wdown;
+    d.N = h;
+    d.K = Il_;
+    d.x = act_;
+    d.ldx = Il_;
+    d.M = M;
+    d.out_bf16 = h_;
+    d.resid = h_;
+    d.ld_out = h;
+    CK(launch_gemv(d, EPI_RESID, NORM_NONE, lc(true)));
+    launches += 5;
+    if (taps_ && l == 0) {
+      CK(cudaMemcpyAsync(tap_h0_, h_, (size_t)M * h * 2, cudaMemcpyDeviceToDevice, stream_));
+      tap_rows_ = M;
+    }
+  }
+  if (n_logit_rows > 0) {
+    GemvArgs g = {};
+    g.W = lm_head_;
+    g.N = cfg_.vocab;
+    g.K = h;
+    g.x = h_;
+    g.ldx = h;
+    g.M = n_logit_rows;
+    g.row_map = decode_mode ? nullptr : logit_rows_;
+    g.norm_w = final_norm_;
+    g.eps = cfg_.eps;
+    g.out_f32 = logits_;
+    g.ld_out = cfg_.vocab;
+    CK(launch_gemv(g, EPI_F32_BF16R, NORM_RMS, lc(true)));
+    CK(launch_argmax(logits_, cfg_.vocab, n_logit_rows, decode_mode ? row_tok_ : next_tok_, decode_mode ? hist_ : nullptr,
+                     step_, decode_mode ? row_pos_ : nullptr, lc(true)));
+    launches += 2;
+  }
+  launches_per_forward_ = launches;
+  timing_.kernel_launches += launches;
+  return SSB_OK;
+}
+
+int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits) {
+  if (nseq < 1 || nseq > max_batch_) RET(SSB_EINVAL, "nseq out of range");
+  CK(cudaSetDevice(device_));
+  int total = 0;
+  std::vector<int> slots(seq_ids, seq_ids + nseq);
+  for (int i = 0; i < nseq; ++i) {
+    const int s = seq_ids[i];
+    if (s < 0 || s >= max_batch_ || !slots_[s].used) RET(SSB_EINVAL, "bad seq_id");
+    if (lens[i] < 1) RET(SSB_EINVAL, "empty prompt");
+    for (int j = 0; j < i; ++j)
+      if (seq_ids[j] == s) RET(SSB_EINVAL, "duplicate seq_id");
+    TRY(ensure_blocks(s, slots_[s].len + lens[i]));
+    total += lens[i];
+  }
+  for (int i = 0, o = 0; i < nseq; o += lens[i], ++i)
+    for (int t = 0; t < lens[i]; ++t)
+      if (tokens[o + t] < 0 || tokens[o + t] >= cfg_.vocab) RET(SSB_EINVAL, "token id out of range");
+  TRY(upload_block_rows(slots));
+  // flatten rows
+  std::vector<int> r_tok(total), r_slot(total), r_pos(total), r_last(total, -1);
+  for (int i = 0, o = 0; i < nseq; o += lens[i], ++i)
+    for (int t = 0; t < lens[i]; ++t) {
+      r_tok[o + t] = tokens[o + t];
+      r_slot[o + t] = seq_ids[i];
+      r_pos[o + t] = slots_[seq_ids[i]].len + t;
+      if (t == lens[i] - 1) r_last[o + t] = i;
+    }
+  CK(cudaEventRecord(ev0_, stream_));
+  std::vector<int> h_next(nseq, 0);
+  for (int base = 0; base < total; base += m_max_) {
+    const int M = std::min(m_max_, total - base);
+    std::vector<int> lrows, lseq;
+    for (int r = 0; r < M; ++r)
+      if (r_last[base + r] >= 0) {
+        lrows.push_back(r);
+        lseq.push_back(r_last[base + r]);
+      }
+    CK(cudaMemcpyAsync(row_tok_, r_tok.data() + base, M * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(row_slot_, r_slot.data() + base, M * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(row_pos_, r_pos.data() + base, M * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    timing_.h2d_bytes += 3LL * M * sizeof(int);
+    if (!lrows.empty()) {
+      CK(cudaMemcpyAsync(logit_rows_, lrows.data(), lrows.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      timing_.h2d_bytes += (int64_t)(lrows.size() * sizeof(int));
+    }
+    TRY(forward(M, (int)lrows.size(), false));
+    if (!lrows.empty()) {
+      std::vector<int> tmp(lrows.size());
+      CK(cudaMemcpyAsync(tmp.data(), next_tok_, lrows.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      timing_.d2h_bytes += (int64_t)(lrows.size() * sizeof(int));
+      if (logits) {
+        // rows of logits_ are in lrows order; scatter to the caller's [nseq, V]
+        std::vector<float> lt(lrows.size() * (size_t)cfg_.vocab);
+        CK(cudaMemcpyAsync(lt.data(), logits_, lt.size() * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        timing_.d2h_bytes += (int64_t)(lt.size() * sizeof(float));
+        for (size_t k = 0; k < lrows.size(); ++k)
+          memcpy(logits + (size_t)lseq[k] * cfg_.vocab, lt.data() + k * cfg_.vocab, (size_t)cfg_.vocab * sizeof(float));
+      } else {
+        CK(cudaStreamSynchronize(stream_));
+      }
+      for (size_t k = 0; k < lrows.size(); ++k) h_next[lseq[k]] = tmp[k];
+    }
+  }
+  CK(cudaEventRecord(ev1_, stream_));
+  CK(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  timing_.prefill_ms = ms;
+  for (int i = 0; i < nseq; ++i) {
+    slots_[seq_ids[i]].len += lens[i];
+    next_tok[i] = h_next[i];
+  }
+  return SSB_OK;
+}
+
+int Engine::build_graph(int B) {
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+  int rc = forward(B, B, true);
+  cudaError_t e = cudaStreamEndCapture(stream_, &graph);
+  if (rc != SSB_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) RET(SSB_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) RET(SSB_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  graphs_[B] = exec;
+  timing_.kernel_launches -= launches_per_forward_;  // capture enqueued nothing
+  return SSB_OK;
+}
+
+int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float* logits) {
+  if (nseq < 1 || nseq > max_batch_) RET(SSB_EINVAL, "nseq out of range");
+  if (nsteps < 1 || nsteps > max_steps_) RET(SSB_EINVAL, "nsteps out of range");
+  CK(cudaSetDevice(device_));
+  std::vector<int> slots(seq_ids, seq_ids + nseq), pos(nseq);
+  for (int i = 0; i < nseq; ++i) {
+    const int s = seq_ids[i];
+    if (s < 0 || s >= max_batch_ || !slots_[s].used) RET(SSB_EINVAL, "bad seq_id");
+    for (int j = 0; j < i; ++j)
+      if (seq_ids[j] == s) RET(SSB_EINVAL, "duplicate seq_id");
+    if (last_tok[i] < 0 || last_tok[i] >= cfg_.vocab) RET(SSB_EINVAL, "token id out of range");
+    TRY(ensure_blocks(s, slots_[s].len + nsteps));
+    pos[i] = slots_[s].len;
+  }
+  TRY(upload_block_rows(slots));
+  CK(cudaMemcpyAsync(row_tok_, last_tok, nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CK(cudaMemcpyAsync(row_slot_, slots.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CK(cudaMemcpyAsync(row_pos_, pos.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CK(cudaMemsetAsync(step_, 0xFF, sizeof(int), stream_));  // -1: the embed kernel pre-increments
+  timing_.h2d_bytes += 3LL * nseq * sizeof(int);
+  const bool graph = use_graph_ && !taps_;
+  if (graph && !graphs_.count(nseq)) {
+    CK(cudaStreamSynchronize(stream_));
+    TRY(build_graph(nseq));
+  }
+  CK(cudaEventRecord(ev0_, stream_));
+  for (int s = 0; s < nsteps; ++s) {
+    if (graph) {
+      CK(cudaGraphLaunch(graphs_[nseq], stream_));
+      timing_.kernel_launches += launches_per_forward_;
+    } else {
+      TRY(forward(nseq, nseq, true));
+    }
+    if (logits) {
+      CK(cudaMemcpyAsync(logits + (size_t)s * nseq * cfg_.vocab, logits_, (size_t)nseq * cfg_.vocab * sizeof(float),
+                         cudaMemcpyDeviceToHost, stream_));
+      timing_.d2h_bytes += (int64_t)nseq * cfg_.vocab * sizeof(float);
+    }
+  }
+  CK(cudaEventRecord(ev1_, stream_));
+  std::vector<int> hist((size_t)nsteps * nseq);
+  CK(cudaMemcpyAsync(hist.data(), hist_, hist.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CK(cudaStreamSynchronize(stream_));
+  timing_.d2h_bytes += (int64_t)(hist.size() * sizeof(int));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  timing_.decode_ms = ms;
+  for (int i = 0; i < nseq; ++i) {
+    for (int s = 0; s < nsteps; ++s) out_tok[(size_t)i * nsteps + s] = hist[(size_t)s * nseq + i];
+    slots_[seq_ids[i]].len += nsteps;
+  }
+  return SSB_OK;
+}
+
+// Times `iters` back-to-back launches of one kernel class, cycling over the layers' weights (so nothing is served
+// from L2), between CUDA events on the engine stream.  rows = batch rows; ctx = cached length for "attn".
+int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double* ms_out, int64_t* bytes_out) {
+  if (rows < 1 || rows > max_batch_ || iters < 1) RET(SSB_EINVAL, "bad rows/iters");
+  CK(cudaSetDevice(device_));
+  const std::string w = which ? which : "";
+  const int h = cfg_.hidden, D = cfg_.head_dim;
+  // stage a decode-like batch: rows sequences of length ctx (slots 0..rows-1 must be free)
+  std::vector<int> sl(rows), tok(rows, 1), pos(rows, ctx - 1);
+  for (int i = 0; i < rows; ++i) {
+    if (slots_[i].used) RET(SSB_ESTATE, "bench_kernel needs free sequence slots");
+    sl[i] = i;
+  }
+  for (int i = 0; i < rows; ++i) {
+    slots_[i].used = true;
+    int rc = ensure_blocks(i, ctx);
+    if (rc != SSB_OK) {
+      for (int j = 0; j <= i; ++j) seq_free(j);
+      return rc;
+    }
+  }
+  int rc = upload_block_rows(sl);
+  if (rc == SSB_OK) {
+    cudaMemcpyAsync(row_tok_, tok.data(), rows * sizeof(int), cudaMemcpyHostToDevice, stream_);
+    cudaMemcpyAsync(row_slot_, sl.data(), rows * sizeof(int), cudaMemcpyHostToDevice, stream_);
+    cudaMemcpyAsync(row_pos_, pos.data(), rows * sizeof(int), cudaMemcpyHostToDevice, stream_);
+    cudaMemsetAsync(h_, 0, (size_t)rows * h * 2, stream_);
+    cudaMemsetAsync(attn_, 0, (size_t)rows * Hl_ * D * 2, stream_);
+    cudaMemsetAsync(act_, 0, (size_t)rows * Il_ * 2, stream_);
+    cudaMemsetAsync(q_, 0, (size_t)rows * Hl_ * D * 2, stream_);
+  }
+  int64_t bytes = 0;
+  auto one = [&](int l) -> int {
+    const LayerW& lwv = lw_[l % cfg_.layers];
+    GemvArgs g = {};
+    g.x = h_;
+    g.ldx = h;
+    g.K = h;
+    g.M = rows;
+    g.eps = cfg_.eps;
+    if (w == "qkv") {
+      g.W = lwv.wqkv;
+      g.N = (Hl_ + 2 * KVHl_) * D;
+      g.norm_w = lwv.ln1;
+      g.q_out = q_;
+      g.q_rows = Hl_ * D;
+      g.kv_rows = KVHl_ * D;
+      g.head_dim = D;
+      g.kcache = kpool_ + (size_t)(l % cfg_.layers) * kv_layer_elems_;
+      g.vcache = vpool_ + (size_t)(l % cfg_.layers) * kv_layer_elems_;
+      g.block_table = block_table_;
+      g.bt_stride = max_blocks_per_seq_;
+      g.row_slot = row_slot_;
+      g.row_pos = row_pos_;
+      g.rope_cs = rope_cs_;
+      g.block_size = block_size_;
+      g.kvh = KVHl_;
+      bytes = 2LL * g.N * g.K;
+      CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
+    } else if (w == "gate_up") {
+      g.W = lwv.wgu;
+      g.N = 2 * Il_;
+      g.norm_w = lwv.ln2;
+      g.out_bf16 = act_;
+      g.ld_out = Il_;
+      bytes = 2LL * g.N * g.K;
+      CK(launch_gemv(g, EPI_SWIGLU, NORM_RMS, lc(true)));
+    } else if (w == "o") {
+      g.W = lwv.wo;
+      g.N = h;
+      g.K = Hl_ * D;
+      g.x = attn_;
+      g.ldx = Hl_ * D;
+      g.out_bf16 = h_;
+      g.resid = h_;
+      g.ld_out = h;
+      bytes = 2LL * g.N * g.K;
+      CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
+    } else if (w == "down") {
+      g.W = lwv.wdown;
+      g.N = h;
+      g.K = Il_;
+      g.x = act_;
+      g.ldx = Il_;
+      g.out_bf16 = h_;
+      g.resid = h_;
+      g.ld_out = h;
+      bytes = 2LL * g.N * g.K;
+      CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
+    } else if (w == "lm_head") {
+      g.W = lm_head_;
+      g.N = cfg_.vocab;
+      g.norm_w = final_norm_;
+      g.out_f32 = logits_;
+      g.ld_out = cfg_.vocab;
+      bytes = 2LL * g.N * g.K;
+      CK(launch_gemv(g, EPI_F32_BF16R, NORM_RMS, lc(true)));
+    } else if (w == "attn") {
+      AttnArgs a = {};
+      a.q = q_;
+      a.kcache = kpool_ + (size_t)(l % cfg_.layers) * kv_layer_elems_;
+      a.vcache = vpool_ + (size_t)(l % cfg_.layers) * kv_layer_elems_;
+      a.block_table = block_table_;
+      a.bt_stride = max_blocks_per_seq_;
+      a.row_slot = row_slot_;
+      a.row_pos = row_pos_;
+      a.out = attn_;
+      a.part_o = part_o_;
+      a.part_ml = part_ml_;
+      a.counters = counters_;
+      a.M = rows;
+      a.n_heads = Hl_;
+      a.kvh = KVHl_;
+      a.group = cfg_.heads / cfg_.kv_heads;
+      a.head_dim = D;
+      a.block_size = block_size_;
+      a.n_splits = decode_splits_(rows);
+      a.scale = 1.0f / sqrtf((float)D);
+      bytes = 2LL * rows * ctx * KVHl_ * D * 2;
+      CK(launch_attn_decode(a, lc(true)));
+    } else {
+      RET(SSB_EINVAL, "unknown kernel '" + w + "' (qkv|o|gate_up|down|lm_head|attn)");
+    }
+    return SSB_OK;
+  };
+  for (int i = 0; i < 3 && rc == SSB_OK; ++i) rc = one(i);
+  if (rc == SSB_OK) {
+    cudaEventRecord(ev0_, stream_);
+    for (int i = 0; i < iters && rc == SSB_OK; ++i) rc = one(i + 3);
+    cudaEventRecord(ev1_, stream_);
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    if (rc == SSB_OK && e != cudaSuccess) {
+      set_error(std::string("bench_kernel: ") + cudaGetErrorString(e));
+      rc = SSB_ECUDA;
+    }
+    float ms = 0;
+    if (rc == SSB_OK) {
+      cudaEventElapsedTime(&ms, ev0_, ev1_);
+      *ms_out = (double)ms / iters;
+      *bytes_out = bytes;
+      timing_.kernel_launches += iters + 3;
+    }
+  }
+  for (int i = 0; i < rows; ++i) seq_free(i);
+  return rc;
+}
+
+int Engine::last_timing(ssb_timing* t) const {
+  *t = timing_;
+  return SSB_OK;
+}
+
+void Engine::timing_reset() { timing_ = ssb_timing{}; }
+
+int Engine::debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols) {
+  if (!taps_) RET(SSB_ESTATE, "engine was not created with params.debug_taps=1");
+  CK(cudaSetDevice(device_));
+  const std::string nm = name ? name : "";
+  const bf16* src = nullptr;
+  int c = 0;
+  if (nm == "q0") {
+    src = tap_q0_;
+    c = Hl_ * cfg_.head_dim;
+  } else if (nm == "attn0") {
+    src = tap_attn0_;
+    c = Hl_ * cfg_.head_dim;
+  } else if (nm == "h0") {
+    src = tap_h0_;
+    c = cfg_.hidden;
+  } else if (nm == "h") {
+    src = h_;
+    c = cfg_.hidden;
+  } else {
+    RET(SSB_EINVAL, "unknown tap '" + nm + "'");
+  }
+  const int64_t need = (int64_t)tap_rows_ * c;
+  *rows = tap_rows_;
+  *cols = c;
+  if (n < need) RET(SSB_EINVAL, "destination too small");
+  float* tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)need * sizeof(float)));
+  cudaError_t e = launch_bf16_to_f32(src, tmp, need, stream_);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, (size_t)need * sizeof(float), cudaMemcpyDeviceToHost, stream_);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+  cudaFree(tmp);
+  if (e != cudaSuccess) RET(SSB_ECUDA, cudaGetErrorString(e));
+  return SSB_OK;
+}
+
+}  // namespace ssb
+
+// ===================================================================================================================
+// C ABI (include/ssb.h)
+// ===================================================================================================================
+using ssb::Engine;
+struct ssb_engine {
+  Engine impl;
+};
+
+extern "C" {
+
+int ssb_engine_create(const char* model_dir, const char* params_json, ssb_engine** out) {
+  if (!model_dir || !out) {
+    ssb::set_error("null argument");
+    return SSB_EINVAL;
+  }
+  *out = nullptr;
+  ssb_engine* e = new (std::nothrow) ssb_engine();
+  if (!e) return SSB_ENOMEM;
+  int rc;
+  try {
+    rc = e->impl.init(model_dir, params_json ? params_json : "{}");
+  } catch (std::exception& ex) {
+    ssb::set_error(std::string("exception: ") + ex.what());
+    rc = SSB_EINVAL;
+  }
+  if (rc != SSB_OK) {
+    std::string keep = ssb::get_error();
+    delete e;
+    ssb::set_error(keep);
+    return rc;
+  }
+  *out = e;
+  return SSB_OK;
+}
+
+void ssb_engine_destroy(ssb_engine* e) { delete e; }
+
+#define GUARD(e)                        \
+  if (!(e)) {                           \
+    ssb::set_error("null engine");      \
+    return SSB_EINVAL;                  \
+  }
+
+int ssb_engine_info(ssb_engine* e, ssb_info* out) {
+  GUARD(e);
+  return out ? e->impl.info(out) : SSB_EINVAL;
+}
+int ssb_seq_create(ssb_engine* e, int* seq_id) {
+  GUARD(e);
+  return seq_id ? e->impl.seq_create(seq_id) : SSB_EINVAL;
+}
+int ssb_seq_free(ssb_engine* e, int seq_id) {
+  GUARD(e);
+  return e->impl.seq_free(seq_id);
+}
+int ssb_seq_len(ssb_engine* e, int seq_id, int* len) {
+  GUARD(e);
+  return len ? e->impl.seq_len(seq_id, len) : SSB_EINVAL;
+}
+int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok,
+                float* logits_opt) {
+  GUARD(e);
+  if (!seq_ids || !tokens || !lens || !next_tok) {
+    ssb::set_error("null argument");
+    return SSB_EINVAL;
+  }
+  try {
+    return e->impl.prefill(seq_ids, tokens, lens, nseq, next_tok, logits_opt);
+  } catch (std::exception& ex) {
+    ssb::set_error(std::string("exception: ") + ex.what());
+    return SSB_ENOMEM;
+  }
+}
+int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok,
+               float* logits_opt) {
+  GUARD(e);
+  if (!seq_ids || !last_tok || !out_tok) {
+    ssb::set_error("null argument");
+    return SSB_EINVAL;
+  }
+  try {
+    return e->impl.decode(seq_ids, last_tok, nseq, nsteps, out_tok, logits_opt);
+  } catch (std::exception& ex) {
+    ssb::set_error(std::string("exception: ") + ex.what());
+    return SSB_ENOMEM;
+  }
+}
+int ssb_last_timing(ssb_engine* e, ssb_timing* out) {
+  GUARD(e);
+  return out ? e->impl.last_timing(out) : SSB_EINVAL;
+}
+int ssb_timing_reset(ssb_engine* e) {
+  GUARD(e);
+  e->impl.timing_reset();
+  return SSB_OK;
+}
+int ssb_tp_handle_size(void) { return 256; }
+int ssb_tp_export(ssb_engine* e, void* handle_out) {
+  GUARD(e);
+  (void)handle_out;
+  ssb::set_error("tensor parallel bootstrap is not available in this build step");
+  return SSB_ESTATE;
+}
+int ssb_tp_connect(ssb_engine* e, const void* all_handles, int n_ranks) {
+  GUARD(e);
+  (void)all_handles;
+  (void)n_ranks;
+  ssb::set_error("tensor parallel bootstrap is not available in this build step");
+  return SSB_ESTATE;
+}
+int ssb_bench_kernel(ssb_engine* e, const char* which, int rows, int ctx, int iters, double* ms_per_launch,
+                     int64_t* algorithmic_bytes) {
+  GUARD(e);
+  if (!ms_per_launch || !algorithmic_bytes) return SSB_EINVAL;
+  return e->impl.bench_kernel(which, rows, ctx, iters, ms_per_launch, algorithmic_bytes);
+}
+int ssb_debug_read(ssb_engine* e, const char* name, float* dst, int64_t dst_elems, int* rows, int* cols) {
+  GUARD(e);
+  if (!dst || !rows || !cols) return SSB_EINVAL;
+  return e->impl.debug_read(name, dst, dst_elems, rows, cols);
+}
+int ssb_synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst) {
+  if (!dst || n < 0) return SSB_EINVAL;
+  synth_fill_host(seed, tid, start, n, amp, base, dst);
+  return SSB_OK;
+}
+const char* ssb_last_error(void) { return ssb::get_error(); }
+const char* ssb_version(void) { return "substratus_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// engine.h — the decode engine behind include/ssb.h (one engine = one GPU rank).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ssb.h"
+#include "json.h"
+#include "kernels.h"
+#include "loader.h"
+
+namespace ssb {
+
+struct ModelCfg {
+  std::string model_type = "llama";
+  int hidden = 0, inter = 0, layers = 0, heads = 0, kv_heads = 0, head_dim = 0, vocab = 0, max_pos = 0;
+  float eps = 1e-5f, theta = 10000.f;
+  bool tie_embeddings = false;
+};
+
+struct LayerW {
+  bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+};
+
+struct SeqSlot {
+  bool used = false;
+  int len = 0;
+  std::vector<int> blocks;
+};
+
+class Engine {
+ public:
+  Engine() = default;
+  ~Engine();
+  int init(const std::string& model_dir, const std::string& params_json);
+  int info(ssb_info* out) const;
+  int seq_create(int* id);
+  int seq_free(int id);
+  int seq_len(int id, int* len) const;
+  int prefill(const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits);
+  int decode(const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float* logits);
+  int last_timing(ssb_timing* t) const;
+  void timing_reset();
+  int debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols);
+  int bench_kernel(const char* which, int rows, int ctx, int iters, double* ms_out, int64_t* bytes_out);
+
+ private:
+  // setup
+  int load_config(const std::string& dir, const Json& params);
+  int alloc_weights();
+  int fill_weights(const std::string& dir, bool synthetic, uint64_t seed);
+  int alloc_runtime(const Json& params);
+  template <typename T>
+  int dmalloc(T** p, size_t n);
+  // run
+  int ensure_blocks(int slot, int new_len);
+  int upload_block_rows(const std::vector<int>& slots);
+  int forward(int M, int n_logit_rows, bool decode_mode);  // enqueue one forward over the staged rows
+  int build_graph(int B);
+  LaunchCfg lc(bool pdl) const { return LaunchCfg{stream_, pdl && use_pdl_, n_sm_}; }
+
+  ModelCfg cfg_;
+  int tp_size_ = 1, tp_rank_ = 0, device_ = 0, n_sm_ = 148;
+  int Hl_ = 0, KVHl_ = 0, Il_ = 0;  // per-rank heads / kv heads / intermediate
+  int max_batch_ = 32, max_seq_ = 4096, block_size_ = 16, n_blocks_ = 0, max_blocks_per_seq_ = 0, m_max_ = 0;
+  bool use_pdl_ = true, use_graph_ = true, taps_ = false;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+
+  // weights
+  std::vector<LayerW> lw_;
+  bf16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr;
+  uint32_t* rope_cs_ = nullptr;
+  // KV pool: per layer [n_blocks][KVHl][block][D]
+  bf16 *kpool_ = nullptr, *vpool_ = nullptr;
+  size_t kv_layer_elems_ = 0;
+  // activations
+  bf16 *h_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr;
+  float *logits_ = nullptr, *part_o_ = nullptr, *part_ml_ = nullptr;
+  int *counters_ = nullptr, *row_tok_ = nullptr, *row_slot_ = nullptr, *row_pos_ = nullptr, *logit_rows_ = nullptr;
+  int *next_tok_ = nullptr, *hist_ = nullptr, *step_ = nullptr, *block_table_ = nullptr;
+  int max_steps_ = 0;
+  // taps
+  bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
+  int tap_rows_ = 0;
+  // host state
+  std::vector<SeqSlot> slots_;
+  std::vector<int> free_blocks_;
+  std::vector<int> host_bt_;
+  std::map<int, cudaGraphExec_t> graphs_;
+  std::vector<void*> allocs_;
+  size_t hbm_bytes_ = 0;
+  int64_t weight_bytes_step_ = 0;
+  int launches_per_forward_ = 0;
+  // stats
+  mutable ssb_timing timing_ = {};
+  int decode_splits_(int M) const;
+};
+
+void set_error(const std::string& s);
+const char* get_error();
+
+}  // namespace ssb

@@ -1,0 +1,646 @@
+// kernels.cu — hand-written sm_100a kernels of the decode loop (small-batch path).
+//
+// Math follows the HF-transformers Llama forward the reference's serving image wraps
+// (HF = site-packages/transformers):
+//   RMSNorm      HF:models/llama/modeling_llama.py:62-67   (fp32 stats, cast to bf16 BEFORE the weight multiply)
+//   q/k/v/o/mlp  HF:models/llama/modeling_llama.py:177-183,238-288 (bf16 Linear, fp32 accumulate, bf16 output)
+//   RoPE         HF:models/llama/modeling_llama.py:124-168 (bf16 cos/sin, half-split pairing (j, j+d/2))
+//   attention    HF:models/llama/modeling_llama.py:199-221 (scores rounded to bf16, * d^-1/2 in bf16, fp32 softmax)
+//   greedy pick  HF:generation/utils.py:2762,2793 (logits.float(), argmax)
+//
+// The dominant kernel is gemv_kernel: y[M<=4, N] = x * W^T with W streamed from HBM exactly once through a
+// TMA-engine (cp.async.bulk) -> shared-memory mbarrier ring, consumed by 8 warps with fp32 FMAs and warp-shuffle
+// reductions; norm prologue and RoPE/KV-append/SwiGLU/residual epilogues are fused.  It is HBM-bound:
+// algorithmic bytes per launch = 2*N*K.
+#include "common.cuh"
+#include "kernels.h"
+#include <cstring>
+
+// =====================================================================================================================
+// gemv_kernel
+// =====================================================================================================================
+constexpr int GV_CW = 8;                        // consumer warps
+constexpr int GV_THREADS = (GV_CW + 1) * 32;    // + 1 producer warp
+constexpr int GV_ROWS = 2 * GV_CW;              // weight rows per stage (each consumer warp owns one row pair)
+constexpr int GV_KC = 1024;                     // K elements per stage
+constexpr int GV_STAGES = 3;                    // 3 x 32 KiB in flight per SM
+constexpr int GV_TILE_BYTES = GV_STAGES * GV_ROWS * GV_KC * 2;
+
+static size_t gemv_smem_bytes(int bt, int K) { return (size_t)GV_TILE_BYTES + (size_t)bt * K * 2 + 2 * GV_STAGES * 8 + 64; }
+
+int gemv_pick_bt(int M, int K) {
+  int bt = M >= 4 ? 4 : (M >= 2 ? 2 : 1);
+  while (bt > 1 && gemv_smem_bytes(bt, K) > 220 * 1024) bt >>= 1;
+  return bt;
+}
+
+template <int BT, int EPI>
+SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, float v1) {
+  // v0/v1: fp32 dot products of physical rows (2*pair, 2*pair+1) for tile row m (global row index)
+  if constexpr (EPI == EPI_F32) {
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = v0;
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = v1;
+  } else if constexpr (EPI == EPI_F32_BF16R) {
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = bf16r(v0);
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = bf16r(v1);
+  } else if constexpr (EPI == EPI_BF16) {
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)m * a.ld_out + 2 * pair) = pack_bf16(v0, v1);
+  } else if constexpr (EPI == EPI_RESID) {
+    size_t o = (size_t)m * a.ld_out + 2 * pair;
+    uint32_t r = *reinterpret_cast<const uint32_t*>(a.resid + o);
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(bf16r(v0) + bf_lo(r), bf16r(v1) + bf_hi(r));
+  } else if constexpr (EPI == EPI_SWIGLU) {
+    float g = bf16r(v0), u = bf16r(v1);
+    float s = bf16r(g / (1.0f + expf(-g)));
+    a.out_bf16[(size_t)m * a.ld_out + pair] = __float2bfloat16_rn(s * u);
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int hd = a.head_dim, half = hd >> 1;
+    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+    const int pos = a.row_pos[m];
+    if (pair < q_pairs + k_pairs) {
+      const bool is_q = pair < q_pairs;
+      const int pp = is_q ? pair : pair - q_pairs;
+      const int head = pp / half, j = pp - head * half;
+      const uint32_t cs = a.rope_cs[(size_t)pos * half + j];
+      const float c = bf_lo(cs), s = bf_hi(cs);
+      const float x0 = bf16r(v0), x1 = bf16r(v1);  // Linear outputs are bf16
+      // (q*cos) + (rotate_half(q)*sin), every op rounded to bf16 like the HF bf16 tensor ops
+      const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
+      const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
+      if (is_q) {
+        bf16* q = a.q_out + (size_t)m * a.q_rows + head * hd + j;
+        q[0] = __float2bfloat16_rn(y0);
+        q[half] = __float2bfloat16_rn(y1);
+      } else {
+        const int slot = a.row_slot[m];
+        const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
+        bf16* k = a.kcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+        k[0] = __float2bfloat16_rn(y0);
+        k[half] = __float2bfloat16_rn(y1);
+      }
+    } else {
+      const int e = 2 * (pair - q_pairs - k_pairs);
+      const int head = e / hd, j = e - head * hd;
+      const int slot = a.row_slot[m];
+      const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
+      bf16* v = a.vcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+      *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
+    }
+  }
+}
+
+template <int BT, int EPI, int NORM>
+__global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  bf16* tiles = reinterpret_cast<bf16*>(smem_raw);            // [STAGES][ROWS][KC]
+  bf16* xs = tiles + GV_STAGES * GV_ROWS * GV_KC;             // [BT][K]
+  uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t)BT * a.K);
+  uint64_t* empty = full + GV_STAGES;
+  float* red = reinterpret_cast<float*>(empty + GV_STAGES);   // [GV_CW]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = a.K;
+  const int P = a.N >> 1;  // row pairs
+  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  const int m0 = blockIdx.y * BT;
+  const int nk = (K + GV_KC - 1) / GV_KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < GV_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], GV_CW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  if (warp == GV_CW) {
+    // ------------------------------------------------------------ producer: weights never depend on the previous
+    // kernel, so the stream from HBM starts before griddepcontrol.wait (PDL prologue overlap).
+    const uint64_t pol = policy_evict_first();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ps = p0; ps < p1; ps += GV_CW) {
+      const int nr = 2 * min(GV_CW, p1 - ps);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int k0 = kc * GV_KC;
+        const int len = min(GV_KC, K - k0);
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stage], (uint32_t)(nr * len * 2));
+        __syncwarp();
+        if (lane < nr)
+          bulk_g2s_hint(tiles + ((size_t)stage * GV_ROWS + lane) * GV_KC, a.W + (size_t)(2 * ps + lane) * K + k0,
+                        (uint32_t)(len * 2), &full[stage], pol);
+        if (++stage == GV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumers
+    pdl_wait();  // activations of the previous kernel are now visible
+    const int ctid = tid;  // 0..255
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const int m = m0 + b;
+      bf16* xrow = xs + (size_t)b * K;
+      if (m >= a.M) {
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) *reinterpret_cast<uint4*>(xrow + k) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const bf16* src = a.x + (size_t)(a.row_map ? a.row_map[m] : m) * a.ldx;
+      if constexpr (NORM == NORM_RMS) {
+        float ss = 0.f;
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) {
+          uint4 v = *reinterpret_cast<const uint4*>(src + k);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float lo = bf_lo(u[i]), hi = bf_hi(u[i]);
+            ss += lo * lo + hi * hi;
+          }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        named_bar_sync(1, GV_CW * 32);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < GV_CW; ++w) tot += red[w];
+        named_bar_sync(1, GV_CW * 32);  // red[] reused by the next tile row
+        const float rstd = rsqrtf(tot / (float)K + a.eps);
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) {
+          uint4 v = *reinterpret_cast<const uint4*>(src + k);
+          uint4 w = ldg128(a.norm_w + k);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // w * bf16(x * rstd): normalised value is cast to bf16 BEFORE the (bf16) weight multiply
+            float lo = bf16r(bf_lo(u[i]) * rstd) * bf_lo(wu[i]);
+            float hi = bf16r(bf_hi(u[i]) * rstd) * bf_hi(wu[i]);
+            o[i] = pack_bf16(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(xrow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8)
+          *reinterpret_cast<uint4*>(xrow + k) = *reinterpret_cast<const uint4*>(src + k);
+      }
+    }
+    named_bar_sync(1, GV_CW * 32);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ps = p0; ps < p1; ps += GV_CW) {
+      const int pair = ps + warp;
+      const bool valid = pair < p1;
+      float acc0[BT], acc1[BT];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc0[b] = acc1[b] = 0.f;
+      for (int kc = 0; kc < nk; ++kc) {
+        const int k0 = kc * GV_KC;
+        const int len = min(GV_KC, K - k0);
+        mbar_wait(&full[stage], phase);
+        if (valid) {
+          const bf16* w0 = tiles + ((size_t)stage * GV_ROWS + 2 * warp) * GV_KC;
+          const bf16* w1 = w0 + GV_KC;
+          for (int c = lane * 8; c < len; c += 256) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(w0 + c);
+            const uint4 a1 = *reinterpret_cast<const uint4*>(w1 + c);
+            const uint32_t u0[4] = {a0.x, a0.y, a0.z, a0.w};
+            const uint32_t u1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + k0 + c);
+              const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
+                acc0[b] = fmaf(bf_lo(u0[i]), xl, acc0[b]);
+                acc0[b] = fmaf(bf_hi(u0[i]), xh, acc0[b]);
+                acc1[b] = fmaf(bf_lo(u1[i]), xl, acc1[b]);
+                acc1[b] = fmaf(bf_hi(u1[i]), xh, acc1[b]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == GV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (valid) {
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          const float s0 = warp_sum(acc0[b]);
+          const float s1 = warp_sum(acc1[b]);
+          if (lane == b) {
+            v0 = s0;
+            v1 = s1;
+          }
+        }
+        if (lane < BT && m0 + lane < a.M) gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
+      }
+    }
+  }
+}
+
+template <typename KernelT, typename... Args>
+static cudaError_t launch_ex(KernelT kernel, dim3 grid, dim3 block, size_t smem, const LaunchCfg& lc, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <int BT, int EPI, int NORM>
+static cudaError_t launch_gemv_t(const GemvArgs& a, const LaunchCfg& lc) {
+  const size_t smem = gemv_smem_bytes(BT, a.K);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int P = a.N / 2;
+  int gx = lc.n_sm < P ? lc.n_sm : P;
+  dim3 grid(gx, (a.M + BT - 1) / BT);
+  return launch_ex(gemv_kernel<BT, EPI, NORM>, grid, dim3(GV_THREADS), smem, lc, a);
+}
+
+template <int EPI, int NORM>
+static cudaError_t launch_gemv_bt(const GemvArgs& a, const LaunchCfg& lc) {
+  switch (gemv_pick_bt(a.M, a.K)) {
+    case 4: return launch_gemv_t<4, EPI, NORM>(a, lc);
+    case 2: return launch_gemv_t<2, EPI, NORM>(a, lc);
+    default: return launch_gemv_t<1, EPI, NORM>(a, lc);
+  }
+}
+
+cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& lc) {
+  if ((a.N & 1) || (a.K & 7)) return cudaErrorInvalidValue;
+  if (norm == NORM_RMS) {
+    switch (epi) {
+      case EPI_QKV_ROPE: return launch_gemv_bt<EPI_QKV_ROPE, NORM_RMS>(a, lc);
+      case EPI_SWIGLU: return launch_gemv_bt<EPI_SWIGLU, NORM_RMS>(a, lc);
+      case EPI_F32_BF16R: return launch_gemv_bt<EPI_F32_BF16R, NORM_RMS>(a, lc);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (epi) {
+    case EPI_RESID: return launch_gemv_bt<EPI_RESID, NORM_NONE>(a, lc);
+    case EPI_F32: return launch_gemv_bt<EPI_F32, NORM_NONE>(a, lc);
+    case EPI_BF16: return launch_gemv_bt<EPI_BF16, NORM_NONE>(a, lc);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// =====================================================================================================================
+// paged-KV decode attention, split over the context, flash-style merge, last-arriving CTA combines the splits
+// =====================================================================================================================
+constexpr int AT_WARPS = 4;
+constexpr int AT_THREADS = AT_WARPS * 32;
+
+template <int D, int G>
+__global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const AttnArgs a) {
+  constexpr int LPR = D / 8;        // lanes per K/V row (16 B each)
+  constexpr int RPW = 32 / LPR;     // rows per warp iteration
+  constexpr int NSUB = AT_WARPS * RPW;
+  __shared__ float sm_m[NSUB][G];
+  __shared__ float sm_l[NSUB][G];
+  __shared__ float sm_o[NSUB][G][D];
+  __shared__ int sm_last;
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int split = blockIdx.x, row = blockIdx.z;
+  const int kvh = blockIdx.y / (a.group / G);   // G = query heads handled by this CTA (all share one KV head)
+  const int head0 = blockIdx.y * G;             // heads are kv-major: head = kvh*group + g
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int slot = a.row_slot[row];
+  const int ctx = a.row_pos[row] + 1;
+  const int BS = a.block_size;
+  int chunk = (ctx + a.n_splits - 1) / a.n_splits;
+  chunk = ((chunk + BS - 1) / BS) * BS;
+  const int n_active = (ctx + chunk - 1) / chunk;
+  if (split >= n_active) return;
+  const int t_begin = split * chunk;
+  const int t_end = min(ctx, t_begin + chunk);
+  const int HD = a.n_heads * D;  // q/out row stride
+
+  float q[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const uint4 v = *reinterpret_cast<const uint4*>(a.q + (size_t)row * HD + (head0 + g) * D + li * 8);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[g][2 * i] = bf_lo(u[i]);
+      q[g][2 * i + 1] = bf_hi(u[i]);
+    }
+  }
+  float m[G], l[G], acc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -1e30f;
+    l[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+  }
+  const int* bt = a.block_table + (size_t)slot * a.bt_stride;
+  for (int t = t_begin + warp * RPW + sub; t < t_end; t += AT_WARPS * RPW) {
+    const int blk = bt[t / BS];
+    const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
+    const uint4 kv = *reinterpret_cast<const uint4*>(a.kcache + off);
+    const uint4 vv = *reinterpret_cast<const uint4*>(a.vcache + off);
+    const uint32_t ku[4] = {kv.x, kv.y, kv.z, kv.w};
+    const uint32_t vu[4] = {vv.x, vv.y, vv.z, vv.w};
+    float kf[8], vf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      kf[2 * i] = bf_lo(ku[i]);
+      kf[2 * i + 1] = bf_hi(ku[i]);
+      vf[2 * i] = bf_lo(vu[i]);
+      vf[2 * i + 1] = bf_hi(vu[i]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      const float s = bf16r(bf16r(d) * a.scale);  // matmul output is bf16, then "* scaling" in bf16
+      const float mn = fmaxf(m[g], s);
+      const float corr = __expf(m[g] - mn);
+      const float p = __expf(s - mn);
+      m[g] = mn;
+      l[g] = l[g] * corr + p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(p, vf[i], acc[g][i] * corr);
+    }
+  }
+  const int sidx = warp * RPW + sub;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (li == 0) {
+      sm_m[sidx][g] = m[g];
+      sm_l[sidx][g] = l[g];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm_o[sidx][g][li * 8 + i] = acc[g][i];
+  }
+  __syncthreads();
+  const size_t pbase = ((size_t)row * gridDim.y + blockIdx.y) * a.n_splits;
+  for (int idx = tid; idx < G * D; idx += AT_THREADS) {
+    const int g = idx / D, dd = idx % D;
+    float mm = -1e30f;
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) mm = fmaxf(mm, sm_m[s][g]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+      const float w = __expf(sm_m[s][g] - mm);
+      ll += sm_l[s][g] * w;
+      oo += sm_o[s][g][dd] * w;
+    }
+    if (n_active == 1) {
+      a.out[(size_t)row * HD + (head0 + g) * D + dd] = __float2bfloat16_rn(oo / ll);
+    } else {
+      a.part_o[(pbase + split) * (G * D) + idx] = oo;
+      if (dd == 0) {
+        a.part_ml[(pbase + split) * (2 * G) + g] = mm;
+        a.part_ml[(pbase + split) * (2 * G) + G + g] = ll;
+      }
+    }
+  }
+  if (n_active == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(&a.counters[row * gridDim.y + blockIdx.y], 1);
+    sm_last = (old == n_active - 1);
+  }
+  __syncthreads();
+  if (!sm_last) return;
+  __threadfence();
+  for (int idx = tid; idx < G * D; idx += AT_THREADS) {
+    const int g = idx / D, dd = idx % D;
+    float mm = -1e30f;
+    for (int s = 0; s < n_active; ++s) mm = fmaxf(mm, __ldcg(&a.part_ml[(pbase + s) * (2 * G) + g]));
+    float ll = 0.f, oo = 0.f;
+    for (int s = 0; s < n_active; ++s) {
+      const float w = __expf(__ldcg(&a.part_ml[(pbase + s) * (2 * G) + g]) - mm);
+      ll += __ldcg(&a.part_ml[(pbase + s) * (2 * G) + G + g]) * w;
+      oo += __ldcg(&a.part_o[(pbase + s) * (G * D) + idx]) * w;
+    }
+    a.out[(size_t)row * HD + (head0 + g) * D + dd] = __float2bfloat16_rn(oo / ll);
+  }
+  if (tid == 0) a.counters[row * gridDim.y + blockIdx.y] = 0;
+}
+
+template <int D, int G>
+static cudaError_t launch_attn_t(const AttnArgs& a, const LaunchCfg& lc) {
+  dim3 grid(a.n_splits, a.kvh * (a.group / G), a.M);
+  return launch_ex(attn_decode_kernel<D, G>, grid, dim3(AT_THREADS), 0, lc, a);
+}
+
+cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc) {
+  const int gc = (a.group % 8 == 0) ? 8 : (a.group % 4 == 0) ? 4 : (a.group % 2 == 0) ? 2 : 1;
+  if (a.head_dim == 128) {
+    switch (gc) {
+      case 1: return launch_attn_t<128, 1>(a, lc);
+      case 2: return launch_attn_t<128, 2>(a, lc);
+      case 4: return launch_attn_t<128, 4>(a, lc);
+      case 8: return launch_attn_t<128, 8>(a, lc);
+    }
+  } else if (a.head_dim == 64) {
+    switch (gc) {
+      case 1: return launch_attn_t<64, 1>(a, lc);
+      case 2: return launch_attn_t<64, 2>(a, lc);
+      case 4: return launch_attn_t<64, 4>(a, lc);
+      case 8: return launch_attn_t<64, 8>(a, lc);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+// =====================================================================================================================
+// embedding gather, greedy argmax
+// =====================================================================================================================
+__global__ void __launch_bounds__(128) embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ row_tok,
+                                                    bf16* __restrict__ h, int hidden, int* step_counter) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int m = blockIdx.x;
+  if (m == 0 && threadIdx.x == 0 && step_counter) *step_counter += 1;
+  const bf16* src = embed + (size_t)row_tok[m] * hidden;
+  bf16* dst = h + (size_t)m * hidden;
+  for (int k = threadIdx.x * 8; k < hidden; k += 128 * 8)
+    *reinterpret_cast<uint4*>(dst + k) = *reinterpret_cast<const uint4*>(src + k);
+}
+
+cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
+                         const LaunchCfg& lc) {
+  return launch_ex(embed_kernel, dim3(M), dim3(128), 0, lc, embed, row_tok, h, hidden, step_counter);
+}
+
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int n_rows,
+                                                      int* __restrict__ tok_out, int* __restrict__ hist,
+                                                      const int* __restrict__ step, int* __restrict__ pos_inc) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int r = blockIdx.x;
+  const float* lg = logits + (size_t)r * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += 1024) {
+    const float v = lg[i];
+    if (v > best || (v == best && i < bi)) {
+      best = v;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (threadIdx.x == 0) {
+      tok_out[r] = bi;
+      if (hist) hist[(size_t)(*step) * n_rows + r] = bi;
+      if (pos_inc) pos_inc[r] += 1;
+    }
+  }
+}
+
+cudaError_t launch_argmax(const float* logits, int V, int n_rows, int* tok_out, int* hist, const int* step,
+                          int* pos_inc, const LaunchCfg& lc) {
+  return launch_ex(argmax_kernel, dim3(n_rows), dim3(1024), 0, lc, logits, V, n_rows, tok_out, hist, step, pos_inc);
+}
+
+// =====================================================================================================================
+// load-time kernels: row gather + dtype convert, synthetic weights
+// =====================================================================================================================
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+
+template <typename T>
+__global__ void gather_rows_kernel(bf16* __restrict__ dst, int64_t dst_ld, const T* __restrict__ src, int64_t src_ld,
+                                   const int* __restrict__ row_idx, int rows, int col0, int cols) {
+  const int r = blockIdx.y;
+  const int64_t sr = row_idx ? row_idx[r] : r;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+    dst[(size_t)r * dst_ld + c] = __float2bfloat16_rn(to_f32<T>(src[sr * src_ld + col0 + c]));
+}
+
+cudaError_t launch_gather_rows(bf16* dst, int64_t dst_ld, const void* src, int src_dtype, int64_t src_ld,
+                               const int* row_idx, int rows, int col0, int cols, cudaStream_t s) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  dim3 grid((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256, rows);
+  if (src_dtype == 0)
+    gather_rows_kernel<bf16><<<grid, 256, 0, s>>>(dst, dst_ld, (const bf16*)src, src_ld, row_idx, rows, col0, cols);
+  else if (src_dtype == 1)
+    gather_rows_kernel<__half><<<grid, 256, 0, s>>>(dst, dst_ld, (const __half*)src, src_ld, row_idx, rows, col0, cols);
+  else if (src_dtype == 2)
+    gather_rows_kernel<float><<<grid, 256, 0, s>>>(dst, dst_ld, (const float*)src, src_ld, row_idx, rows, col0, cols);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// twin of oracle/synth.py::synth_f32 + f32_to_bf16_bits (bit-exact; no FMA contraction)
+__host__ __device__ inline uint16_t synth_value(uint64_t seed, uint32_t tid, uint64_t idx, float amp, float base) {
+  uint64_t z = idx + (uint64_t)tid * 0x9E3779B97F4A7C15ull + seed * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const float u = ((float)(uint32_t)(z >> 41) - 4194304.0f + 0.5f) * 2.384185791015625e-07f;  // 2^-22
+#ifdef __CUDA_ARCH__
+  const float v = __fadd_rn(base, __fmul_rn(u, amp));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+#else
+  volatile float prod = u * amp;
+  volatile float v = base + prod;
+  uint32_t b;
+  float vv = v;
+  memcpy(&b, &vv, 4);
+  const uint32_t rnd = ((b >> 16) & 1u) + 0x7FFFu;
+  return (uint16_t)((b + rnd) >> 16);
+#endif
+}
+
+__global__ void synth_fill_kernel(bf16* __restrict__ dst, int64_t dst_ld, const int* __restrict__ row_idx, int rows, int col0, int cols,
+                                  int64_t full_cols, uint64_t seed, uint32_t tid, float amp, float base) {
+  const int r = blockIdx.y;
+  const int64_t lr = row_idx ? row_idx[r] : r;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+    dst[(size_t)r * dst_ld + c] = __ushort_as_bfloat16(synth_value(seed, tid, (uint64_t)(lr * full_cols + col0 + c), amp, base));
+}
+
+cudaError_t launch_synth_fill(bf16* dst, int64_t dst_ld, const int* row_idx, int rows, int col0, int cols, int64_t full_cols,
+                              uint64_t seed, uint32_t tid, float amp, float base, cudaStream_t s) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  dim3 grid((cols + 255) / 256 > 64 ? 64 : (cols + 255) / 256, rows);
+  synth_fill_kernel<<<grid, 256, 0, s>>>(dst, dst_ld, row_idx, rows, col0, cols, full_cols, seed, tid, amp, base);
+  return cudaGetLastError();
+}
+
+void synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst) {
+  for (int64_t i = 0; i < n; ++i) dst[i] = synth_value(seed, tid, (uint64_t)(start + i), amp, base);
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+cudaError_t launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  bf16_to_f32_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}

@@ -1,0 +1,91 @@
+// kernels.h — host-visible launch API of the sm_100a decode kernels (plain structs, no torch).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+enum GemvEpi : int {
+  EPI_F32 = 0,       // out_f32[m][n] = acc                      (TP partial sums, raw fp32)
+  EPI_F32_BF16R = 1, // out_f32[m][n] = float(bf16(acc))          (lm_head logits: HF Linear output is bf16, then .float())
+  EPI_RESID = 2,     // out_bf16[m][n] = bf16(float(bf16(acc)) + resid[m][n])   (o_proj / down_proj + residual)
+  EPI_SWIGLU = 3,    // rows (2i,2i+1) = (gate_i, up_i): out_bf16[m][i] = bf16(bf16(silu(bf16 g)) * bf16 u)
+  EPI_QKV_ROPE = 4,  // pair-interleaved q|k|v rows: RoPE on q,k; q -> q_out, k/v -> paged KV cache at (slot,pos)
+  EPI_BF16 = 5,      // out_bf16[m][n] = bf16(acc + bias)
+};
+
+enum NormKind : int { NORM_NONE = 0, NORM_RMS = 1 };
+
+struct GemvArgs {
+  // y[M, N] = x[M, K] * W[N, K]^T ; W bf16 row-major (physical row order, see DESIGN.md "weight layout")
+  const bf16* W;
+  int N, K;
+  const bf16* x;  // [*, ldx]
+  int ldx, M;
+  const int* row_map;  // optional: tile row m reads x row row_map[m]
+  const bf16* norm_w;  // NORM_RMS: weight[K]
+  float eps;
+  // outputs
+  float* out_f32;
+  bf16* out_bf16;
+  const bf16* resid;
+  int ld_out;
+  // EPI_QKV_ROPE
+  bf16* q_out;       // [M, q_rows]
+  int q_rows;        // H_local * head_dim
+  int kv_rows;       // KVH_local * head_dim
+  int head_dim;
+  bf16* kcache;      // this layer: [blocks][KVH_local][block_size][head_dim]
+  bf16* vcache;
+  const int* block_table;  // [slots][bt_stride]
+  int bt_stride;
+  const int* row_slot;     // [M]
+  const int* row_pos;      // [M]
+  const uint32_t* rope_cs; // [max_pos][head_dim/2] packed (cos bf16 | sin bf16 << 16)
+  int block_size;
+  int kvh;                 // KVH_local
+};
+
+struct AttnArgs {
+  const bf16* q;  // [M, H_local*D]
+  const bf16* kcache;
+  const bf16* vcache;
+  const int* block_table;
+  int bt_stride;
+  const int* row_slot;
+  const int* row_pos;
+  bf16* out;  // [M, H_local*D]
+  float* part_o;  // [M][H_local/GC][n_splits][GC*D]   (GC = heads per CTA)
+  float* part_ml; // [M][H_local/GC][n_splits][2*GC]
+  int* counters;  // [M][H_local/GC], zero on entry, zero on exit
+  int M, n_heads, kvh, group, head_dim, block_size, n_splits;
+  float scale;
+};
+
+struct LaunchCfg {
+  cudaStream_t stream;
+  bool pdl;
+  int n_sm;
+};
+
+cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& lc);
+int gemv_pick_bt(int M, int K);
+cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc);
+// h[m][:] = embed[row_tok[m]][:]; thread 0 of block 0 also does (*step_counter)++ when non-null
+cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
+                         const LaunchCfg& lc);
+// greedy pick per row (lowest index wins ties, as torch.argmax on CPU): tok_out[r] = argmax logits[r][:]
+// hist != null: hist[(*step) * n_rows + r] = tok ; pos_inc != null: pos_inc[r] += 1
+cudaError_t launch_argmax(const float* logits, int V, int n_rows, int* tok_out, int* hist, const int* step,
+                          int* pos_inc, const LaunchCfg& lc);
+
+// ---- load-time kernels
+// dst[r*dst_ld + c] = bf16(src[row_idx[r]][col0 + c]), src element type: 0 bf16, 1 f16, 2 f32
+cudaError_t launch_gather_rows(bf16* dst, int64_t dst_ld, const void* src, int src_dtype, int64_t src_ld,
+                               const int* row_idx, int rows, int col0, int cols, cudaStream_t s);
+// dst[r*dst_ld + c] = synth(seed, tid, row_idx[r]*full_cols + col0 + c)  (row_idx null => identity)
+cudaError_t launch_synth_fill(bf16* dst, int64_t dst_ld, const int* row_idx, int rows, int col0, int cols, int64_t full_cols,
+                              uint64_t seed, uint32_t tid, float amp, float base, cudaStream_t s);
+void synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst);
+cudaError_t launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s);
