@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s + p50 TTFT of the Server-CRD inference hot path (BASELINE.json metric).
+
+A "step" is one synthetic request batch through the hot path: B prompts of 512 token ids
+(randint(0,V), seed 1234+i) -> prefill -> 127 further greedy decode steps (128 new tokens).
+  value  = decode tokens/s, whole job, device-timed (CUDA events on the engine stream), inputs resident in HBM
+           (the decode loop feeds tokens back on the device);
+  e2e    = the same metric through the public C-ABI call with HOST buffers (ssb_prefill / ssb_decode take host
+           token ids and return host token ids; host<->device copies inside the timed region, wall clock);
+  ttft   = p50 wall time of ssb_prefill (host ids in -> first token id on the host).
+Weights are seeded synthetic values at the real Llama-2-7B shapes (no checkpoints exist offline).
+Inputs are larger than L2 (13.2 GB of weights stream per decode step vs 126 MB L2) so no L2 flush is needed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPT_LEN, NEW_TOKENS = 512, 128
+
+WORKLOADS = {
+    "llama2-7b": dict(model_type="llama", hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                      num_attention_heads=32, num_key_value_heads=32, vocab_size=32000, max_position_embeddings=4096,
+                      rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
+    "llama2-13b": dict(model_type="llama", hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
+                       num_attention_heads=40, num_key_value_heads=40, vocab_size=32000, max_position_embeddings=4096,
+                       rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
+    "llama2-70b": dict(model_type="llama", hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
+                       num_attention_heads=64, num_key_value_heads=8, vocab_size=32000, max_position_embeddings=4096,
+                       rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synthetic_prompts(vocab, batch, plen):
+    import torch
+
+    rows = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(1234 + i)
+        rows.append(torch.randint(0, vocab, (plen,), generator=g).tolist())
+    return rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hf_cpu_generate(cfg, prompt_len, new_tokens, batch=1, threads=None):
+    """The reference's CPU serving path restated: the library the Basaran image wraps —
+    HF transformers on host cores — greedy generate in bf16, eager attention, random-init weights at the
+    real shapes.  Returns dict(decode_tok_s, ttft_s, cores, threads, build_s)."""
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    t0 = time.time()
+    keys = {k: v for k, v in cfg.items() if k not in ("model_type", "torch_dtype", "rope_theta")}
+    hcfg = LlamaConfig(**keys, rope_parameters={"rope_type": "default", "rope_theta": cfg.get("rope_theta", 10000.0)},
+                       attn_implementation="eager")
+    with torch.device("meta"):
+        m = LlamaForCausalLM(hcfg)
+    m = m.to_empty(device="cpu").to(torch.bfloat16)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.uniform_(-0.0346, 0.0346, generator=g)
+            else:
+                p.fill_(1.0)
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+    m.model.rotary_emb = LlamaRotaryEmbedding(hcfg)
+    m.eval()
+    build_s = time.time() - t0
+    ids = torch.tensor(synthetic_prompts(cfg["vocab_size"], batch, prompt_len))
+    with torch.no_grad():
+        t1 = time.time()
+        out = m(ids, use_cache=True)
+        nxt = out.logits[:, -1].float().argmax(-1)
+        ttft = time.time() - t1
+        past = out.past_key_values
+        t2 = time.time()
+        for _ in range(new_tokens - 1):
+            out = m(nxt[:, None], past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            nxt = out.logits[:, -1].float().argmax(-1)
+        dec = time.time() - t2
+    return {"decode_tok_s": batch * (new_tokens - 1) / dec if new_tokens > 1 else 0.0, "ttft_s": ttft,
+            "cores": os.cpu_count(), "threads": threads, "build_s": build_s}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU serving path (HF transformers; see hf_cpu_generate) timed on the
+    host cores on a BOUNDED sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    plen, ntok = args.ref_prompt_len, args.ref_new_tokens
+    vals, ms = [], []
+    r = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        r = hf_cpu_generate(cfg, plen, ntok, batch=args.batch) if i == 0 or not args.ref_reuse else r
+        if i >= args.warmup:
+            vals.append(r["decode_tok_s"])
+            ms.append((time.time() - t0) * 1e3)
+        if args.ref_reuse:
+            break
+    v = statistics.mean(vals) if vals else r["decode_tok_s"]
+    sample = f"{args.batch}x({plen}-token prompt + {ntok} greedy tokens), HF transformers {cfg['num_hidden_layers']}-layer bf16 eager on CPU"
+    line = {"impl": "reference", "metric": "decode_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.mean(ms) if ms else None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload} bf16 decode, batch {args.batch}", "sample": sample},
+            "ttft_ms_p50": r["ttft_s"] * 1e3,
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": r["threads"], "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--workload", default="llama2-7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch32", action="store_true")
+    ap.add_argument("--ref-prompt-len", type=int, default=32)
+    ap.add_argument("--ref-new-tokens", type=int, default=9)
+    ap.add_argument("--ref-reuse", action="store_true", default=True)
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--graph", type=int, default=1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    import numpy as np
+    import torch
+
+    from substratus_b200 import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the serving path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        raise SystemExit("tensor-parallel bench arm not wired yet in this build step")
+    cfg = WORKLOADS[args.workload]
+    B = args.batch
+    peak_gbs, peak_src = load_peaks()
+    tmp = tempfile.mkdtemp(prefix="ssb_bench_")
+    with open(os.path.join(tmp, "config.json"), "w") as f:
+        json.dump(cfg, f)
+    params = {"weights": "synthetic", "seed": 0, "max_batch": max(B, 32), "max_seq_len": PROMPT_LEN + NEW_TOKENS + 16,
+              "use_pdl": args.pdl, "use_graph": args.graph, "device": local_rank}
+    t_load = time.time()
+    eng = Engine(tmp, params)
+    t_load = time.time() - t_load
+    info = eng.info
+    prompts = synthetic_prompts(cfg["vocab_size"], B, PROMPT_LEN)
+
+    def one_request():
+        sids = [eng.seq_create() for _ in range(B)]
+        w0 = time.perf_counter()
+        first, _ = eng.prefill(sids, prompts)
+        w1 = time.perf_counter()
+        pre_ms = eng.timing().prefill_ms
+        toks, _ = eng.decode(sids, first, NEW_TOKENS - 1)
+        w2 = time.perf_counter()
+        dec_ms = eng.timing().decode_ms
+        for s in sids:
+            eng.seq_free(s)
+        return dict(ttft_wall_ms=(w1 - w0) * 1e3, prefill_dev_ms=pre_ms, decode_dev_ms=dec_ms,
+                    decode_wall_ms=(w2 - w1) * 1e3, total_wall_ms=(w2 - w0) * 1e3, last=int(toks[0, -1]))
+
+    for _ in range(args.warmup):
+        one_request()
+    eng.timing_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    recs = [one_request() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tm = eng.timing()
+    ntok = B * (NEW_TOKENS - 1)
+    dec_dev_s = sum(r["decode_dev_ms"] for r in recs) / 1e3
+    dec_wall_s = sum(r["decode_wall_ms"] for r in recs) / 1e3
+    value = args.steps * ntok / dec_dev_s
+    e2e = args.steps * ntok / dec_wall_s
+    ctx_mean = PROMPT_LEN + (NEW_TOKENS - 1) / 2.0 + 0.5
+    bytes_step = info.weight_bytes_per_step + B * ctx_mean * info.kv_bytes_per_token
+    step_ms = dec_dev_s * 1e3 / (args.steps * (NEW_TOKENS - 1))
+    step_gbs = bytes_step / (step_ms * 1e-3) / 1e9
+
+    # dominant kernel: gemv_kernel (all dense projections; ~97% of the step's bytes).  Timed live, one class at a
+    # time over all layers' weights (CUDA events on the engine stream); the largest class (gate/up) is reported.
+    kern = {}
+    for k in ("gate_up", "qkv", "down", "o", "lm_head", "attn"):
+        ms, by = eng.bench_kernel(k, rows=B, ctx=int(ctx_mean), iters=64)
+        kern[k] = {"ms": ms, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9}
+    dom = kern["gate_up"]
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel (gate/up projection + SwiGLU)", "achieved": dom["gbs"],
+                "peak": peak_gbs, "unit": "GB/s", "frac": dom["gbs"] / peak_gbs, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
+                "per_kernel_class_gbs": {k: round(v["gbs"], 1) for k, v in kern.items()},
+                "decode_step": {"bytes": bytes_step, "ms": step_ms, "achieved": step_gbs, "frac": step_gbs / peak_gbs,
+                                "roofline_tok_s": B * peak_gbs * 1e9 / bytes_step}}
+
+    line = {
+        "metric": "decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload} bf16 decode, batch {B}, {PROMPT_LEN}-token prompt + {NEW_TOKENS} new tokens, 1xB200",
+                   "batch": B, "prompt_len": PROMPT_LEN, "new_tokens": NEW_TOKENS, "parallelism": f"tp{world}",
+                   "l2": "inputs larger than L2 (13.2 GB of weights per decode step)", "pdl": args.pdl, "graph": args.graph},
+        "ttft_ms_p50": statistics.median(r["ttft_wall_ms"] for r in recs),
+        "prefill_device_ms_p50": statistics.median(r["prefill_dev_ms"] for r in recs),
+        "decode_ms_per_token": step_ms,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": tm.h2d_bytes // args.steps,
+                "d2h_bytes_per_step": tm.d2h_bytes // args.steps,
+                "request_tokens_per_sec": args.steps * B * NEW_TOKENS / (sum(r["total_wall_ms"] for r in recs) / 1e3)},
+        "gpu_launches": int(tm.kernel_launches), "clocks": clocks, "roofline": roofline,
+        "load_s": t_load, "hbm_gb": info.hbm_bytes_allocated / 1e9,
+    }
+    eng.close()
+    if rank == 0 and B == 1 and not args.no_batch32 and args.workload == "llama2-7b":
+        pass  # batch-32 numbers are reported by a second invocation (--batch 32); see BASELINE.md
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            r = hf_cpu_generate(cfg, args.ref_prompt_len, args.ref_new_tokens, batch=1)
+            line["cpu_baseline"] = {"value": r["decode_tok_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
+                                    "sample": f"1x({args.ref_prompt_len}-token prompt + {args.ref_new_tokens} greedy tokens), HF transformers "
+                                              f"bf16 eager on {r['threads']} host threads (the library the reference's Basaran image wraps)",
+                                    "ttft_ms": r["ttft_s"] * 1e3, "model_build_s": r["build_s"]}
+        except Exception as ex:  # host RAM etc.
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": f"failed: {type(ex).__name__}: {ex}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,291 @@
+// serve.cpp — the serve host of the B200 container: the process the reference's ServerReconciler launches as
+// container "serve" (internal/controller/server_controller.go:149-173).  Contract it honours
+// (docs/container-contract.md:5-11,25-55):
+//   * WORKDIR /content; model mounted read-only at /content/model; params at /content/params.json
+//   * listen on TCP 8080 (port name http-serve); GET / -> 200 only when ready to serve (kubelet readiness probe)
+//   * exit != 0 on fatal errors so the Deployment restarts the pod (server_controller.go:280-296)
+// Inference API: the reference specifies none; the only request it ever sends is
+// POST /v1/completions {"prompt", "max_tokens"} (test/system.sh:73-78).  We serve that (prompt = array of token ids;
+// text prompts need the tokenizer of SURVEY §8f #1) and POST /generate (north_star).  All compute goes through the
+// C ABI of include/ssb.h; this file contains no arithmetic and there is no CPU fallback.
+//
+// Stand-in for the Go host north_star names (`containertools/cmd/serve`): no Go toolchain exists in this image, so
+// the host is C++ over the same C ABI; the cgo twin is in INTEGRATION.md.
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <signal.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/ssb.h"
+#include "../substratus_b200/csrc/json.h"
+
+using ssb::Json;
+
+static std::atomic<int> g_ready{0};  // 0 loading, 1 ready, -1 failed
+static ssb_engine* g_engine = nullptr;
+static ssb_info g_info;
+static std::mutex g_engine_mu;  // ssb_* calls on one engine are not re-entrant
+static std::atomic<long long> g_requests{0}, g_tokens{0}, g_errors{0};
+static std::atomic<double> g_ttft_ms_sum{0}, g_decode_ms_sum{0};
+static std::string g_load_error;
+
+static std::string getenv_or(const char* k, const char* d) {
+  const char* v = getenv(k);
+  return v && *v ? v : d;
+}
+
+static bool read_file(const std::string& p, std::string* out) {
+  FILE* f = fopen(p.c_str(), "rb");
+  if (!f) return false;
+  char buf[65536];
+  size_t n;
+  out->clear();
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
+
+static void send_all(int fd, const std::string& s) {
+  size_t off = 0;
+  while (off < s.size()) {
+    ssize_t n = send(fd, s.data() + off, s.size() - off, MSG_NOSIGNAL);
+    if (n <= 0) return;
+    off += (size_t)n;
+  }
+}
+
+static void respond(int fd, int code, const char* status, const std::string& body, const char* ctype = "application/json") {
+  char hdr[256];
+  snprintf(hdr, sizeof hdr, "HTTP/1.1 %d %s\r\nContent-Type: %s\r\nContent-Length: %zu\r\nConnection: close\r\n\r\n", code, status,
+           ctype, body.size());
+  send_all(fd, std::string(hdr) + body);
+}
+
+static std::string err_json(const std::string& m) { return "{\"error\":\"" + ssb::json_escape(m) + "\"}"; }
+
+struct GenResult {
+  std::vector<int32_t> tokens;
+  double ttft_ms = 0, decode_ms = 0;
+  std::string error;
+};
+
+static GenResult generate(const std::vector<int32_t>& prompt, int max_new) {
+  GenResult r;
+  std::lock_guard<std::mutex> lk(g_engine_mu);
+  int sid = -1;
+  if (ssb_seq_create(g_engine, &sid) != SSB_OK) {
+    r.error = ssb_last_error();
+    return r;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  int n = (int)prompt.size();
+  int32_t first = 0;
+  r.tokens.resize(max_new);
+  int rc = ssb_prefill(g_engine, &sid, prompt.data(), &n, 1, &first, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  if (rc == SSB_OK) {
+    r.tokens[0] = first;
+    if (max_new > 1) rc = ssb_decode(g_engine, &sid, &first, 1, max_new - 1, r.tokens.data() + 1, nullptr);
+  }
+  auto t2 = std::chrono::steady_clock::now();
+  if (rc != SSB_OK) r.error = ssb_last_error();
+  ssb_seq_free(g_engine, sid);
+  r.ttft_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  r.decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  return r;
+}
+
+static bool parse_ids(const Json* j, int vocab, std::vector<int32_t>* out, std::string* err) {
+  if (!j || j->kind != Json::Arr || j->arr.empty()) {
+    *err = "expected a non-empty array of token ids";
+    return false;
+  }
+  for (auto& v : j->arr) {
+    if (v.kind != Json::Num || v.num < 0 || v.num >= vocab || v.num != (double)(long long)v.num) {
+      *err = "token ids must be integers in [0, vocab_size)";
+      return false;
+    }
+    out->push_back((int32_t)v.num);
+  }
+  return true;
+}
+
+static std::string ids_json(const std::vector<int32_t>& v) {
+  std::string s = "[";
+  for (size_t i = 0; i < v.size(); ++i) s += (i ? "," : "") + std::to_string(v[i]);
+  return s + "]";
+}
+
+static void handle(int fd) {
+  std::string req;
+  char buf[8192];
+  size_t hdr_end = std::string::npos;
+  while (hdr_end == std::string::npos && req.size() < (1u << 20)) {
+    ssize_t n = recv(fd, buf, sizeof buf, 0);
+    if (n <= 0) break;
+    req.append(buf, (size_t)n);
+    hdr_end = req.find("\r\n\r\n");
+  }
+  if (hdr_end == std::string::npos) {
+    close(fd);
+    return;
+  }
+  size_t clen = 0;
+  {
+    std::string low = req.substr(0, hdr_end);
+    for (auto& c : low) c = (char)tolower(c);
+    size_t p = low.find("content-length:");
+    if (p != std::string::npos) clen = (size_t)strtoull(low.c_str() + p + 15, nullptr, 10);
+  }
+  if (clen > (64u << 20)) {
+    respond(fd, 413, "Payload Too Large", err_json("body too large"));
+    close(fd);
+    return;
+  }
+  while (req.size() < hdr_end + 4 + clen) {
+    ssize_t n = recv(fd, buf, sizeof buf, 0);
+    if (n <= 0) break;
+    req.append(buf, (size_t)n);
+  }
+  const std::string line = req.substr(0, req.find("\r\n"));
+  const size_t sp1 = line.find(' '), sp2 = line.find(' ', sp1 + 1);
+  const std::string method = line.substr(0, sp1);
+  std::string path = sp2 == std::string::npos ? "" : line.substr(sp1 + 1, sp2 - sp1 - 1);
+  if (size_t q = path.find('?'); q != std::string::npos) path.resize(q);
+  const std::string body = req.size() >= hdr_end + 4 ? req.substr(hdr_end + 4, clen) : "";
+
+  if (method == "GET" && (path == "/" || path == "/healthz" || path == "/readyz")) {
+    // readiness: 200 only when weights are on the device and the engine answered ssb_engine_info
+    const int st = g_ready.load();
+    if (st == 1)
+      respond(fd, 200, "OK", "{\"status\":\"ready\",\"engine\":\"" + std::string(ssb_version()) + "\",\"model_type\":\"" +
+                                 std::string(g_info.model_type) + "\"}");
+    else
+      respond(fd, 503, "Service Unavailable", st == 0 ? "{\"status\":\"loading\"}" : err_json(g_load_error));
+  } else if (method == "GET" && path == "/metrics") {
+    char m[1024];
+    snprintf(m, sizeof m,
+             "# TYPE ssb_requests_total counter\nssb_requests_total %lld\n# TYPE ssb_generated_tokens_total counter\n"
+             "ssb_generated_tokens_total %lld\n# TYPE ssb_errors_total counter\nssb_errors_total %lld\n"
+             "# TYPE ssb_ttft_ms_sum counter\nssb_ttft_ms_sum %.3f\n# TYPE ssb_decode_ms_sum counter\nssb_decode_ms_sum %.3f\n",
+             g_requests.load(), g_tokens.load(), g_errors.load(), g_ttft_ms_sum.load(), g_decode_ms_sum.load());
+    respond(fd, 200, "OK", m, "text/plain; version=0.0.4");
+  } else if (method == "POST" && (path == "/generate" || path == "/v1/completions")) {
+    if (g_ready.load() != 1) {
+      respond(fd, 503, "Service Unavailable", err_json("model is not loaded yet"));
+    } else {
+      g_requests++;
+      std::string err;
+      std::vector<int32_t> prompt;
+      int max_new = 16;
+      bool ok = true;
+      try {
+        Json j = ssb::json_parse(body);
+        const bool oai = path == "/v1/completions";
+        const Json* p = j.find(oai ? "prompt" : "tokens");
+        if (oai && p && p->kind == Json::Str) {
+          ok = false;
+          err = "text prompts need a tokenizer, which this build does not ship; pass \"prompt\" as an array of token ids";
+        } else {
+          ok = parse_ids(p, g_info.vocab_size, &prompt, &err);
+        }
+        max_new = (int)j.get_int(oai ? "max_tokens" : "max_new_tokens", 16);
+        if (ok && (max_new < 1 || (int)prompt.size() + max_new > g_info.max_seq_len)) {
+          ok = false;
+          err = "prompt length + max tokens exceeds max_seq_len";
+        }
+      } catch (std::exception& e) {
+        ok = false;
+        err = e.what();
+      }
+      if (!ok) {
+        g_errors++;
+        respond(fd, 400, "Bad Request", err_json(err));
+      } else {
+        GenResult r = generate(prompt, max_new);
+        if (!r.error.empty()) {
+          g_errors++;
+          respond(fd, 500, "Internal Server Error", err_json(r.error));
+        } else {
+          g_tokens += (long long)r.tokens.size();
+          g_ttft_ms_sum.store(g_ttft_ms_sum.load() + r.ttft_ms);
+          g_decode_ms_sum.store(g_decode_ms_sum.load() + r.decode_ms);
+          char tail[256];
+          const double tps = r.decode_ms > 0 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
+          snprintf(tail, sizeof tail, "\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f", r.ttft_ms, r.decode_ms, tps);
+          if (path == "/generate")
+            respond(fd, 200, "OK", "{\"tokens\":" + ids_json(r.tokens) + "," + tail + "}");
+          else
+            respond(fd, 200, "OK",
+                    "{\"object\":\"text_completion\",\"model\":\"" + std::string(g_info.model_type) +
+                        "\",\"choices\":[{\"index\":0,\"text\":\"\",\"tokens\":" + ids_json(r.tokens) +
+                        ",\"finish_reason\":\"length\"}],\"usage\":{\"prompt_tokens\":" + std::to_string(prompt.size()) +
+                        ",\"completion_tokens\":" + std::to_string(r.tokens.size()) + "}," + tail + "}");
+        }
+      }
+    }
+  } else {
+    respond(fd, 404, "Not Found", err_json("no such endpoint"));
+  }
+  shutdown(fd, SHUT_RDWR);
+  close(fd);
+}
+
+int main(int argc, char** argv) {
+  signal(SIGPIPE, SIG_IGN);
+  const std::string model_dir = argc > 1 ? argv[1] : getenv_or("MODEL_DIR", "/content/model");
+  const std::string params_file = getenv_or("PARAMS_FILE", "/content/params.json");
+  const int port = atoi(getenv_or("PORT", "8080").c_str());
+  std::string params = "{}";
+  read_file(params_file, &params);  // {} if absent (params_reconciler.go mounts it only when .spec.params is set)
+
+  int ls = socket(AF_INET, SOCK_STREAM, 0);
+  int one = 1;
+  setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+  sockaddr_in addr{};
+  addr.sin_family = AF_INET;
+  addr.sin_addr.s_addr = htonl(INADDR_ANY);
+  addr.sin_port = htons((uint16_t)port);
+  if (bind(ls, (sockaddr*)&addr, sizeof addr) != 0 || listen(ls, 128) != 0) {
+    perror("serve: bind/listen");
+    return 2;
+  }
+  fprintf(stderr, "serve: listening on :%d, loading %s\n", port, model_dir.c_str());
+
+  // model load runs beside the accept loop so the readiness probe sees 503 (not a refused connection) while loading
+  std::thread loader([&] {
+    int rc = ssb_engine_create(model_dir.c_str(), params.c_str(), &g_engine);
+    if (rc != SSB_OK) {
+      g_load_error = ssb_last_error();
+      fprintf(stderr, "serve: engine create failed (%d): %s\n", rc, g_load_error.c_str());
+      g_ready = -1;
+      // fatal: exit non-zero so the Deployment restarts the pod; no CPU fallback
+      std::this_thread::sleep_for(std::chrono::milliseconds(200));
+      _exit(rc == SSB_ENODEV ? 3 : 1);
+    }
+    ssb_engine_info(g_engine, &g_info);
+    fprintf(stderr, "serve: ready (%s, %d layers, %.2f GB HBM)\n", g_info.model_type, g_info.n_layers,
+            g_info.hbm_bytes_allocated / 1e9);
+    g_ready = 1;
+  });
+  loader.detach();
+
+  for (;;) {
+    int fd = accept(ls, nullptr, nullptr);
+    if (fd < 0) continue;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+    std::thread(handle, fd).detach();
+  }
+}

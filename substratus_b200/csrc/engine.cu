@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <unistd.h>
 
 namespace ssb {
 
@@ -46,6 +47,7 @@ static const uint32_t kGlobal = 1u << 20;
 Engine::~Engine() {
   if (device_ >= 0) cudaSetDevice(device_);
   for (auto& g : graphs_) cudaGraphExecDestroy(g.second);
+  for (void* p : ipc_opened_) cudaIpcCloseMemHandle(p);
   for (void* p : allocs_) cudaFree(p);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -272,6 +274,17 @@ int Engine::alloc_runtime(const Json& params) {
   TRY(dmalloc(&q_, (size_t)m_max_ * Hl_ * D));
   TRY(dmalloc(&attn_, (size_t)m_max_ * Hl_ * D));
   TRY(dmalloc(&act_, (size_t)m_max_ * Il_));
+  TRY(dmalloc(&xn_, (size_t)m_max_ * h));
+  TRY(dmalloc(&tp_step_, 1));
+  CK(cudaMemset(tp_step_, 0, sizeof(int)));
+  if (tp_size_ > 1) {
+    // plain cudaMalloc (not a pool) so the buffers can be exported with cudaIpcGetMemHandle
+    TRY(dmalloc(&tp_partials_, 2 * (size_t)m_max_ * h));
+    TRY(dmalloc(&tp_flags_, 8));
+    CK(cudaMemset(tp_flags_, 0, 8 * sizeof(uint32_t)));
+    TRY(dmalloc(&d_peer_partials_, 8));
+    TRY(dmalloc(&d_peer_flags_, 8));
+  }
   TRY(dmalloc(&logits_, (size_t)max_batch_ * cfg_.vocab));
   const int max_splits = 16;
   TRY(dmalloc(&part_o_, (size_t)max_batch_ * Hl_ * max_splits * D));
@@ -341,12 +354,30 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   CK(cudaEventCreate(&ev1_));
   use_pdl_ = params.get_int("use_pdl", 1) != 0;
   use_graph_ = params.get_int("use_graph", 1) != 0;
-  if (tp_size_ > 1) RET(SSB_EINVAL, "tensor parallel engines need ssb_tp_connect (not available in this build step)");
+  if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
   TRY(alloc_weights());
   const std::string wmode = params.get_str("weights", "file");
   if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
   TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0)));
   TRY(alloc_runtime(params));
+  {
+    const std::string gp = params.get_str("gemm_path", "auto");  // "auto" | "gemv" (CUDA cores only) | "tc" (tcgen05 always)
+    if (gp == "gemv")
+      tc_min_rows_ = 1 << 30;
+    else if (gp == "tc")
+      tc_min_rows_ = 1;
+    else if (gp == "auto")
+      tc_min_rows_ = (int)params.get_int("tc_min_rows", 8);
+    else
+      RET(SSB_EINVAL, "params.gemm_path must be auto|gemv|tc");
+    const int h = cfg_.hidden, D = cfg_.head_dim, br = tc_weight_box_rows();
+    for (auto& w : lw_) {
+      CK(tc_make_tmap(&w.tm_qkv, w.wqkv, (int64_t)(Hl_ + 2 * KVHl_) * D, h, h, br));
+      CK(tc_make_tmap(&w.tm_o, w.wo, h, (int64_t)Hl_ * D, (int64_t)Hl_ * D, br));
+      CK(tc_make_tmap(&w.tm_gu, w.wgu, 2 * (int64_t)Il_, h, h, br));
+      CK(tc_make_tmap(&w.tm_down, w.wdown, h, Il_, Il_, br));
+    }
+  }
   CK(cudaStreamSynchronize(stream_));
   timing_reset();
   return SSB_OK;
@@ -433,9 +464,33 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
   const int h = cfg_.hidden, D = cfg_.head_dim;
   const int group = cfg_.heads / cfg_.kv_heads;
   int launches = 0;
-  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, lc(true)));
+  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, lc(true)));
+  const bool tp = tp_size_ > 1;
+  TpArgs ta = {};
+  if (tp) {
+    ta.rank = tp_rank_;
+    ta.size = tp_size_;
+    ta.peer_partials = d_peer_partials_;
+    ta.peer_flags = d_peer_flags_;
+    ta.tp_step = tp_step_;
+    ta.n_per_step = 2 * cfg_.layers;
+    ta.parity_stride = m_max_ * h;
+    ta.M = M;
+    ta.hidden = h;
+    ta.resid = h_;
+    ta.out = h_;
+  }
   ++launches;
   const int n_splits = (M <= max_batch_) ? decode_splits_(M) : 1;
+  // projections: CUDA-core GEMV (weights streamed once, M <= 4 rows per pass) or tcgen05 GEMM (tokens = UMMA N)
+  const bool tc = M >= tc_min_rows_;
+  const int tn = tc_pick_tn(M);
+  TcTensorMap tm_xn, tm_attn, tm_act;
+  if (tc) {
+    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn));
+    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn));
+    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn));
+  }
   for (int l = 0; l < cfg_.layers; ++l) {
     const LayerW& w = lw_[l];
     GemvArgs g = {};
@@ -460,7 +515,13 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     g.rope_cs = rope_cs_;
     g.block_size = block_size_;
     g.kvh = KVHl_;
-    CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
+    if (tc) {
+      CK(launch_rmsnorm(h_, w.ln1, xn_, M, h, cfg_.eps, lc(true)));
+      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn, g, EPI_QKV_ROPE, lc(true)));
+      ++launches;
+    } else {
+      CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
+    }
 
     AttnArgs a = {};
     a.q = q_;
@@ -498,7 +559,17 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     o.out_bf16 = h_;
     o.resid = h_;
     o.ld_out = h;
-    CK(launch_gemv(o, EPI_RESID, NORM_NONE, lc(true)));
+    const int epi_rowpar = tp ? EPI_F32 : EPI_RESID;  // row-parallel under TP: raw fp32 partial -> allreduce + residual
+    if (tp) o.out_f32 = tp_partials_ + (size_t)((2 * l) & 1) * m_max_ * h;
+    if (tc)
+      CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_rowpar, lc(true)));
+    else
+      CK(launch_gemv(o, epi_rowpar, NORM_NONE, lc(true)));
+    if (tp) {
+      ta.seq_in_step = 2 * l;
+      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      ++launches;
+    }
 
     GemvArgs u = {};
     u.W = w.wgu;
@@ -511,7 +582,13 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     u.eps = cfg_.eps;
     u.out_bf16 = act_;
     u.ld_out = Il_;
-    CK(launch_gemv(u, EPI_SWIGLU, NORM_RMS, lc(true)));
+    if (tc) {
+      CK(launch_rmsnorm(h_, w.ln2, xn_, M, h, cfg_.eps, lc(true)));
+      CK(launch_tc_gemm(w.tm_gu, tm_xn, tn, u, EPI_SWIGLU, lc(true)));
+      ++launches;
+    } else {
+      CK(launch_gemv(u, EPI_SWIGLU, NORM_RMS, lc(true)));
+    }
 
     GemvArgs d = {};
     d.W = w.wdown;
@@ -523,7 +600,16 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     d.out_bf16 = h_;
     d.resid = h_;
     d.ld_out = h;
-    CK(launch_gemv(d, EPI_RESID, NORM_NONE, lc(true)));
+    if (tp) d.out_f32 = tp_partials_ + (size_t)((2 * l + 1) & 1) * m_max_ * h;
+    if (tc)
+      CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_rowpar, lc(true)));
+    else
+      CK(launch_gemv(d, epi_rowpar, NORM_NONE, lc(true)));
+    if (tp) {
+      ta.seq_in_step = 2 * l + 1;
+      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      ++launches;
+    }
     launches += 5;
     if (taps_ && l == 0) {
       CK(cudaMemcpyAsync(tap_h0_, h_, (size_t)M * h * 2, cudaMemcpyDeviceToDevice, stream_));
@@ -555,6 +641,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
 
 int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits) {
   if (nseq < 1 || nseq > max_batch_) RET(SSB_EINVAL, "nseq out of range");
+  if (tp_size_ > 1 && !tp_connected_) RET(SSB_ESTATE, "tensor-parallel engine: call ssb_tp_connect first");
   CK(cudaSetDevice(device_));
   int total = 0;
   std::vector<int> slots(seq_ids, seq_ids + nseq);
@@ -651,6 +738,7 @@ int Engine::build_graph(int B) {
 int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float* logits) {
   if (nseq < 1 || nseq > max_batch_) RET(SSB_EINVAL, "nseq out of range");
   if (nsteps < 1 || nsteps > max_steps_) RET(SSB_EINVAL, "nsteps out of range");
+  if (tp_size_ > 1 && !tp_connected_) RET(SSB_ESTATE, "tensor-parallel engine: call ssb_tp_connect first");
   CK(cudaSetDevice(device_));
   std::vector<int> slots(seq_ids, seq_ids + nseq), pos(nseq);
   for (int i = 0; i < nseq; ++i) {
@@ -849,6 +937,72 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
   return rc;
 }
 
+// ---- tensor-parallel bootstrap: exchange buffers are exported as CUDA IPC handles (or raw pointers inside one process)
+struct TpHandle {
+  uint32_t magic;
+  int32_t rank, size, device;
+  int64_t pid;
+  cudaIpcMemHandle_t partials, flags;
+  uint64_t raw_partials, raw_flags;
+};
+static_assert(sizeof(TpHandle) <= 256, "ssb_tp_handle_size");
+
+int Engine::tp_export(void* out) {
+  if (tp_size_ < 2) RET(SSB_ESTATE, "engine is not tensor parallel");
+  CK(cudaSetDevice(device_));
+  TpHandle hd;
+  memset(&hd, 0, sizeof hd);
+  hd.magic = 0x53534254u;
+  hd.rank = tp_rank_;
+  hd.size = tp_size_;
+  hd.device = device_;
+  hd.pid = (int64_t)getpid();
+  CK(cudaIpcGetMemHandle(&hd.partials, tp_partials_));
+  CK(cudaIpcGetMemHandle(&hd.flags, tp_flags_));
+  hd.raw_partials = (uint64_t)(uintptr_t)tp_partials_;
+  hd.raw_flags = (uint64_t)(uintptr_t)tp_flags_;
+  memset(out, 0, 256);
+  memcpy(out, &hd, sizeof hd);
+  return SSB_OK;
+}
+
+int Engine::tp_connect(const void* all, int n) {
+  if (tp_size_ < 2) RET(SSB_ESTATE, "engine is not tensor parallel");
+  if (n != tp_size_) RET(SSB_EINVAL, "n_ranks != tp_size");
+  CK(cudaSetDevice(device_));
+  std::vector<float*> pp(8, nullptr);
+  std::vector<uint32_t*> pf(8, nullptr);
+  for (int r = 0; r < n; ++r) {
+    TpHandle hd;
+    memcpy(&hd, (const char*)all + (size_t)r * 256, sizeof hd);
+    if (hd.magic != 0x53534254u || hd.rank != r || hd.size != tp_size_) RET(SSB_EINVAL, "bad TP handle for rank " + std::to_string(r));
+    if (r == tp_rank_) {
+      pp[r] = tp_partials_;
+      pf[r] = tp_flags_;
+    } else if (hd.pid == (int64_t)getpid()) {  // several ranks in one process (serve host): plain peer access
+      if (hd.device != device_) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(hd.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+      }
+      pp[r] = (float*)(uintptr_t)hd.raw_partials;
+      pf[r] = (uint32_t*)(uintptr_t)hd.raw_flags;
+    } else {
+      void *a = nullptr, *b = nullptr;
+      CK(cudaIpcOpenMemHandle(&a, hd.partials, cudaIpcMemLazyEnablePeerAccess));
+      ipc_opened_.push_back(a);
+      CK(cudaIpcOpenMemHandle(&b, hd.flags, cudaIpcMemLazyEnablePeerAccess));
+      ipc_opened_.push_back(b);
+      pp[r] = (float*)a;
+      pf[r] = (uint32_t*)b;
+    }
+  }
+  CK(cudaMemcpy(d_peer_partials_, pp.data(), 8 * sizeof(float*), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_peer_flags_, pf.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  tp_connected_ = true;
+  return SSB_OK;
+}
+
 int Engine::last_timing(ssb_timing* t) const {
   *t = timing_;
   return SSB_OK;
@@ -992,16 +1146,11 @@ int ssb_timing_reset(ssb_engine* e) {
 int ssb_tp_handle_size(void) { return 256; }
 int ssb_tp_export(ssb_engine* e, void* handle_out) {
   GUARD(e);
-  (void)handle_out;
-  ssb::set_error("tensor parallel bootstrap is not available in this build step");
-  return SSB_ESTATE;
+  return handle_out ? e->impl.tp_export(handle_out) : SSB_EINVAL;
 }
 int ssb_tp_connect(ssb_engine* e, const void* all_handles, int n_ranks) {
   GUARD(e);
-  (void)all_handles;
-  (void)n_ranks;
-  ssb::set_error("tensor parallel bootstrap is not available in this build step");
-  return SSB_ESTATE;
+  return all_handles ? e->impl.tp_connect(all_handles, n_ranks) : SSB_EINVAL;
 }
 int ssb_bench_kernel(ssb_engine* e, const char* which, int rows, int ctx, int iters, double* ms_per_launch,
                      int64_t* algorithmic_bytes) {

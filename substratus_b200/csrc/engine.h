@@ -11,6 +11,7 @@
 #include "json.h"
 #include "kernels.h"
 #include "loader.h"
+#include "tc_gemm.h"
 
 namespace ssb {
 
@@ -23,6 +24,7 @@ struct ModelCfg {
 
 struct LayerW {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  TcTensorMap tm_qkv, tm_o, tm_gu, tm_down;  // TMA descriptors of the four projection matrices (tcgen05 path)
 };
 
 struct SeqSlot {
@@ -46,6 +48,8 @@ class Engine {
   void timing_reset();
   int debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols);
   int bench_kernel(const char* which, int rows, int ctx, int iters, double* ms_out, int64_t* bytes_out);
+  int tp_export(void* handle_out);
+  int tp_connect(const void* all_handles, int n_ranks);
 
  private:
   // setup
@@ -67,6 +71,7 @@ class Engine {
   int Hl_ = 0, KVHl_ = 0, Il_ = 0;  // per-rank heads / kv heads / intermediate
   int max_batch_ = 32, max_seq_ = 4096, block_size_ = 16, n_blocks_ = 0, max_blocks_per_seq_ = 0, m_max_ = 0;
   bool use_pdl_ = true, use_graph_ = true, taps_ = false;
+  int tc_min_rows_ = 8;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 
@@ -78,11 +83,19 @@ class Engine {
   bf16 *kpool_ = nullptr, *vpool_ = nullptr;
   size_t kv_layer_elems_ = 0;
   // activations
-  bf16 *h_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr;
+  bf16 *h_ = nullptr, *q_ = nullptr, *attn_ = nullptr, *act_ = nullptr, *xn_ = nullptr;
   float *logits_ = nullptr, *part_o_ = nullptr, *part_ml_ = nullptr;
   int *counters_ = nullptr, *row_tok_ = nullptr, *row_slot_ = nullptr, *row_pos_ = nullptr, *logit_rows_ = nullptr;
   int *next_tok_ = nullptr, *hist_ = nullptr, *step_ = nullptr, *block_table_ = nullptr;
   int max_steps_ = 0;
+  // tensor parallel exchange (peer-mapped over NVLink; see tp_allreduce_resid_kernel)
+  float* tp_partials_ = nullptr;       // [2][m_max][hidden] fp32 partial sums of this rank
+  uint32_t* tp_flags_ = nullptr;       // [8] epoch flags written by the peers
+  int* tp_step_ = nullptr;             // forwards executed (device counter)
+  float** d_peer_partials_ = nullptr;  // [tp_size] device array of peer-mapped pointers
+  uint32_t** d_peer_flags_ = nullptr;
+  std::vector<void*> ipc_opened_;
+  bool tp_connected_ = false;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;

@@ -1,0 +1,64 @@
+// epilogue.cuh — fused projection epilogues shared by the CUDA-core GEMV (kernels.cu) and the tcgen05 GEMM
+// (tc_gemm.cu).  Both kernels hand over the fp32 dot products of one PAIR of physical weight rows (2*pair, 2*pair+1)
+// for token row m; the engine lays weights out so that the pair is (RoPE partner j, j+d/2) for q/k and
+// (gate_i, up_i) for the MLP (DESIGN.md "weight layout").  Rounding points follow HF bf16 tensor ops
+// (HF:models/llama/modeling_llama.py:138-168 RoPE, :177-183 SwiGLU, :325,:331 residual adds).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+template <int BT, int EPI>
+SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, float v1) {
+  // v0/v1: fp32 dot products of physical rows (2*pair, 2*pair+1) for tile row m (global row index)
+  if constexpr (EPI == EPI_F32) {
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = v0;
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = v1;
+  } else if constexpr (EPI == EPI_F32_BF16R) {
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = bf16r(v0);
+    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = bf16r(v1);
+  } else if constexpr (EPI == EPI_BF16) {
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)m * a.ld_out + 2 * pair) = pack_bf16(v0, v1);
+  } else if constexpr (EPI == EPI_RESID) {
+    size_t o = (size_t)m * a.ld_out + 2 * pair;
+    uint32_t r = *reinterpret_cast<const uint32_t*>(a.resid + o);
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(bf16r(v0) + bf_lo(r), bf16r(v1) + bf_hi(r));
+  } else if constexpr (EPI == EPI_SWIGLU) {
+    float g = bf16r(v0), u = bf16r(v1);
+    float s = bf16r(g / (1.0f + expf(-g)));
+    a.out_bf16[(size_t)m * a.ld_out + pair] = __float2bfloat16_rn(s * u);
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int hd = a.head_dim, half = hd >> 1;
+    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+    const int pos = a.row_pos[m];
+    if (pair < q_pairs + k_pairs) {
+      const bool is_q = pair < q_pairs;
+      const int pp = is_q ? pair : pair - q_pairs;
+      const int head = pp / half, j = pp - head * half;
+      const uint32_t cs = a.rope_cs[(size_t)pos * half + j];
+      const float c = bf_lo(cs), s = bf_hi(cs);
+      const float x0 = bf16r(v0), x1 = bf16r(v1);  // Linear outputs are bf16
+      // (q*cos) + (rotate_half(q)*sin), every op rounded to bf16 like the HF bf16 tensor ops
+      const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
+      const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
+      if (is_q) {
+        bf16* q = a.q_out + (size_t)m * a.q_rows + head * hd + j;
+        q[0] = __float2bfloat16_rn(y0);
+        q[half] = __float2bfloat16_rn(y1);
+      } else {
+        const int slot = a.row_slot[m];
+        const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
+        bf16* k = a.kcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+        k[0] = __float2bfloat16_rn(y0);
+        k[half] = __float2bfloat16_rn(y1);
+      }
+    } else {
+      const int e = 2 * (pair - q_pairs - k_pairs);
+      const int head = e / hd, j = e - head * hd;
+      const int slot = a.row_slot[m];
+      const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
+      bf16* v = a.vcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+      *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
+    }
+  }
+}
+

@@ -34,60 +34,7 @@ int gemv_pick_bt(int M, int K) {
   return bt;
 }
 
-template <int BT, int EPI>
-SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, float v1) {
-  // v0/v1: fp32 dot products of physical rows (2*pair, 2*pair+1) for tile row m (global row index)
-  if constexpr (EPI == EPI_F32) {
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = v0;
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = v1;
-  } else if constexpr (EPI == EPI_F32_BF16R) {
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = bf16r(v0);
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = bf16r(v1);
-  } else if constexpr (EPI == EPI_BF16) {
-    *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)m * a.ld_out + 2 * pair) = pack_bf16(v0, v1);
-  } else if constexpr (EPI == EPI_RESID) {
-    size_t o = (size_t)m * a.ld_out + 2 * pair;
-    uint32_t r = *reinterpret_cast<const uint32_t*>(a.resid + o);
-    *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(bf16r(v0) + bf_lo(r), bf16r(v1) + bf_hi(r));
-  } else if constexpr (EPI == EPI_SWIGLU) {
-    float g = bf16r(v0), u = bf16r(v1);
-    float s = bf16r(g / (1.0f + expf(-g)));
-    a.out_bf16[(size_t)m * a.ld_out + pair] = __float2bfloat16_rn(s * u);
-  } else if constexpr (EPI == EPI_QKV_ROPE) {
-    const int hd = a.head_dim, half = hd >> 1;
-    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
-    const int pos = a.row_pos[m];
-    if (pair < q_pairs + k_pairs) {
-      const bool is_q = pair < q_pairs;
-      const int pp = is_q ? pair : pair - q_pairs;
-      const int head = pp / half, j = pp - head * half;
-      const uint32_t cs = a.rope_cs[(size_t)pos * half + j];
-      const float c = bf_lo(cs), s = bf_hi(cs);
-      const float x0 = bf16r(v0), x1 = bf16r(v1);  // Linear outputs are bf16
-      // (q*cos) + (rotate_half(q)*sin), every op rounded to bf16 like the HF bf16 tensor ops
-      const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
-      const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
-      if (is_q) {
-        bf16* q = a.q_out + (size_t)m * a.q_rows + head * hd + j;
-        q[0] = __float2bfloat16_rn(y0);
-        q[half] = __float2bfloat16_rn(y1);
-      } else {
-        const int slot = a.row_slot[m];
-        const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
-        bf16* k = a.kcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
-        k[0] = __float2bfloat16_rn(y0);
-        k[half] = __float2bfloat16_rn(y1);
-      }
-    } else {
-      const int e = 2 * (pair - q_pairs - k_pairs);
-      const int head = e / hd, j = e - head * hd;
-      const int slot = a.row_slot[m];
-      const int blk = a.block_table[(size_t)slot * a.bt_stride + pos / a.block_size];
-      bf16* v = a.vcache + (((size_t)blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
-      *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
-    }
-  }
-}
+#include "epilogue.cuh"
 
 template <int BT, int EPI, int NORM>
 __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
@@ -364,11 +311,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const AttnArgs 
     for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
   }
   const int* bt = a.block_table + (size_t)slot * a.bt_stride;
-  for (int t = t_begin + warp * RPW + sub; t < t_end; t += AT_WARPS * RPW) {
-    const int blk = bt[t / BS];
-    const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
-    const uint4 kv = *reinterpret_cast<const uint4*>(a.kcache + off);
-    const uint4 vv = *reinterpret_cast<const uint4*>(a.vcache + off);
+  // the trip count is warp-uniform (tb), the per-sub-group token may be past the end: the shuffles below use the
+  // full mask, so every lane must execute them (a half-warp leaving the loop early would deadlock the warp)
+  for (int tb = t_begin + warp * RPW; tb < t_end; tb += AT_WARPS * RPW) {
+    const int t = tb + sub;
+    const bool tv = t < t_end;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (tv) {
+      const int blk = bt[t / BS];
+      const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
+      kv = *reinterpret_cast<const uint4*>(a.kcache + off);
+      vv = *reinterpret_cast<const uint4*>(a.vcache + off);
+    }
     const uint32_t ku[4] = {kv.x, kv.y, kv.z, kv.w};
     const uint32_t vu[4] = {vv.x, vv.y, vv.z, vv.w};
     float kf[8], vf[8];
@@ -386,6 +340,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const AttnArgs 
       for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (!tv) continue;
       const float s = bf16r(bf16r(d) * a.scale);  // matmul output is bf16, then "* scaling" in bf16
       const float mn = fmaxf(m[g], s);
       const float corr = __expf(m[g] - mn);
@@ -485,11 +440,14 @@ cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc) {
 // embedding gather, greedy argmax
 // =====================================================================================================================
 __global__ void __launch_bounds__(128) embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ row_tok,
-                                                    bf16* __restrict__ h, int hidden, int* step_counter) {
+                                                    bf16* __restrict__ h, int hidden, int* step_counter, int* fwd_counter) {
   pdl_wait();
   pdl_launch_dependents();
   const int m = blockIdx.x;
-  if (m == 0 && threadIdx.x == 0 && step_counter) *step_counter += 1;
+  if (m == 0 && threadIdx.x == 0) {
+    if (step_counter) *step_counter += 1;
+    if (fwd_counter) *fwd_counter += 1;
+  }
   const bf16* src = embed + (size_t)row_tok[m] * hidden;
   bf16* dst = h + (size_t)m * hidden;
   for (int k = threadIdx.x * 8; k < hidden; k += 128 * 8)
@@ -497,8 +455,8 @@ __global__ void __launch_bounds__(128) embed_kernel(const bf16* __restrict__ emb
 }
 
 cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
-                         const LaunchCfg& lc) {
-  return launch_ex(embed_kernel, dim3(M), dim3(128), 0, lc, embed, row_tok, h, hidden, step_counter);
+                         int* fwd_counter, const LaunchCfg& lc) {
+  return launch_ex(embed_kernel, dim3(M), dim3(128), 0, lc, embed, row_tok, h, hidden, step_counter, fwd_counter);
 }
 
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int n_rows,
@@ -643,4 +601,73 @@ cudaError_t launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStrea
   if (n == 0) return cudaSuccess;
   bf16_to_f32_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, n);
   return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// tensor-parallel one-shot allreduce + residual: h = bf16(bf16(sum_r partial_r) + h)
+// Every rank pushes a flag to every peer (release, system scope), polls its own flags (acquire), then reads the peers'
+// fp32 partials straight over NVLink (peer-mapped pointers) and sums them in rank order, so all ranks produce the
+// same bits.  Partials are double-buffered by allreduce parity: a buffer is rewritten two allreduces later, after a
+// barrier every peer passed only once it had finished reading (program order), so no second barrier is needed.
+// HF semantics: o_proj/down_proj output is bf16(sum over the full K) then "+ residual" in bf16
+// (HF:models/llama/modeling_llama.py:325,331); the fp32 cross-rank sum is the same sum in a different order.
+// =====================================================================================================================
+SSB_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+SSB_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SSB_DEVINL float4 ld_relaxed_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int TP_MAX = 8;
+constexpr int TP_THREADS = 256;
+
+__global__ void __launch_bounds__(TP_THREADS) tp_allreduce_resid_kernel(const TpArgs a) {
+  pdl_wait();  // this rank's partials (previous kernel) are complete and visible
+  pdl_launch_dependents();
+  const uint32_t epoch = (uint32_t)(*a.tp_step) * (uint32_t)a.n_per_step + (uint32_t)a.seq_in_step + 1u;
+  const int parity = a.seq_in_step & 1;
+  if (blockIdx.x == 0 && threadIdx.x < a.size && threadIdx.x != a.rank) {
+    __threadfence_system();
+    st_release_sys(a.peer_flags[threadIdx.x] + a.rank, epoch);  // "rank's partials for `epoch` are ready"
+  }
+  if (threadIdx.x < a.size && threadIdx.x != a.rank) {
+    const uint32_t* f = a.peer_flags[a.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+  const int total4 = a.M * a.hidden / 4;
+  const size_t poff = (size_t)parity * a.parity_stride;
+  for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < total4; i += gridDim.x * TP_THREADS) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {
+      if (r < a.size) {
+        const float4 v = ld_relaxed_sys_f4(a.peer_partials[r] + poff + (size_t)i * 4);
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
+      }
+    }
+    const uint2 rv = *reinterpret_cast<const uint2*>(a.resid + (size_t)i * 4);
+    uint2 o;
+    o.x = pack_bf16(bf16r(s.x) + bf_lo(rv.x), bf16r(s.y) + bf_hi(rv.x));
+    o.y = pack_bf16(bf16r(s.z) + bf_lo(rv.y), bf16r(s.w) + bf_hi(rv.y));
+    *reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = o;
+  }
+}
+
+cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc) {
+  if (a.size > TP_MAX || (a.hidden & 3)) return cudaErrorInvalidValue;
+  const int total4 = a.M * a.hidden / 4;
+  int grid = (total4 + TP_THREADS * 2 - 1) / (TP_THREADS * 2);
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  return launch_ex(tp_allreduce_resid_kernel, dim3(grid), dim3(TP_THREADS), 0, lc, a);
 }

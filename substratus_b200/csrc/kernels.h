@@ -74,7 +74,7 @@ int gemv_pick_bt(int M, int K);
 cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc);
 // h[m][:] = embed[row_tok[m]][:]; thread 0 of block 0 also does (*step_counter)++ when non-null
 cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
-                         const LaunchCfg& lc);
+                         int* fwd_counter, const LaunchCfg& lc);
 // greedy pick per row (lowest index wins ties, as torch.argmax on CPU): tok_out[r] = argmax logits[r][:]
 // hist != null: hist[(*step) * n_rows + r] = tok ; pos_inc != null: pos_inc[r] += 1
 cudaError_t launch_argmax(const float* logits, int V, int n_rows, int* tok_out, int* hist, const int* step,
@@ -89,3 +89,17 @@ cudaError_t launch_synth_fill(bf16* dst, int64_t dst_ld, const int* row_idx, int
                               uint64_t seed, uint32_t tid, float amp, float base, cudaStream_t s);
 void synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst);
 cudaError_t launch_bf16_to_f32(const bf16* src, float* dst, int64_t n, cudaStream_t s);
+
+// ---- tensor-parallel exchange (one-shot allreduce over NVLink peer memory, fused with the residual add)
+struct TpArgs {
+  int rank, size;
+  float* const* peer_partials;   // [size] device pointers (peer-mapped) to each rank's partial buffer [2][rows_max][hidden]
+  uint32_t* const* peer_flags;   // [size] device pointers to each rank's flag array [size] (flags live at the RECEIVER)
+  const int* tp_step;            // device counter, +1 per forward (same on every rank)
+  int seq_in_step, n_per_step;   // index of this allreduce inside the forward, allreduces per forward
+  int parity_stride;             // elements between the two parity buffers (rows_max * hidden)
+  int M, hidden;
+  const bf16* resid;             // [M][hidden] local residual stream
+  bf16* out;                     // [M][hidden] (may alias resid)
+};
+cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);

@@ -1,0 +1,341 @@
+// tc_gemm.cu — dense projections on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   Y[M_tok, N] = X[M_tok, K] * W[N, K]^T          (HF nn.Linear, HF:models/llama/modeling_llama.py:238-249,177-183)
+//
+// computed transposed so the WEIGHT rows ride the 128 TMEM lanes:  D[128 weight rows, TN tokens] += A * B^T with
+//   A = W tile  [128 x 64]  (K-major, TMA 128B-swizzled)      -> UMMA M = 128
+//   B = X tile  [TN  x 64]  (K-major, TMA 128B-swizzled)      -> UMMA N = TN (16..256)
+// Tokens are the UMMA N dimension, so the same kernel serves prefill (TN = 128/256, tensor-pipe bound) and batched
+// decode (TN = 16/32, HBM bound: weights stream HBM -> TMA -> smem -> tensor core without touching registers).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> fused RoPE/KV-append | SwiGLU | residual, same math as gemv_epilogue).
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_gemm.h"
+
+#include "epilogue.cuh"
+
+constexpr int TC_BM = 128;   // weight rows per tile (UMMA M)
+constexpr int TC_BK = 64;    // K elements per stage = one 128-byte swizzle span of bf16
+constexpr int TC_THREADS = 192;
+
+SSB_DEVINL void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+SSB_DEVINL void prefetch_tmap(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+SSB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SSB_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+SSB_DEVINL void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+SSB_DEVINL void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+SSB_DEVINL void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+SSB_DEVINL void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row groups of 128 B rows, groups 1024 B apart
+// (cute::UMMA::SmemDescriptor bit layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64))
+SSB_DEVINL uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int TN>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;                       // 16 KiB
+  static constexpr int B_BYTES = TN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * TN <= 32) ? 32 : (2 * TN <= 64) ? 64 : (2 * TN <= 128) ? 128 : (2 * TN <= 256) ? 256 : 512;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int TN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemvArgs a) {
+  using Cfg = TcCfg<TN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ntiles = (a.N + TC_BM - 1) / TC_BM;
+  const int n_mtiles = (a.M + TN - 1) / TN;
+  const int n_tiles = n_ntiles * n_mtiles;
+  const int nkb = (a.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // activations (B operand, residual) come from the previous kernel
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(sa, &tmA, kb * TC_BK, nt * TC_BM, &full[stage]);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * TC_BK, mt * TN, &full[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (one thread)
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint64_t ad = umma_desc_k_sw128(sa);
+          const uint64_t bd = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B: advance the start address inside the span
+            tc_mma_bf16(tmem_base + acc * TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc_commit(&empty[stage]);                    // frees the smem stage when these MMAs retire
+          if (kb == nkb - 1) tc_commit(&tfull[acc]);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = nt * TC_BM + quad * 32 + lane;  // physical weight row (even = first of a pair)
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN;
+#pragma unroll 1
+      for (int c = 0; c < TN; c += 8) {
+        if (mt * TN + c >= a.M) break;  // warp-uniform
+        uint32_t v[8];
+        tc_ld8(taddr + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float mine = __uint_as_float(v[j]);
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          const int m = mt * TN + c + j;
+          if (!(lane & 1) && row < a.N && m < a.M) gemv_epilogue<1, EPI>(a, row >> 1, m, mine, other);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D K-major bf16 tensor map: global [rows, cols] with row pitch ld elements, box [box_rows, 64 cols], 128B swizzle
+cudaError_t tc_make_tmap(TcTensorMap* out, const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  static_assert(sizeof(TcTensorMap) == sizeof(CUtensorMap), "tensor map size");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+int tc_pick_tn(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
+int tc_weight_box_rows() { return TC_BM; }
+
+template <int TN, int EPI>
+static cudaError_t launch_tc_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
+  using Cfg = TcCfg<TN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int n_tiles = ((a.N + TC_BM - 1) / TC_BM) * ((a.M + TN - 1) / TN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_tiles < lc.n_sm ? n_tiles : lc.n_sm);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<TN, EPI>, *reinterpret_cast<const CUtensorMap*>(&tmA),
+                            *reinterpret_cast<const CUtensorMap*>(&tmB), a);
+}
+
+template <int EPI>
+static cudaError_t launch_tc_e(int tn, const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
+  switch (tn) {
+    case 16: return launch_tc_t<16, EPI>(tmA, tmB, a, lc);
+    case 32: return launch_tc_t<32, EPI>(tmA, tmB, a, lc);
+    case 64: return launch_tc_t<64, EPI>(tmA, tmB, a, lc);
+    case 128: return launch_tc_t<128, EPI>(tmA, tmB, a, lc);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// tmB must have been built with box_rows == tn
+cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc) {
+  if ((a.N & 1) || (a.K & 7)) return cudaErrorInvalidValue;
+  switch (epi) {
+    case EPI_QKV_ROPE: return launch_tc_e<EPI_QKV_ROPE>(tn, tmA, tmB, a, lc);
+    case EPI_SWIGLU: return launch_tc_e<EPI_SWIGLU>(tn, tmA, tmB, a, lc);
+    case EPI_RESID: return launch_tc_e<EPI_RESID>(tn, tmA, tmB, a, lc);
+    case EPI_BF16: return launch_tc_e<EPI_BF16>(tn, tmA, tmB, a, lc);
+    case EPI_F32: return launch_tc_e<EPI_F32>(tn, tmA, tmB, a, lc);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm (prefill)
+// xn[m][:] = w * bf16(x[m][:] * rsqrt(mean(x^2) + eps))     HF:models/llama/modeling_llama.py:62-67
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ out,
+                                                      int K, float eps) {
+  __shared__ float red[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const bf16* src = x + (size_t)m * K;
+  float ss = 0.f;
+  for (int k = tid * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = bf_lo(u[i]), hi = bf_hi(u[i]);
+      ss += lo * lo + hi * hi;
+    }
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)K + eps);
+  for (int k = tid * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+    const uint4 wv = ldg128(w + k);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = pack_bf16(bf16r(bf_lo(u[i]) * rstd) * bf_lo(wu[i]), bf16r(bf_hi(u[i]) * rstd) * bf_hi(wu[i]));
+    *reinterpret_cast<uint4*>(out + (size_t)m * K + k) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_rmsnorm(const bf16* x, const bf16* w, bf16* out, int M, int K, float eps, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M);
+  cfg.blockDim = dim3(256);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, rmsnorm_kernel, x, w, out, K, eps);
+}

@@ -55,7 +55,8 @@ def _teacher_forced_logits(cfg, sd, dtype, prompt_rows, forced):
 
 
 @pytest.mark.parametrize("name", ["tiny_mha", "tiny_gqa"])
-@pytest.mark.parametrize("mode", [{"use_pdl": 1, "use_graph": 1}, {"use_pdl": 0, "use_graph": 0}])
+@pytest.mark.parametrize("mode", [{"use_pdl": 1, "use_graph": 1}, {"use_pdl": 0, "use_graph": 0},
+                                  {"gemm_path": "tc"}, {"gemm_path": "tc", "use_pdl": 0, "use_graph": 0}])
 def test_logits_and_tokens_vs_oracle(Engine, tmp_path, name, mode):
     g = load_gold(name)
     cfg, ngen = g["config"], g["max_new_tokens"]
@@ -105,6 +106,29 @@ def test_layer_taps_vs_oracle(Engine, tmp_path):
         err = rel_err(got, want)
         _diag(f"[taps] {nm}: rel err vs bf16 oracle {err:.3e}")
         assert err < 2e-2, (nm, err)
+
+
+def test_tensor_core_path_matches_gemv_path(Engine, tmp_path):
+    """tcgen05 GEMM (tokens as UMMA N, TMA-swizzled operands, TMEM accumulators) vs the CUDA-core GEMV on the same
+    weights: fp32 accumulation order differs, roundings are the same -> logits agree to bf16-rounding flips.
+    Shapes cover ragged token tiles (M=37 -> TN=64, OOB rows zero-filled), N not a multiple of 128 (2*I = 2752) and
+    K not a multiple of 64 (I = 1376 -> 21.5 k-blocks, zero-filled tail)."""
+    cfg = synth.TINY_GQA
+    sd = synth.llama_state_dict(cfg, 13)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (37, 5, 64)]
+    res = {}
+    for path in ("gemv", "tc"):
+        with Engine(str(tmp_path), {"max_batch": 4, "max_seq_len": 160, "gemm_path": path}) as e:
+            res[path] = e.generate(prompts, 6, want_logits=True)
+    err = rel_err(res["tc"][1], res["gemv"][1])
+    _diag(f"[tc vs gemv] logits rel err {err:.3e}; tokens equal: {np.array_equal(res['tc'][0], res['gemv'][0])}")
+    assert err < 1e-2, err
+    l32 = _teacher_forced_logits(cfg, sd, torch.float32, [prompts[2]], res["tc"][0][2:3])
+    lbf = _teacher_forced_logits(cfg, sd, torch.bfloat16, [prompts[2]], res["tc"][0][2:3])
+    for s_ in range(6):
+        assert rel_err(res["tc"][1][s_, 2], l32[0, s_]) <= rel_err(lbf[0, s_], l32[0, s_]) + TOL
 
 
 def test_synthetic_weights_match_oracle(Engine, tmp_path):

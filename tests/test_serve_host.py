@@ -1,0 +1,102 @@
+"""Serve host (container "serve") against the reference's container contract
+(docs/container-contract.md:50-55; internal/controller/server_controller.go:156-172): listens on the port,
+`GET /` is 503 while loading and 200 only when ready; fatal load errors exit non-zero (pod restart); and the
+/generate + /v1/completions bodies carry the engine's greedy ids (gpu test: equal to the oracle's)."""
+import json
+import os
+import socket
+import subprocess
+import time
+import urllib.error
+import urllib.request
+
+import pytest
+import torch
+
+from oracle import llama_ref, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SERVE = os.path.join(ROOT, "host", "serve")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _get(url, data=None, timeout=10):
+    req = urllib.request.Request(url, data=json.dumps(data).encode() if data is not None else None,
+                                 headers={"Content-Type": "application/json"})
+    try:
+        with urllib.request.urlopen(req, timeout=timeout) as r:
+            return r.status, json.loads(r.read() or b"{}")
+    except urllib.error.HTTPError as e:
+        return e.code, json.loads(e.read() or b"{}")
+
+
+def _spawn(model_dir, params, port):
+    pf = os.path.join(model_dir, "params.json")
+    with open(pf, "w") as f:
+        json.dump(params, f)
+    env = dict(os.environ, PORT=str(port), PARAMS_FILE=pf, MODEL_DIR=model_dir)
+    return subprocess.Popen([SERVE], env=env, stderr=subprocess.PIPE, text=True)
+
+
+def test_serve_without_gpu_is_not_ready_and_exits_nonzero(tmp_path):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert os.path.exists(SERVE), "host/serve not built (python -c 'import __graft_entry__ as g; g.build()')"
+    llama_ref.write_hf_dir(str(tmp_path), synth.TINY_MHA, {})
+    port = _free_port()
+    p = _spawn(str(tmp_path), {"weights": "synthetic"}, port)
+    try:
+        rc = p.wait(timeout=30)
+        err = p.stderr.read()
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert rc == 3, (rc, err)  # SSB_ENODEV: no CPU fallback, the Deployment restarts the pod
+    assert "no CUDA device" in err or "sm_" in err
+
+
+@pytest.mark.gpu
+def test_serve_contract_and_generate(tmp_path):
+    cfg = synth.TINY_GQA
+    sd = synth.llama_state_dict(cfg, 3)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    port = _free_port()
+    p = _spawn(str(tmp_path), {"max_batch": 2, "max_seq_len": 128}, port)
+    base = f"http://127.0.0.1:{port}"
+    try:
+        deadline = time.time() + 120
+        st = None
+        while time.time() < deadline:
+            try:
+                st, _ = _get(base + "/", timeout=2)
+                if st == 200:
+                    break
+            except (urllib.error.URLError, ConnectionError, socket.timeout):
+                pass
+            time.sleep(0.2)
+        assert st == 200
+        prompt = torch.randint(0, cfg["vocab_size"], (1, 20), generator=torch.Generator().manual_seed(1234))
+        want, lg = llama_ref.LlamaRef(cfg, sd, torch.float32).generate(prompt, 6)
+        st, r = _get(base + "/generate", {"tokens": prompt[0].tolist(), "max_new_tokens": 6})
+        assert st == 200 and len(r["tokens"]) == 6
+        from util import greedy_agree
+
+        ok, exact, msg = greedy_agree([r["tokens"]], want.numpy(), lg.numpy(), 0.05)
+        assert ok and exact >= 1, msg
+        st, r2 = _get(base + "/v1/completions", {"prompt": prompt[0].tolist(), "max_tokens": 3})
+        assert st == 200 and r2["choices"][0]["tokens"] == r["tokens"][:3] and r2["usage"]["prompt_tokens"] == 20
+        st, r3 = _get(base + "/v1/completions", {"prompt": "hello", "max_tokens": 3})
+        assert st == 400 and "tokenizer" in r3["error"]
+        st, _ = _get(base + "/generate", {"tokens": [cfg["vocab_size"]], "max_new_tokens": 2})
+        assert st == 400
+        st, _ = _get(base + "/nope")
+        assert st == 404
+    finally:
+        p.kill()
