@@ -117,6 +117,11 @@ int ssb_bench_kernel(ssb_engine* e, const char* which, int rows, int ctx, int it
  * "h0" (layer-0 taps).  rows/cols returned through the out params. */
 int ssb_debug_read(ssb_engine* e, const char* name, float* dst, int64_t dst_elems, int* rows, int* cols);
 
+/* GGUF block dequantisation kernel exposed for the bit-exact check against llama.cpp's gguf-py (tests only):
+ * ggml_type = GGML type id (0 F32, 1 F16, 2 Q4_0, 8 Q8_0, 12 Q4_K, 14 Q6_K, 30 BF16); blocks = raw bytes (host);
+ * dst = n_elems bf16 bit patterns (host).  Runs the load-time CUDA kernel. */
+int ssb_debug_dequant(int ggml_type, const void* blocks, int64_t nbytes, int64_t n_elems, uint16_t* dst_bf16);
+
 /* Deterministic synthetic-weight generator exposed for the oracle cross-check
  * (tests/: bit-exact against oracle/synth.py).  Fills dst (host, uint16 bf16 bits). */
 int ssb_synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst);

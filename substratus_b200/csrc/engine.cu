@@ -70,6 +70,27 @@ int Engine::dmalloc(T** p, size_t n) {
 }
 
 int Engine::load_config(const std::string& dir, const Json& params) {
+  if (files_.is_gguf()) {
+    // GGUF carries its own hyper-parameters (llama.cpp convention `<arch>.<key>`); there is no config.json
+    // (examples/llama2-13b-chat-gguf/base-model.yaml:8-9 stores a single `model.bin`).
+    const Json& m = files_.gguf_meta();
+    const std::string arch = m.get_str("general.architecture", "llama");
+    if (arch != "llama") RET(SSB_EINVAL, "GGUF architecture '" + arch + "' is not supported (llama only)");
+    cfg_.model_type = "llama";
+    cfg_.hidden = (int)m.get_int(arch + ".embedding_length", 0);
+    cfg_.inter = (int)m.get_int(arch + ".feed_forward_length", 0);
+    cfg_.layers = (int)m.get_int(arch + ".block_count", 0);
+    cfg_.heads = (int)m.get_int(arch + ".attention.head_count", 0);
+    cfg_.kv_heads = (int)m.get_int(arch + ".attention.head_count_kv", cfg_.heads);
+    cfg_.head_dim = (int)m.get_int(arch + ".attention.key_length", cfg_.heads ? cfg_.hidden / cfg_.heads : 0);
+    cfg_.max_pos = (int)m.get_int(arch + ".context_length", 2048);
+    cfg_.eps = (float)m.get_num(arch + ".attention.layer_norm_rms_epsilon", 1e-5);
+    cfg_.theta = (float)m.get_num(arch + ".rope.freq_base", 10000.0);
+    const TensorView* te = files_.find("token_embd.weight");
+    if (!te) RET(SSB_EIO, "GGUF file has no token_embd.weight");
+    cfg_.vocab = (int)te->rows();
+    cfg_.tie_embeddings = files_.find("output.weight") == nullptr;
+  } else {
   std::string txt;
   if (!read_text_file(dir + "/config.json", &txt)) RET(SSB_EIO, "cannot read " + dir + "/config.json");
   Json c;
@@ -96,6 +117,7 @@ int Engine::load_config(const std::string& dir, const Json& params) {
     if (rs->kind == Json::Obj && rs->get_str("rope_type", rs->get_str("type", "default")) != "default")
       RET(SSB_EINVAL, "rope_scaling other than 'default' is not supported");
   cfg_.tie_embeddings = c.get_num("tie_word_embeddings", 0) != 0;
+  }
   if (cfg_.hidden <= 0 || cfg_.inter <= 0 || cfg_.layers <= 0 || cfg_.heads <= 0 || cfg_.vocab <= 0)
     RET(SSB_EINVAL, "config.json: missing model dimensions");
   if (cfg_.head_dim != 64 && cfg_.head_dim != 128) RET(SSB_EINVAL, "head_dim must be 64 or 128");
@@ -185,18 +207,54 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
   if (!cfg_.tie_embeddings) jobs.push_back({lm_head_, h, {}, cfg_.vocab, 0, h, h, "lm_head.weight", kGlobal + 2, kWAmp * kLmHeadGain, 0.f});
   jobs.push_back({final_norm_, h, {}, 1, 0, h, h, "model.norm.weight", kGlobal + 1, kNormAmp, 1.f});
 
-  ModelFiles files;
-  size_t max_src = 0;
+  ModelFiles& files = files_;
+  size_t max_src = 0, max_deq = 0;
+  const bool gguf = !synthetic && files.is_gguf();
+  if (gguf) {
+    // HF name -> GGUF name (llama.cpp convert_hf_to_gguf tensor map).  GGUF stores q/k rows already permuted per head
+    // to (j, j + d/2) -> (2j, 2j+1) for llama.cpp's interleaved RoPE; that IS this engine's pair-interleaved layout,
+    // so q/k rows are taken in file order.
+    auto rename = [](std::string n) {
+      auto rep = [&](const std::string& a, const std::string& b) {
+        size_t p = n.find(a);
+        if (p != std::string::npos) n.replace(p, a.size(), b);
+      };
+      rep("model.layers.", "blk.");
+      rep("self_attn.q_proj", "attn_q");
+      rep("self_attn.k_proj", "attn_k");
+      rep("self_attn.v_proj", "attn_v");
+      rep("self_attn.o_proj", "attn_output");
+      rep("mlp.gate_proj", "ffn_gate");
+      rep("mlp.up_proj", "ffn_up");
+      rep("mlp.down_proj", "ffn_down");
+      rep("input_layernorm", "attn_norm");
+      rep("post_attention_layernorm", "ffn_norm");
+      if (n == "model.embed_tokens.weight") n = "token_embd.weight";
+      if (n == "model.norm.weight") n = "output_norm.weight";
+      if (n == "lm_head.weight") n = "output.weight";
+      return n;
+    };
+    for (auto& j : jobs) {
+      const bool qk = j.name.find("q_proj") != std::string::npos || j.name.find("k_proj") != std::string::npos;
+      if (qk) {
+        const bool isq = j.name.find("q_proj") != std::string::npos;
+        j.rows = ident((isq ? h0 : kv0) * D, (isq ? Hl_ : KVHl_) * D);
+      }
+      j.name = rename(j.name);
+    }
+  }
   if (!synthetic) {
-    std::string err;
-    if (!files.open(dir, &err)) RET(SSB_EIO, err);
-    if (files.is_gguf()) RET(SSB_EINVAL, "GGUF checkpoints are handled by the gguf path (not in this build step)");
     for (auto& j : jobs) {
       const TensorView* tv = files.find(j.name);
       if (!tv) RET(SSB_EIO, "checkpoint is missing tensor " + j.name);
-      if (tv->dtype > DT_F32) RET(SSB_EINVAL, "unsupported dtype for " + j.name);
+      if (tv->dtype == DT_OTHER || (!gguf && tv->dtype > DT_F32)) RET(SSB_EINVAL, "unsupported dtype for " + j.name);
       if (tv->cols() != j.full_cols) RET(SSB_EINVAL, "unexpected shape for " + j.name);
       max_src = std::max(max_src, tv->nbytes);
+      if (tv->dtype >= DT_Q4_0) {
+        int64_t n = 1;
+        for (auto d : tv->shape) n *= d;
+        max_deq = std::max(max_deq, (size_t)n * 2);
+      }
     }
   }
   int* d_rows = nullptr;
@@ -204,7 +262,9 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
   for (auto& j : jobs) max_rows = std::max(max_rows, j.rows.size());
   CK(cudaMalloc(&d_rows, std::max<size_t>(max_rows, 1) * sizeof(int)));
   void* d_src = nullptr;
+  bf16* d_deq = nullptr;
   if (max_src) CK(cudaMalloc(&d_src, max_src));
+  if (max_deq) CK(cudaMalloc(&d_deq, max_deq));
   int rc = SSB_OK;
   for (auto& j : jobs) {
     const int* rows = nullptr;
@@ -219,7 +279,15 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
       const TensorView* tv = files.find(j.name);
       cudaMemcpyAsync(d_src, tv->data, tv->nbytes, cudaMemcpyHostToDevice, stream_);
       timing_.h2d_bytes += (int64_t)tv->nbytes;
-      e = launch_gather_rows(j.dst, j.dst_ld, d_src, tv->dtype, tv->cols(), rows, j.n_rows, j.col0, j.cols, stream_);
+      if (tv->dtype >= DT_Q4_0) {  // GGUF block formats: dequantise the whole tensor to bf16, then permute/shard
+        int64_t n = 1;
+        for (auto d : tv->shape) n *= d;
+        e = launch_dequant(d_src, tv->dtype, n, d_deq, stream_);
+        if (e == cudaSuccess)
+          e = launch_gather_rows(j.dst, j.dst_ld, d_deq, DT_BF16, tv->cols(), rows, j.n_rows, j.col0, j.cols, stream_);
+      } else {
+        e = launch_gather_rows(j.dst, j.dst_ld, d_src, tv->dtype, tv->cols(), rows, j.n_rows, j.col0, j.cols, stream_);
+      }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);  // d_rows / d_src are reused by the next job
     if (e != cudaSuccess) {
@@ -230,6 +298,7 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
   }
   cudaFree(d_rows);
   if (d_src) cudaFree(d_src);
+  if (d_deq) cudaFree(d_deq);
   return rc;
 }
 
@@ -237,8 +306,8 @@ int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
   const int ctas = M * (Hl_ / gc);
-  int s = (2 * n_sm_ + ctas - 1) / ctas;
-  return std::max(1, std::min(s, 16));
+  int s = (4 * n_sm_ + ctas - 1) / ctas;
+  return std::max(1, std::min(s, 32));
 }
 
 int Engine::alloc_runtime(const Json& params) {
@@ -286,7 +355,7 @@ int Engine::alloc_runtime(const Json& params) {
     TRY(dmalloc(&d_peer_flags_, 8));
   }
   TRY(dmalloc(&logits_, (size_t)max_batch_ * cfg_.vocab));
-  const int max_splits = 16;
+  const int max_splits = 32;
   TRY(dmalloc(&part_o_, (size_t)max_batch_ * Hl_ * max_splits * D));
   TRY(dmalloc(&part_ml_, (size_t)max_batch_ * Hl_ * max_splits * 2));
   TRY(dmalloc(&counters_, (size_t)m_max_ * Hl_));
@@ -338,6 +407,12 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
     device_ = -1;
     RET(SSB_ENODEV, "no CUDA device: libsubstratus_b200 has no CPU fallback");
   }
+  const std::string wmode = params.get_str("weights", "file");
+  if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
+  if (wmode == "file") {
+    std::string err;
+    if (!files_.open(model_dir, &err)) RET(SSB_EIO, err);
+  }
   TRY(load_config(model_dir, params));
   device_ = (int)params.get_int("device", tp_rank_ % ndev);
   if (device_ < 0 || device_ >= ndev) RET(SSB_EINVAL, "bad device index");
@@ -356,8 +431,6 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   use_graph_ = params.get_int("use_graph", 1) != 0;
   if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
   TRY(alloc_weights());
-  const std::string wmode = params.get_str("weights", "file");
-  if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
   TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0)));
   TRY(alloc_runtime(params));
   {
@@ -1162,6 +1235,39 @@ int ssb_debug_read(ssb_engine* e, const char* name, float* dst, int64_t dst_elem
   GUARD(e);
   if (!dst || !rows || !cols) return SSB_EINVAL;
   return e->impl.debug_read(name, dst, dst_elems, rows, cols);
+}
+int ssb_debug_dequant(int ggml_type, const void* blocks, int64_t nbytes, int64_t n_elems, uint16_t* dst_bf16) {
+  if (!blocks || !dst_bf16 || n_elems <= 0) return SSB_EINVAL;
+  int dt;
+  switch (ggml_type) {
+    case 0: dt = ssb::DT_F32; break;
+    case 1: dt = ssb::DT_F16; break;
+    case 2: dt = ssb::DT_Q4_0; break;
+    case 8: dt = ssb::DT_Q8_0; break;
+    case 12: dt = ssb::DT_Q4_K; break;
+    case 14: dt = ssb::DT_Q6_K; break;
+    case 30: dt = ssb::DT_BF16; break;
+    default: ssb::set_error("unsupported ggml type"); return SSB_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    ssb::set_error("no CUDA device: libsubstratus_b200 has no CPU fallback");
+    return SSB_ENODEV;
+  }
+  void* d_src = nullptr;
+  bf16* d_dst = nullptr;
+  cudaError_t e = cudaMalloc(&d_src, (size_t)nbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_dst, (size_t)n_elems * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(d_src, blocks, (size_t)nbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_dequant(d_src, dt, n_elems, d_dst, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(dst_bf16, d_dst, (size_t)n_elems * 2, cudaMemcpyDeviceToHost);
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  if (e != cudaSuccess) {
+    ssb::set_error(cudaGetErrorString(e));
+    return SSB_ECUDA;
+  }
+  return SSB_OK;
 }
 int ssb_synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst) {
   if (!dst || n < 0) return SSB_EINVAL;

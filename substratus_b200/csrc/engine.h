@@ -100,6 +100,7 @@ class Engine {
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;
   // host state
+  ModelFiles files_;
   std::vector<SeqSlot> slots_;
   std::vector<int> free_blocks_;
   std::vector<int> host_bt_;

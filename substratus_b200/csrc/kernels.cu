@@ -311,44 +311,58 @@ __global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const AttnArgs 
     for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
   }
   const int* bt = a.block_table + (size_t)slot * a.bt_stride;
-  // the trip count is warp-uniform (tb), the per-sub-group token may be past the end: the shuffles below use the
-  // full mask, so every lane must execute them (a half-warp leaving the loop early would deadlock the warp)
-  for (int tb = t_begin + warp * RPW; tb < t_end; tb += AT_WARPS * RPW) {
-    const int t = tb + sub;
-    const bool tv = t < t_end;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (tv) {
-      const int blk = bt[t / BS];
-      const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
-      kv = *reinterpret_cast<const uint4*>(a.kcache + off);
-      vv = *reinterpret_cast<const uint4*>(a.vcache + off);
+  // Latency-bound at small batch: issue the K/V loads of UNR token groups before consuming any (2*UNR 16-byte loads in
+  // flight per lane).  The trip count is warp-uniform; the shuffles use the full mask, so every lane executes them even
+  // when its own token is past the end (a half-warp leaving early would deadlock the warp).
+  constexpr int UNR = (G <= 2) ? 4 : 2;
+  constexpr int TSTEP = AT_WARPS * RPW;
+  for (int tb = t_begin + warp * RPW; tb < t_end; tb += TSTEP * UNR) {
+    uint4 kq[UNR], vq[UNR];
+    bool tvq[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int t = tb + u * TSTEP + sub;
+      tvq[u] = t < t_end;
+      kq[u] = make_uint4(0, 0, 0, 0);
+      vq[u] = make_uint4(0, 0, 0, 0);
+      if (tvq[u]) {
+        const int blk = bt[t / BS];
+        const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
+        kq[u] = *reinterpret_cast<const uint4*>(a.kcache + off);
+        vq[u] = *reinterpret_cast<const uint4*>(a.vcache + off);
+      }
     }
-    const uint32_t ku[4] = {kv.x, kv.y, kv.z, kv.w};
-    const uint32_t vu[4] = {vv.x, vv.y, vv.z, vv.w};
-    float kf[8], vf[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      kf[2 * i] = bf_lo(ku[i]);
-      kf[2 * i + 1] = bf_hi(ku[i]);
-      vf[2 * i] = bf_lo(vu[i]);
-      vf[2 * i + 1] = bf_hi(vu[i]);
-    }
+    for (int u = 0; u < UNR; ++u) {
+      if (tb + u * TSTEP >= t_end) break;  // warp-uniform
+      const bool tv = tvq[u];
+      const uint32_t ku[4] = {kq[u].x, kq[u].y, kq[u].z, kq[u].w};
+      const uint32_t vu[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+      float kf[8], vf[8];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float d = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        kf[2 * i] = bf_lo(ku[i]);
+        kf[2 * i + 1] = bf_hi(ku[i]);
+        vf[2 * i] = bf_lo(vu[i]);
+        vf[2 * i + 1] = bf_hi(vu[i]);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
+      for (int g = 0; g < G; ++g) {
+        float d = 0.f;
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      if (!tv) continue;
-      const float s = bf16r(bf16r(d) * a.scale);  // matmul output is bf16, then "* scaling" in bf16
-      const float mn = fmaxf(m[g], s);
-      const float corr = __expf(m[g] - mn);
-      const float p = __expf(s - mn);
-      m[g] = mn;
-      l[g] = l[g] * corr + p;
+        for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(p, vf[i], acc[g][i] * corr);
+        for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (!tv) continue;
+        const float s = bf16r(bf16r(d) * a.scale);  // matmul output is bf16, then "* scaling" in bf16
+        const float mn = fmaxf(m[g], s);
+        const float corr = __expf(m[g] - mn);
+        const float p = __expf(s - mn);
+        m[g] = mn;
+        l[g] = l[g] * corr + p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(p, vf[i], acc[g][i] * corr);
+      }
     }
   }
   const int sidx = warp * RPW + sub;

@@ -103,3 +103,6 @@ struct TpArgs {
   bf16* out;                     // [M][hidden] (may alias resid)
 };
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);
+
+// GGUF block dequantisation (dequant.cu): src = raw tensor bytes on the device, dtype = ssb::DType, n elements
+cudaError_t launch_dequant(const void* src, int dtype, int64_t n, bf16* dst, cudaStream_t s);

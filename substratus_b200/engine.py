@@ -45,7 +45,7 @@ class SsbTiming(C.Structure):
 EXPORTS = [
     "ssb_engine_create", "ssb_engine_destroy", "ssb_engine_info", "ssb_seq_create", "ssb_seq_free", "ssb_seq_len",
     "ssb_prefill", "ssb_decode", "ssb_last_timing", "ssb_timing_reset", "ssb_tp_handle_size", "ssb_tp_export",
-    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_read", "ssb_synth_fill_host", "ssb_last_error", "ssb_version",
+    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library(path: str | None = None):
     lib.ssb_bench_kernel.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                                      C.POINTER(C.c_int64)]
     lib.ssb_debug_read.argtypes = [vp, C.c_char_p, fp, C.c_int64, ip, ip]
+    lib.ssb_debug_dequant.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint16)]
     lib.ssb_synth_fill_host.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_float, C.c_float,
                                         C.POINTER(C.c_uint16)]
     lib.ssb_last_error.restype = C.c_char_p
@@ -191,6 +192,19 @@ class Engine:
     def timing_reset(self):
         _check(self._lib, self._lib.ssb_timing_reset(self._h))
 
+    # ---- tensor parallel bootstrap
+    def tp_export(self) -> bytes:
+        n = self._lib.ssb_tp_handle_size()
+        buf = C.create_string_buffer(n)
+        _check(self._lib, self._lib.ssb_tp_export(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def tp_connect(self, all_handles: bytes):
+        n = self._lib.ssb_tp_handle_size()
+        assert len(all_handles) % n == 0
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        _check(self._lib, self._lib.ssb_tp_connect(self._h, C.cast(buf, C.c_void_p), len(all_handles) // n))
+
     def bench_kernel(self, which: str, rows: int = 1, ctx: int = 576, iters: int = 64):
         """(avg device ms per launch, algorithmic bytes per launch) of one kernel class of the decode step."""
         ms, by = C.c_double(), C.c_int64()
@@ -211,4 +225,14 @@ def synth_fill_host(seed: int, tid: int, start: int, n: int, amp: float, base: f
     out = np.zeros(n, dtype=np.uint16)
     rc = lib.ssb_synth_fill_host(seed, tid, start, n, amp, base, out.ctypes.data_as(C.POINTER(C.c_uint16)))
     _check(lib, rc)
+    return out
+
+
+def debug_dequant(ggml_type: int, blocks: np.ndarray, n_elems: int) -> np.ndarray:
+    """Run the load-time GGUF dequant kernel on raw block bytes; returns bf16 bit patterns (tests only)."""
+    lib = load_library()
+    raw = np.ascontiguousarray(blocks).view(np.uint8).ravel()
+    out = np.zeros(n_elems, dtype=np.uint16)
+    _check(lib, lib.ssb_debug_dequant(ggml_type, raw.ctypes.data_as(C.c_void_p), raw.size, n_elems,
+                                      out.ctypes.data_as(C.POINTER(C.c_uint16))))
     return out

@@ -1,0 +1,76 @@
+"""Tensor-parallel parity on >= 2 GPUs (skipped on a 1-GPU box): TP=2 (and 4 when available) engines, one process
+per GPU, allreduce over NVLink peer memory, must reproduce the TP=1 logits up to fp32 summation order and meet the
+same oracle tolerance; every rank must produce identical token ids."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import llama_ref, synth
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from substratus_b200 import Engine, tp
+
+        e = Engine(model_dir, dict(mode, tp_size=world, tp_rank=rank, device=rank, max_batch=4, max_seq_len=160))
+        tp.connect(e)
+        toks, lg = e.generate(prompts, ngen, want_logits=True)
+        dist.barrier()
+        e.close()
+        q.put((rank, toks, lg if rank == 0 else None))
+    except Exception as ex:  # surface the failure instead of hanging the parent
+        q.put((rank, repr(ex), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}])
+def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from substratus_b200 import Engine
+
+    cfg = dict(synth.TINY_GQA, num_attention_heads=8, num_key_value_heads=4, hidden_size=1024, intermediate_size=2752)
+    sd = synth.llama_state_dict(cfg, 17)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(5)
+    prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (19, 40)]
+    ngen = 6
+    with Engine(str(tmp_path), dict(mode, max_batch=4, max_seq_len=160)) as e:
+        t1, l1 = e.generate(prompts, ngen, want_logits=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path), prompts, ngen, mode, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in ps], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+    for r, toks, _ in res:
+        assert not isinstance(toks, str), f"rank {r}: {toks}"
+        assert np.array_equal(toks, res[0][1]), f"rank {r} diverged"
+    ltp = res[0][2]
+    assert rel_err(ltp[0], l1[0]) < 5e-3
+    ref32 = llama_ref.LlamaRef(cfg, sd, torch.float32).forward(torch.tensor([prompts[1]]))[0, -1].numpy()
+    refbf = llama_ref.LlamaRef(cfg, sd, torch.bfloat16).forward(torch.tensor([prompts[1]]))[0, -1].float().numpy()
+    assert rel_err(ltp[0, 1], ref32) <= rel_err(refbf, ref32) + 1e-3
