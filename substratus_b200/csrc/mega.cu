@@ -1,0 +1,599 @@
+// mega.cu — the whole small-batch decode step as ONE persistent kernel (one CTA per SM).
+//
+// Why: at batch <= 4 every projection is a GEMV whose weights stream from HBM exactly once; with one kernel per
+// projection the HBM stream stops at every kernel boundary (drain + launch + refill ~3 us x 5 kernels x L layers,
+// measured: profiles/).  Here a producer warp per SM streams the weights of ALL phases of the step back to back
+// through one mbarrier ring (cp.async.bulk, up to 6 x 32 KiB in flight per SM) and never waits for a phase boundary;
+// the 8 consumer warps follow it through the phases
+//     embed | per layer: RMSNorm+QKV+RoPE+KV-append | paged attention | O+residual | RMSNorm+gate/up+SwiGLU |
+//     down+residual | final RMSNorm + lm_head | greedy pick
+// separated by grid-wide barriers (atomic counter in L2).  While consumers sit in a barrier or in the attention phase
+// the producer keeps the ring full, so HBM stays busy.  Math and rounding points are identical to gemv_kernel /
+// attn_decode_kernel (HF:models/llama/modeling_llama.py:62-67,138-221,292-332; HF:generation/utils.py:2762,2793).
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "kernels.h"
+#include "mega.h"
+
+constexpr int MG_CW = 8;                      // consumer warps
+constexpr int MG_THREADS = (MG_CW + 1) * 32;  // + producer warp
+constexpr int MG_ROWS = 2 * MG_CW;
+constexpr int MG_KC = 1024;
+constexpr int MG_STAGE_ELEMS = MG_ROWS * MG_KC;  // 32 KiB of bf16
+
+struct Ring {
+  int stage;
+  uint32_t phase;
+};
+
+SSB_DEVINL uint4 ldcg128(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+SSB_DEVINL unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// grid-wide barrier among the consumer threads of all CTAs (the producer warp does not take part)
+SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
+  named_bar_sync(1, MG_CW * 32);
+  ++n_done;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = n_done * n_ctas;
+    while (ld_acquire_gpu(bar) < target) {
+    }
+    __threadfence();
+  }
+  named_bar_sync(1, MG_CW * 32);
+}
+
+// ---------------------------------------------------------------- producer: stream this CTA's rows of one matrix
+SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
+                        uint64_t pol, int lane) {
+  const int P = N >> 1;
+  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  const int nk = (K + MG_KC - 1) / MG_KC;
+  for (int ps = p0; ps < p1; ps += MG_CW) {
+    const int nr = 2 * min(MG_CW, p1 - ps);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int k0 = kc * MG_KC;
+      const int len = min(MG_KC, K - k0);
+      mbar_wait(&empty[r.stage], r.phase ^ 1);
+      if (lane == 0) mbar_expect_tx(&full[r.stage], (uint32_t)(nr * len * 2));
+      __syncwarp();
+      if (lane < nr)
+        bulk_g2s_hint(tiles + ((size_t)r.stage * MG_ROWS + lane) * MG_KC, W + (size_t)(2 * ps + lane) * K + k0, (uint32_t)(len * 2),
+                      &full[r.stage], pol);
+      if (++r.stage == n_stages) {
+        r.stage = 0;
+        r.phase ^= 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- consumers: stage x (optionally RMS-normalised)
+template <int BT, int NORM>
+SSB_DEVINL void stage_x(const bf16* x, int ldx, int M, int K, const bf16* norm_w, float eps, bf16* xs, float* red, int tid, int warp,
+                        int lane) {
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    bf16* xrow = xs + (size_t)b * K;
+    if (b >= M) {
+      for (int k = tid * 8; k < K; k += MG_CW * 32 * 8) *reinterpret_cast<uint4*>(xrow + k) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const bf16* src = x + (size_t)b * ldx;
+    if constexpr (NORM == NORM_RMS) {
+      float ss = 0.f;
+      for (int k = tid * 8; k < K; k += MG_CW * 32 * 8) {
+        const uint4 v = ldcg128(src + k);
+        *reinterpret_cast<uint4*>(xrow + k) = v;  // raw copy first, normalised in place below
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = bf_lo(u[i]), hi = bf_hi(u[i]);
+          ss += lo * lo + hi * hi;
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red[warp] = ss;
+      named_bar_sync(1, MG_CW * 32);
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < MG_CW; ++w) tot += red[w];
+      named_bar_sync(1, MG_CW * 32);
+      const float rstd = rsqrtf(tot / (float)K + eps);
+      for (int k = tid * 8; k < K; k += MG_CW * 32 * 8) {  // same thread -> same elements as the copy above
+        const uint4 v = *reinterpret_cast<const uint4*>(xrow + k);
+        const uint4 w = ldg128(norm_w + k);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o[i] = pack_bf16(bf16r(bf_lo(u[i]) * rstd) * bf_lo(wu[i]), bf16r(bf_hi(u[i]) * rstd) * bf_hi(wu[i]));
+        *reinterpret_cast<uint4*>(xrow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      for (int k = tid * 8; k < K; k += MG_CW * 32 * 8) *reinterpret_cast<uint4*>(xrow + k) = ldcg128(src + k);
+    }
+  }
+  named_bar_sync(1, MG_CW * 32);
+}
+
+// ---------------------------------------------------------------- consumers: one projection (same loop as gemv_kernel)
+template <int BT, int EPI>
+SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
+                        int warp, int lane) {
+  const int K = a.K;
+  const int P = a.N >> 1;
+  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  const int nk = (K + MG_KC - 1) / MG_KC;
+  for (int ps = p0; ps < p1; ps += MG_CW) {
+    const int pair = ps + warp;
+    const bool valid = pair < p1;
+    float acc0[BT], acc1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc0[b] = acc1[b] = 0.f;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int k0 = kc * MG_KC;
+      const int len = min(MG_KC, K - k0);
+      mbar_wait(&full[r.stage], r.phase);
+      if (valid) {
+        const bf16* w0 = tiles + ((size_t)r.stage * MG_ROWS + 2 * warp) * MG_KC;
+        const bf16* w1 = w0 + MG_KC;
+        for (int c = lane * 8; c < len; c += 256) {
+          const uint4 a0 = *reinterpret_cast<const uint4*>(w0 + c);
+          const uint4 a1 = *reinterpret_cast<const uint4*>(w1 + c);
+          const uint32_t u0[4] = {a0.x, a0.y, a0.z, a0.w};
+          const uint32_t u1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int b = 0; b < BT; ++b) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + k0 + c);
+            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
+              acc0[b] = fmaf(bf_lo(u0[i]), xl, acc0[b]);
+              acc0[b] = fmaf(bf_hi(u0[i]), xh, acc0[b]);
+              acc1[b] = fmaf(bf_lo(u1[i]), xl, acc1[b]);
+              acc1[b] = fmaf(bf_hi(u1[i]), xh, acc1[b]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[r.stage]);
+      if (++r.stage == n_stages) {
+        r.stage = 0;
+        r.phase ^= 1;
+      }
+    }
+    if (valid) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float s0 = warp_sum(acc0[b]);
+        const float s1 = warp_sum(acc1[b]);
+        if (lane == b) {
+          v0 = s0;
+          v1 = s1;
+        }
+      }
+      if (lane < BT && lane < a.M) gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- consumers: paged attention, one (row, head unit, 16-token
+// chunk) per warp; all K/V loads of the chunk are issued before any is consumed; the last-arriving warp of a
+// (row, head unit) merges the chunk partials.
+template <int D, int G>
+SSB_DEVINL void attention_phase(const MegaArgs& a, const bf16* kcache, const bf16* vcache, int warp, int lane) {
+  constexpr int LPR = D / 8, RPW = 32 / LPR;
+  constexpr int UNR = (G <= 2) ? 8 : 2;
+  constexpr int CH = RPW * UNR;  // tokens per unit
+  const int HU = a.n_heads / G;  // head units per row
+  const int sub = lane / LPR, li = lane % LPR;
+  const int HD = a.n_heads * D;
+  const int BS = a.block_size;
+  const int gw = blockIdx.x * MG_CW + warp, nw = gridDim.x * MG_CW;
+  // units are enumerated row-major: (m, hu, chunk); chunk counts differ per row (ragged contexts)
+  int base = 0;
+  for (int m = 0; m < a.M; ++m) {
+    const int ctx = __ldcg(a.row_pos + m) + 1;
+    const int n_chunks = (ctx + CH - 1) / CH;
+    const int n_units = HU * n_chunks;
+    const int slot = a.row_slot[m];
+    const int* bt = a.block_table + (size_t)slot * a.bt_stride;
+    // first unit index of this row owned by this warp
+    int u = ((gw - base) % nw + nw) % nw;
+    for (; u < n_units; u += nw) {
+      const int hu = u / n_chunks, ck = u - hu * n_chunks;
+      const int kvh = (hu * G) / a.group;
+      const int t0 = ck * CH;
+      float q[G][8];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint4 v = ldcg128(a.q + (size_t)m * HD + (hu * G + g) * D + li * 8);
+        const uint32_t uu[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q[g][2 * i] = bf_lo(uu[i]);
+          q[g][2 * i + 1] = bf_hi(uu[i]);
+        }
+      }
+      uint4 kq[UNR], vq[UNR];
+      bool tvq[UNR];
+#pragma unroll
+      for (int x = 0; x < UNR; ++x) {
+        const int t = t0 + x * RPW + sub;
+        tvq[x] = t < ctx;
+        kq[x] = make_uint4(0, 0, 0, 0);
+        vq[x] = make_uint4(0, 0, 0, 0);
+        if (tvq[x]) {
+          const int blk = bt[t / BS];
+          const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
+          kq[x] = ldcg128(kcache + off);
+          vq[x] = ldcg128(vcache + off);
+        }
+      }
+      float mx[G], l[G], acc[G][8];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        mx[g] = -1e30f;
+        l[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < UNR; ++x) {
+        const uint32_t ku[4] = {kq[x].x, kq[x].y, kq[x].z, kq[x].w};
+        const uint32_t vu[4] = {vq[x].x, vq[x].y, vq[x].z, vq[x].w};
+        float kf[8], vf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          kf[2 * i] = bf_lo(ku[i]);
+          kf[2 * i + 1] = bf_hi(ku[i]);
+          vf[2 * i] = bf_lo(vu[i]);
+          vf[2 * i + 1] = bf_hi(vu[i]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (!tvq[x]) continue;
+          const float s = bf16r(bf16r(d) * a.scale);
+          const float mn = fmaxf(mx[g], s);
+          const float corr = __expf(mx[g] - mn);
+          const float p = __expf(s - mn);
+          mx[g] = mn;
+          l[g] = l[g] * corr + p;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(p, vf[i], acc[g][i] * corr);
+        }
+      }
+      // merge the RPW sub-groups of the warp (lanes li + k*LPR hold the same dims of different tokens)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, mx[g], o);
+          const float ol = __shfl_xor_sync(0xffffffffu, l[g], o);
+          const float mn = fmaxf(mx[g], om);
+          const float wa = __expf(mx[g] - mn), wb = __expf(om - mn);
+          l[g] = l[g] * wa + ol * wb;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float oa = __shfl_xor_sync(0xffffffffu, acc[g][i], o);
+            acc[g][i] = acc[g][i] * wa + oa * wb;
+          }
+          mx[g] = mn;
+        }
+      }
+      const size_t pidx = ((size_t)m * HU + hu) * a.max_chunks + ck;
+      if (n_chunks == 1) {
+        if (sub == 0) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const float inv = 1.0f / l[g];
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = pack_bf16(acc[g][2 * i] * inv, acc[g][2 * i + 1] * inv);
+            *reinterpret_cast<uint4*>(a.attn + (size_t)m * HD + (hu * G + g) * D + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        continue;
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float* po = a.part_o + (pidx * G + g) * D + li * 8;
+          *reinterpret_cast<float4*>(po) = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+          *reinterpret_cast<float4*>(po + 4) = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+          if (li == 0) {
+            a.part_ml[(pidx * G + g) * 2] = mx[g];
+            a.part_ml[(pidx * G + g) * 2 + 1] = l[g];
+          }
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = (atomicAdd(&a.counters[m * HU + hu], 1) == n_chunks - 1);
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) continue;
+      __threadfence();
+      // this warp merges all chunks of (m, hu): lane handles 4 consecutive dims of head g = lane / (D/4) (+ stride)
+      const size_t pb = ((size_t)m * HU + hu) * a.max_chunks;
+      for (int e = lane * 4; e < G * D; e += 128) {
+        const int g = e / D, dd = e % D;
+        float M2 = -1e30f;
+        for (int c = 0; c < n_chunks; ++c) M2 = fmaxf(M2, __ldcg(&a.part_ml[((pb + c) * G + g) * 2]));
+        float L2 = 0.f;
+        float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < n_chunks; ++c) {
+          const float w = __expf(__ldcg(&a.part_ml[((pb + c) * G + g) * 2]) - M2);
+          L2 += __ldcg(&a.part_ml[((pb + c) * G + g) * 2 + 1]) * w;
+          const float4 o = __ldcg(reinterpret_cast<const float4*>(a.part_o + ((pb + c) * G + g) * D + dd));
+          O.x += o.x * w;
+          O.y += o.y * w;
+          O.z += o.z * w;
+          O.w += o.w * w;
+        }
+        const float inv = 1.0f / L2;
+        uint2 o;
+        o.x = pack_bf16(O.x * inv, O.y * inv);
+        o.y = pack_bf16(O.z * inv, O.w * inv);
+        *reinterpret_cast<uint2*>(a.attn + (size_t)m * HD + (hu * G + g) * D + dd) = o;
+      }
+      if (lane == 0) a.counters[m * HU + hu] = 0;
+    }
+    base = (base + n_units) % nw;
+  }
+}
+
+template <int BT, int D, int G>
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  bf16* tiles = reinterpret_cast<bf16*>(smem_raw);
+  bf16* xs = tiles + (size_t)a.n_stages * MG_STAGE_ELEMS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t)BT * a.k_max);
+  uint64_t* empty = full + a.n_stages;
+  float* red = reinterpret_cast<float*>(empty + a.n_stages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = a.hidden;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], MG_CW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  Ring r = {0, 0};
+
+  if (warp == MG_CW) {
+    // ================================================================ producer: every weight byte of the step, in order
+    const uint64_t pol = policy_evict_first();
+    for (int l = 0; l < a.n_layers; ++l) {
+      const MegaLayer& w = a.layers[l];
+      produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane);
+      produce(w.wo, h, a.q_rows, tiles, full, empty, a.n_stages, r, pol, lane);
+      produce(w.wgu, 2 * a.inter, h, tiles, full, empty, a.n_stages, r, pol, lane);
+      produce(w.wdown, h, a.inter, tiles, full, empty, a.n_stages, r, pol, lane);
+    }
+    produce(a.lm_head, a.vocab, h, tiles, full, empty, a.n_stages, r, pol, lane);
+    return;
+  }
+
+  // ================================================================== consumers
+  pdl_wait();
+  unsigned n_sync = 0;
+  const unsigned n_ctas = gridDim.x;
+  if (blockIdx.x == 0 && tid == 0) {
+    *a.step += 1;
+    if (a.fwd_counter) *a.fwd_counter += 1;
+  }
+  // embedding gather, distributed over all consumer threads of the grid
+  {
+    const int per_row = h / 8;
+    for (int i = blockIdx.x * (MG_CW * 32) + tid; i < a.M * per_row; i += n_ctas * MG_CW * 32) {
+      const int m = i / per_row, c = i - m * per_row;
+      *reinterpret_cast<uint4*>(a.h + (size_t)m * h + c * 8) = ldg128(a.embed + (size_t)a.row_tok[m] * h + c * 8);
+    }
+  }
+  grid_sync(a.grid_bar, n_sync, n_ctas);
+
+  GemvArgs g = {};
+  g.M = a.M;
+  g.eps = a.eps;
+  g.head_dim = D;
+  g.q_rows = a.q_rows;
+  g.kv_rows = a.kv_rows;
+  g.block_table = a.block_table;
+  g.bt_stride = a.bt_stride;
+  g.row_slot = a.row_slot;
+  g.row_pos = a.row_pos;
+  g.rope_cs = a.rope_cs;
+  g.block_size = a.block_size;
+  g.kvh = a.kvh;
+  g.q_out = a.q;
+
+  for (int l = 0; l < a.n_layers; ++l) {
+    const MegaLayer& w = a.layers[l];
+    // ---- RMSNorm + QKV + RoPE + KV append
+    stage_x<BT, NORM_RMS>(a.h, h, a.M, h, w.ln1, a.eps, xs, red, tid, warp, lane);
+    g.N = a.q_rows + 2 * a.kv_rows;
+    g.K = h;
+    g.kcache = w.kcache;
+    g.vcache = w.vcache;
+    consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    grid_sync(a.grid_bar, n_sync, n_ctas);
+    // ---- attention
+    attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+    grid_sync(a.grid_bar, n_sync, n_ctas);
+    // ---- O projection + residual
+    stage_x<BT, NORM_NONE>(a.attn, a.q_rows, a.M, a.q_rows, nullptr, 0.f, xs, red, tid, warp, lane);
+    g.N = h;
+    g.K = a.q_rows;
+    g.out_bf16 = a.h;
+    g.resid = a.h;
+    g.ld_out = h;
+    consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    grid_sync(a.grid_bar, n_sync, n_ctas);
+    // ---- RMSNorm + gate/up + SwiGLU
+    stage_x<BT, NORM_RMS>(a.h, h, a.M, h, w.ln2, a.eps, xs, red, tid, warp, lane);
+    g.N = 2 * a.inter;
+    g.K = h;
+    g.out_bf16 = a.act;
+    g.ld_out = a.inter;
+    consume<BT, EPI_SWIGLU>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    grid_sync(a.grid_bar, n_sync, n_ctas);
+    // ---- down projection + residual
+    stage_x<BT, NORM_NONE>(a.act, a.inter, a.M, a.inter, nullptr, 0.f, xs, red, tid, warp, lane);
+    g.N = h;
+    g.K = a.inter;
+    g.out_bf16 = a.h;
+    g.resid = a.h;
+    g.ld_out = h;
+    consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    grid_sync(a.grid_bar, n_sync, n_ctas);
+  }
+  // ---- final norm + lm_head
+  stage_x<BT, NORM_RMS>(a.h, h, a.M, h, a.final_norm, a.eps, xs, red, tid, warp, lane);
+  g.N = a.vocab;
+  g.K = h;
+  g.out_f32 = a.logits;
+  g.ld_out = a.vocab;
+  consume<BT, EPI_F32_BF16R>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+  grid_sync(a.grid_bar, n_sync, n_ctas);
+  // ---- greedy pick: CTA m handles row m (lowest index wins ties)
+  if ((int)blockIdx.x < a.M) {
+    const int m = blockIdx.x;
+    const float* lg = a.logits + (size_t)m * a.vocab;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < a.vocab; i += MG_CW * 32) {
+      const float v = __ldcg(lg + i);
+      if (v > best || (v == best && i < bi)) {
+        best = v;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    float* sv = red;                                     // [8] floats
+    int* si = reinterpret_cast<int*>(red + MG_CW);       // [8] ints
+    if (lane == 0) {
+      sv[warp] = best;
+      si[warp] = bi;
+    }
+    named_bar_sync(1, MG_CW * 32);
+    if (tid == 0) {
+      for (int w2 = 1; w2 < MG_CW; ++w2)
+        if (sv[w2] > best || (sv[w2] == best && si[w2] < bi)) {
+          best = sv[w2];
+          bi = si[w2];
+        }
+      a.row_tok[m] = bi;
+      a.hist[(size_t)(__ldcg(a.step)) * a.M + m] = bi;
+      a.row_pos[m] += 1;
+    }
+  }
+  // leave the barrier counter at zero for the next launch: the last CTA through resets it
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(a.grid_bar + 1, 1u) == n_ctas - 1) {
+      a.grid_bar[0] = 0;
+      a.grid_bar[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+size_t mega_smem_bytes(int bt, int k_max, int n_stages) {
+  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128;
+}
+
+int mega_pick_stages(int bt, int k_max) {
+  int s = 6;
+  while (s > 2 && mega_smem_bytes(bt, k_max, s) > 225 * 1024) --s;
+  return mega_smem_bytes(bt, k_max, s) <= 225 * 1024 ? s : 0;
+}
+
+template <int BT, int D, int G>
+static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
+  const size_t smem = mega_smem_bytes(BT, a.k_max, a.n_stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(lc.n_sm);
+  cfg.blockDim = dim3(MG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident (grid-wide barriers)
+  attr[na].val.cooperative = 1;
+  ++na;
+  if (lc.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, decode_mega_kernel<BT, D, G>, a);
+}
+
+template <int BT>
+static cudaError_t launch_mega_b(const MegaArgs& a, const LaunchCfg& lc) {
+  const int g = a.attn_g;
+  if (a.head_dim == 128) {
+    switch (g) {
+      case 1: return launch_mega_t<BT, 128, 1>(a, lc);
+      case 2: return launch_mega_t<BT, 128, 2>(a, lc);
+      case 4: return launch_mega_t<BT, 128, 4>(a, lc);
+      case 8: return launch_mega_t<BT, 128, 8>(a, lc);
+    }
+  } else if (a.head_dim == 64) {
+    switch (g) {
+      case 1: return launch_mega_t<BT, 64, 1>(a, lc);
+      case 2: return launch_mega_t<BT, 64, 2>(a, lc);
+      case 4: return launch_mega_t<BT, 64, 4>(a, lc);
+      case 8: return launch_mega_t<BT, 64, 8>(a, lc);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc) {
+  if (a.M < 1 || a.M > 4 || a.n_stages < 2) return cudaErrorInvalidValue;
+  if (a.M == 1) return launch_mega_b<1>(a, lc);
+  if (a.M == 2) return launch_mega_b<2>(a, lc);
+  return launch_mega_b<4>(a, lc);
+}
+
+int mega_attn_group(int group) { return (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1; }
+int mega_attn_chunk(int head_dim, int g) { return (32 / (head_dim / 8)) * (g <= 2 ? 8 : 2); }

@@ -1,0 +1,38 @@
+// mega.h — launch API of the persistent single-kernel decode step (mega.cu).
+#pragma once
+#include "kernels.h"
+
+struct MegaLayer {
+  const bf16 *wqkv, *wo, *wgu, *wdown, *ln1, *ln2;
+  bf16 *kcache, *vcache;
+};
+
+struct MegaArgs {
+  const MegaLayer* layers;  // device array [n_layers]
+  int n_layers;
+  int hidden, q_rows, kv_rows, head_dim, inter, vocab;
+  int n_heads, kvh, group, attn_g;  // attn_g = query heads per attention unit (all share one KV head)
+  float eps, scale;
+  int M;  // batch rows (1..4)
+  const bf16 *embed, *lm_head, *final_norm;
+  bf16 *h, *q, *attn, *act;
+  float* logits;
+  int* row_tok;
+  const int* row_slot;
+  int* row_pos;
+  const int* block_table;
+  int bt_stride, block_size;
+  const uint32_t* rope_cs;
+  float *part_o, *part_ml;  // [M][n_heads/attn_g][max_chunks][attn_g*D], [..][attn_g*2]
+  int* counters;            // [M][n_heads/attn_g], zero on entry and on exit
+  int max_chunks;
+  int *hist, *step, *fwd_counter;
+  unsigned* grid_bar;  // [2], zero on entry and on exit
+  int n_stages, k_max;
+};
+
+size_t mega_smem_bytes(int bt, int k_max, int n_stages);
+int mega_pick_stages(int bt, int k_max);  // 0 if the step does not fit
+int mega_attn_group(int group);
+int mega_attn_chunk(int head_dim, int g);  // tokens per attention unit
+cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc);
