@@ -391,6 +391,35 @@ int Engine::alloc_runtime(const Json& params) {
   free_blocks_.resize(n_blocks_);
   for (int i = 0; i < n_blocks_; ++i) free_blocks_[i] = n_blocks_ - 1 - i;
   slots_.assign(max_batch_, SeqSlot());
+  // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
+  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1;
+  if (use_mega_) {
+    const int group = cfg_.heads / cfg_.kv_heads, ag = mega_attn_group(group);
+    const int ch = mega_attn_chunk(D, ag);
+    mega_max_chunks_ = (max_seq_ + ch - 1) / ch;
+    mega_k_max_ = std::max(h, std::max(Hl_ * D, Il_));
+    if (mega_pick_stages(1, mega_k_max_) == 0) {
+      use_mega_ = false;
+    } else {
+      std::vector<MegaLayer> ml(cfg_.layers);
+      for (int l = 0; l < cfg_.layers; ++l)
+        ml[l] = MegaLayer{lw_[l].wqkv, lw_[l].wo, lw_[l].wgu, lw_[l].wdown, lw_[l].ln1, lw_[l].ln2,
+                          kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_};
+      TRY(dmalloc(&d_mega_layers_, ml.size()));
+      CK(cudaMemcpy(d_mega_layers_, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+      const size_t units = (size_t)4 * (Hl_ / ag) * mega_max_chunks_;
+      TRY(dmalloc(&mega_part_o_, units * ag * D));
+      TRY(dmalloc(&mega_part_ml_, units * ag * 2));
+      TRY(dmalloc(&mega_counters_, (size_t)4 * Hl_));
+      CK(cudaMemset(mega_counters_, 0, (size_t)4 * Hl_ * sizeof(int)));
+      if (params.get_int("mega_prof", 0)) {
+        TRY(dmalloc(&mega_prof_, 1024));
+        CK(cudaMemset(mega_prof_, 0, 1024 * sizeof(unsigned long long)));
+      }
+      TRY(dmalloc(&mega_bar_, 2));
+      CK(cudaMemset(mega_bar_, 0, 2 * sizeof(unsigned)));
+    }
+  }
   return SSB_OK;
 }
 
@@ -789,6 +818,57 @@ int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, 
   return SSB_OK;
 }
 
+int Engine::forward_mega(int B) {
+  const int D = cfg_.head_dim, group = cfg_.heads / cfg_.kv_heads;
+  MegaArgs a = {};
+  a.layers = d_mega_layers_;
+  a.n_layers = cfg_.layers;
+  a.hidden = cfg_.hidden;
+  a.q_rows = Hl_ * D;
+  a.kv_rows = KVHl_ * D;
+  a.head_dim = D;
+  a.inter = Il_;
+  a.vocab = cfg_.vocab;
+  a.n_heads = Hl_;
+  a.kvh = KVHl_;
+  a.group = group;
+  a.attn_g = mega_attn_group(group);
+  a.eps = cfg_.eps;
+  a.scale = 1.0f / sqrtf((float)D);
+  a.M = B;
+  a.embed = embed_;
+  a.lm_head = lm_head_;
+  a.final_norm = final_norm_;
+  a.h = h_;
+  a.q = q_;
+  a.attn = attn_;
+  a.act = act_;
+  a.logits = logits_;
+  a.row_tok = row_tok_;
+  a.row_slot = row_slot_;
+  a.row_pos = row_pos_;
+  a.block_table = block_table_;
+  a.bt_stride = max_blocks_per_seq_;
+  a.block_size = block_size_;
+  a.rope_cs = rope_cs_;
+  a.part_o = mega_part_o_;
+  a.part_ml = mega_part_ml_;
+  a.counters = mega_counters_;
+  a.max_chunks = mega_max_chunks_;
+  a.hist = hist_;
+  a.step = step_;
+  a.fwd_counter = tp_step_;
+  a.grid_bar = mega_bar_;
+  a.k_max = mega_k_max_;
+  a.prof = mega_prof_;
+  a.n_stages = mega_pick_stages(B == 1 ? 1 : (B == 2 ? 2 : 4), mega_k_max_);
+  if (a.n_stages == 0) RET(SSB_EINVAL, "decode step does not fit the persistent kernel's shared memory");
+  CK(launch_decode_mega(a, LaunchCfg{stream_, false, n_sm_}));
+  launches_per_forward_ = 1;
+  timing_.kernel_launches += 1;
+  return SSB_OK;
+}
+
 int Engine::build_graph(int B) {
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
@@ -829,14 +909,17 @@ int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int ns
   CK(cudaMemcpyAsync(row_pos_, pos.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
   CK(cudaMemsetAsync(step_, 0xFF, sizeof(int), stream_));  // -1: the embed kernel pre-increments
   timing_.h2d_bytes += 3LL * nseq * sizeof(int);
-  const bool graph = use_graph_ && !taps_;
+  const bool mega = use_mega_ && !taps_ && nseq <= 4 && nseq < tc_min_rows_ && mega_pick_stages(nseq == 1 ? 1 : (nseq == 2 ? 2 : 4), mega_k_max_) > 0;
+  const bool graph = use_graph_ && !taps_ && !mega;
   if (graph && !graphs_.count(nseq)) {
     CK(cudaStreamSynchronize(stream_));
     TRY(build_graph(nseq));
   }
   CK(cudaEventRecord(ev0_, stream_));
   for (int s = 0; s < nsteps; ++s) {
-    if (graph) {
+    if (mega) {
+      TRY(forward_mega(nseq));
+    } else if (graph) {
       CK(cudaGraphLaunch(graphs_[nseq], stream_));
       timing_.kernel_launches += launches_per_forward_;
     } else {
@@ -868,7 +951,14 @@ int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int ns
 int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double* ms_out, int64_t* bytes_out) {
   if (rows < 1 || rows > max_batch_ || iters < 1) RET(SSB_EINVAL, "bad rows/iters");
   CK(cudaSetDevice(device_));
-  const std::string w = which ? which : "";
+  std::string w = which ? which : "";
+  // "<name>@l2": reuse layer 0's weights every launch (L2-resident when the matrix fits the 126 MB L2) — separates the
+  // kernel's own consumption rate from the HBM rate
+  bool same_layer = false;
+  if (w.size() > 3 && w.compare(w.size() - 3, 3, "@l2") == 0) {
+    same_layer = true;
+    w.resize(w.size() - 3);
+  }
   const int h = cfg_.hidden, D = cfg_.head_dim;
   // stage a decode-like batch: rows sequences of length ctx (slots 0..rows-1 must be free)
   std::vector<int> sl(rows), tok(rows, 1), pos(rows, ctx - 1);
@@ -896,6 +986,7 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
   }
   int64_t bytes = 0;
   auto one = [&](int l) -> int {
+    if (same_layer) l = 0;
     const LayerW& lwv = lw_[l % cfg_.layers];
     GemvArgs g = {};
     g.x = h_;
@@ -1084,9 +1175,21 @@ int Engine::last_timing(ssb_timing* t) const {
 void Engine::timing_reset() { timing_ = ssb_timing{}; }
 
 int Engine::debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols) {
+  const std::string nm = name ? name : "";
+  if (nm == "mega_prof") {  // phase timestamps of CTA 0 of the LAST persistent decode step, in microseconds from its start
+    if (!mega_prof_) RET(SSB_ESTATE, "engine was not created with params.mega_prof=1");
+    if (n < 1024) RET(SSB_EINVAL, "destination too small");
+    std::vector<unsigned long long> t(1024);
+    CK(cudaMemcpy(t.data(), mega_prof_, 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    int cnt = 0;
+    while (cnt < 1024 && t[cnt] != 0) ++cnt;
+    for (int i = 0; i < cnt; ++i) dst[i] = (float)((double)(t[i] - t[0]) * 1e-3);
+    *rows = 1;
+    *cols = cnt;
+    return SSB_OK;
+  }
   if (!taps_) RET(SSB_ESTATE, "engine was not created with params.debug_taps=1");
   CK(cudaSetDevice(device_));
-  const std::string nm = name ? name : "";
   const bf16* src = nullptr;
   int c = 0;
   if (nm == "q0") {

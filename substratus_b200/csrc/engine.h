@@ -11,6 +11,7 @@
 #include "json.h"
 #include "kernels.h"
 #include "loader.h"
+#include "mega.h"
 #include "tc_gemm.h"
 
 namespace ssb {
@@ -64,6 +65,7 @@ class Engine {
   int upload_block_rows(const std::vector<int>& slots);
   int forward(int M, int n_logit_rows, bool decode_mode);  // enqueue one forward over the staged rows
   int build_graph(int B);
+  int forward_mega(int B);  // one persistent kernel for the whole decode step (B <= 4, single rank)
   LaunchCfg lc(bool pdl) const { return LaunchCfg{stream_, pdl && use_pdl_, n_sm_}; }
 
   ModelCfg cfg_;
@@ -71,6 +73,13 @@ class Engine {
   int Hl_ = 0, KVHl_ = 0, Il_ = 0;  // per-rank heads / kv heads / intermediate
   int max_batch_ = 32, max_seq_ = 4096, block_size_ = 16, n_blocks_ = 0, max_blocks_per_seq_ = 0, m_max_ = 0;
   bool use_pdl_ = true, use_graph_ = true, taps_ = false;
+  bool use_mega_ = true;
+  MegaLayer* d_mega_layers_ = nullptr;
+  float *mega_part_o_ = nullptr, *mega_part_ml_ = nullptr;
+  int* mega_counters_ = nullptr;
+  unsigned* mega_bar_ = nullptr;
+  unsigned long long* mega_prof_ = nullptr;
+  int mega_max_chunks_ = 0, mega_k_max_ = 0;
   int tc_min_rows_ = 8;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

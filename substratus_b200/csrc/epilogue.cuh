@@ -20,7 +20,7 @@ SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, floa
     *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)m * a.ld_out + 2 * pair) = pack_bf16(v0, v1);
   } else if constexpr (EPI == EPI_RESID) {
     size_t o = (size_t)m * a.ld_out + 2 * pair;
-    uint32_t r = *reinterpret_cast<const uint32_t*>(a.resid + o);
+    uint32_t r = __ldcg(reinterpret_cast<const uint32_t*>(a.resid + o));  // L2: other CTAs/phases write h
     *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(bf16r(v0) + bf_lo(r), bf16r(v1) + bf_hi(r));
   } else if constexpr (EPI == EPI_SWIGLU) {
     float g = bf16r(v0), u = bf16r(v1);
@@ -29,7 +29,7 @@ SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, floa
   } else if constexpr (EPI == EPI_QKV_ROPE) {
     const int hd = a.head_dim, half = hd >> 1;
     const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
-    const int pos = a.row_pos[m];
+    const int pos = __ldcg(a.row_pos + m);
     if (pair < q_pairs + k_pairs) {
       const bool is_q = pair < q_pairs;
       const int pp = is_q ? pair : pair - q_pairs;

@@ -20,7 +20,9 @@
 // gemv_kernel
 // =====================================================================================================================
 constexpr int GV_CW = 8;                        // consumer warps
-constexpr int GV_THREADS = (GV_CW + 1) * 32;    // + 1 producer warp
+constexpr int GV_PW = 4;                        // producer warps: the compiler lowers per-lane cp.async.bulk to a serial
+                                                // ELECT loop (~70 cycles per copy), so one warp tops out near 29 B/clk/SM
+constexpr int GV_THREADS = (GV_CW + GV_PW) * 32;
 constexpr int GV_ROWS = 2 * GV_CW;              // weight rows per stage (each consumer warp owns one row pair)
 constexpr int GV_KC = 1024;                     // K elements per stage
 constexpr int GV_STAGES = 3;                    // 3 x 32 KiB in flight per SM
@@ -35,6 +37,7 @@ int gemv_pick_bt(int M, int K) {
 }
 
 #include "epilogue.cuh"
+#include "gemv_core.cuh"
 
 template <int BT, int EPI, int NORM>
 __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < GV_STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], GV_PW);
       mbar_init(&empty[s], GV_CW);
     }
     fence_mbar_init();
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
   __syncthreads();
   pdl_launch_dependents();
 
-  if (warp == GV_CW) {
+  if (warp >= GV_CW) {
     // ------------------------------------------------------------ producer: weights never depend on the previous
     // kernel, so the stream from HBM starts before griddepcontrol.wait (PDL prologue overlap).
     const uint64_t pol = policy_evict_first();
@@ -75,10 +78,14 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
         const int k0 = kc * GV_KC;
         const int len = min(GV_KC, K - k0);
         mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) mbar_expect_tx(&full[stage], (uint32_t)(nr * len * 2));
+        // producer warp pw owns rows [pw*RPP, (pw+1)*RPP) of the stage
+        constexpr int RPP = GV_ROWS / GV_PW;
+        const int r0 = (warp - GV_CW) * RPP;
+        const int mine = max(0, min(RPP, nr - r0));
+        if (lane == 0) mbar_expect_tx(&full[stage], (uint32_t)(mine * len * 2));
         __syncwarp();
-        if (lane < nr)
-          bulk_g2s_hint(tiles + ((size_t)stage * GV_ROWS + lane) * GV_KC, a.W + (size_t)(2 * ps + lane) * K + k0,
+        if (lane < mine)
+          bulk_g2s_hint(tiles + ((size_t)stage * GV_ROWS + r0 + lane) * GV_KC, a.W + (size_t)(2 * ps + r0 + lane) * K + k0,
                         (uint32_t)(len * 2), &full[stage], pol);
         if (++stage == GV_STAGES) {
           stage = 0;
@@ -155,25 +162,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
         if (valid) {
           const bf16* w0 = tiles + ((size_t)stage * GV_ROWS + 2 * warp) * GV_KC;
           const bf16* w1 = w0 + GV_KC;
-          for (int c = lane * 8; c < len; c += 256) {
-            const uint4 a0 = *reinterpret_cast<const uint4*>(w0 + c);
-            const uint4 a1 = *reinterpret_cast<const uint4*>(w1 + c);
-            const uint32_t u0[4] = {a0.x, a0.y, a0.z, a0.w};
-            const uint32_t u1[4] = {a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + k0 + c);
-              const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
-                acc0[b] = fmaf(bf_lo(u0[i]), xl, acc0[b]);
-                acc0[b] = fmaf(bf_hi(u0[i]), xh, acc0[b]);
-                acc1[b] = fmaf(bf_lo(u1[i]), xl, acc1[b]);
-                acc1[b] = fmaf(bf_hi(u1[i]), xh, acc1[b]);
-              }
-            }
-          }
+          gemv_chunk<BT>(w0, w1, xs, K, k0, len, lane, acc0, acc1);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);

@@ -12,11 +12,13 @@
 // attn_decode_kernel (HF:models/llama/modeling_llama.py:62-67,138-221,292-332; HF:generation/utils.py:2762,2793).
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "gemv_core.cuh"
 #include "kernels.h"
 #include "mega.h"
 
 constexpr int MG_CW = 8;                      // consumer warps
-constexpr int MG_THREADS = (MG_CW + 1) * 32;  // + producer warp
+constexpr int MG_PW = 4;                      // producer warps (one warp issues ~1 bulk copy / 70 cycles: see kernels.cu)
+constexpr int MG_THREADS = (MG_CW + MG_PW) * 32;
 constexpr int MG_ROWS = 2 * MG_CW;
 constexpr int MG_KC = 1024;
 constexpr int MG_STAGE_ELEMS = MG_ROWS * MG_KC;  // 32 KiB of bf16
@@ -32,6 +34,16 @@ SSB_DEVINL unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+SSB_DEVINL unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MG_STAMP()                                                          \
+  do {                                                                      \
+    if (a.prof && blockIdx.x == 0 && tid == 0 && n_prof < 1024) a.prof[n_prof++] = gtimer(); \
+  } while (0)
 
 // grid-wide barrier among the consumer threads of all CTAs (the producer warp does not take part)
 SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
@@ -50,7 +62,7 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
 
 // ---------------------------------------------------------------- producer: stream this CTA's rows of one matrix
 SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        uint64_t pol, int lane) {
+                        uint64_t pol, int lane, int pw) {
   const int P = N >> 1;
   const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
   const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
@@ -61,11 +73,14 @@ SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
       mbar_wait(&empty[r.stage], r.phase ^ 1);
-      if (lane == 0) mbar_expect_tx(&full[r.stage], (uint32_t)(nr * len * 2));
+      constexpr int RPP = MG_ROWS / MG_PW;
+      const int r0 = pw * RPP;
+      const int mine = max(0, min(RPP, nr - r0));
+      if (lane == 0) mbar_expect_tx(&full[r.stage], (uint32_t)(mine * len * 2));
       __syncwarp();
-      if (lane < nr)
-        bulk_g2s_hint(tiles + ((size_t)r.stage * MG_ROWS + lane) * MG_KC, W + (size_t)(2 * ps + lane) * K + k0, (uint32_t)(len * 2),
-                      &full[r.stage], pol);
+      if (lane < mine)
+        bulk_g2s_hint(tiles + ((size_t)r.stage * MG_ROWS + r0 + lane) * MG_KC, W + (size_t)(2 * ps + r0 + lane) * K + k0,
+                      (uint32_t)(len * 2), &full[r.stage], pol);
       if (++r.stage == n_stages) {
         r.stage = 0;
         r.phase ^= 1;
@@ -146,25 +161,7 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
       if (valid) {
         const bf16* w0 = tiles + ((size_t)r.stage * MG_ROWS + 2 * warp) * MG_KC;
         const bf16* w1 = w0 + MG_KC;
-        for (int c = lane * 8; c < len; c += 256) {
-          const uint4 a0 = *reinterpret_cast<const uint4*>(w0 + c);
-          const uint4 a1 = *reinterpret_cast<const uint4*>(w1 + c);
-          const uint32_t u0[4] = {a0.x, a0.y, a0.z, a0.w};
-          const uint32_t u1[4] = {a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int b = 0; b < BT; ++b) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + k0 + c);
-            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
-              acc0[b] = fmaf(bf_lo(u0[i]), xl, acc0[b]);
-              acc0[b] = fmaf(bf_hi(u0[i]), xh, acc0[b]);
-              acc1[b] = fmaf(bf_lo(u1[i]), xl, acc1[b]);
-              acc1[b] = fmaf(bf_hi(u1[i]), xh, acc1[b]);
-            }
-          }
-        }
+        gemv_chunk<BT>(w0, w1, xs, K, k0, len, lane, acc0, acc1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[r.stage]);
@@ -373,7 +370,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 
   if (tid == 0) {
     for (int s = 0; s < a.n_stages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], MG_PW);
       mbar_init(&empty[s], MG_CW);
     }
     fence_mbar_init();
@@ -382,22 +379,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   pdl_launch_dependents();
   Ring r = {0, 0};
 
-  if (warp == MG_CW) {
-    // ================================================================ producer: every weight byte of the step, in order
+  if (warp >= MG_CW) {
+    // ================================================================ producers: every weight byte of the step, in order
     const uint64_t pol = policy_evict_first();
+    const int pw = warp - MG_CW;
     for (int l = 0; l < a.n_layers; ++l) {
       const MegaLayer& w = a.layers[l];
-      produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane);
-      produce(w.wo, h, a.q_rows, tiles, full, empty, a.n_stages, r, pol, lane);
-      produce(w.wgu, 2 * a.inter, h, tiles, full, empty, a.n_stages, r, pol, lane);
-      produce(w.wdown, h, a.inter, tiles, full, empty, a.n_stages, r, pol, lane);
+      produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
+      produce(w.wo, h, a.q_rows, tiles, full, empty, a.n_stages, r, pol, lane, pw);
+      produce(w.wgu, 2 * a.inter, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
+      produce(w.wdown, h, a.inter, tiles, full, empty, a.n_stages, r, pol, lane, pw);
     }
-    produce(a.lm_head, a.vocab, h, tiles, full, empty, a.n_stages, r, pol, lane);
+    produce(a.lm_head, a.vocab, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
     return;
   }
 
   // ================================================================== consumers
   pdl_wait();
+  int n_prof = 0;
+  MG_STAMP();
   unsigned n_sync = 0;
   const unsigned n_ctas = gridDim.x;
   if (blockIdx.x == 0 && tid == 0) {
@@ -437,11 +437,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.K = h;
     g.kcache = w.kcache;
     g.vcache = w.vcache;
+    MG_STAMP();  // 1: x staged
     consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    MG_STAMP();  // 2: qkv consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
+    MG_STAMP();  // 3
     // ---- attention
     attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+    MG_STAMP();  // 4: attention done
     grid_sync(a.grid_bar, n_sync, n_ctas);
+    MG_STAMP();  // 5
     // ---- O projection + residual
     stage_x<BT, NORM_NONE>(a.attn, a.q_rows, a.M, a.q_rows, nullptr, 0.f, xs, red, tid, warp, lane);
     g.N = h;
@@ -449,16 +454,22 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.out_bf16 = a.h;
     g.resid = a.h;
     g.ld_out = h;
+    MG_STAMP();  // 6: x staged
     consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    MG_STAMP();  // 7: o consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
+    MG_STAMP();  // 8
     // ---- RMSNorm + gate/up + SwiGLU
     stage_x<BT, NORM_RMS>(a.h, h, a.M, h, w.ln2, a.eps, xs, red, tid, warp, lane);
     g.N = 2 * a.inter;
     g.K = h;
     g.out_bf16 = a.act;
     g.ld_out = a.inter;
+    MG_STAMP();  // 9: x staged
     consume<BT, EPI_SWIGLU>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    MG_STAMP();  // 10: gate/up consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
+    MG_STAMP();  // 11
     // ---- down projection + residual
     stage_x<BT, NORM_NONE>(a.act, a.inter, a.M, a.inter, nullptr, 0.f, xs, red, tid, warp, lane);
     g.N = h;
@@ -466,8 +477,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.out_bf16 = a.h;
     g.resid = a.h;
     g.ld_out = h;
+    MG_STAMP();  // 12: x staged
     consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    MG_STAMP();  // 13: down consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
+    MG_STAMP();  // 14 (= 0 of the next layer)
   }
   // ---- final norm + lm_head
   stage_x<BT, NORM_RMS>(a.h, h, a.M, h, a.final_norm, a.eps, xs, red, tid, warp, lane);

@@ -29,6 +29,7 @@ struct MegaArgs {
   int *hist, *step, *fwd_counter;
   unsigned* grid_bar;  // [2], zero on entry and on exit
   int n_stages, k_max;
+  unsigned long long* prof;  // optional [1024] globaltimer stamps of CTA 0 (debug_taps engines only)
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);
