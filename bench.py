@@ -216,8 +216,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the serving path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        raise SystemExit("tensor-parallel bench arm not wired yet in this build step")
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = WORKLOADS[args.workload]
     B = args.batch
     peak_gbs, peak_src = load_peaks()
@@ -225,9 +228,13 @@ def main():
     with open(os.path.join(tmp, "config.json"), "w") as f:
         json.dump(cfg, f)
     params = {"weights": "synthetic", "seed": 0, "max_batch": max(B, 32), "max_seq_len": PROMPT_LEN + NEW_TOKENS + 16,
-              "use_pdl": args.pdl, "use_graph": args.graph, "device": local_rank}
+              "use_pdl": args.pdl, "use_graph": args.graph, "device": local_rank, "tp_size": world, "tp_rank": rank}
     t_load = time.time()
     eng = Engine(tmp, params)
+    if world > 1:
+        from substratus_b200 import tp
+
+        tp.connect(eng)  # all-gather the CUDA-IPC handles of the exchange buffers; allreduce then runs over NVLink
     t_load = time.time() - t_load
     info = eng.info
     prompts = synthetic_prompts(cfg["vocab_size"], B, PROMPT_LEN)
@@ -246,17 +253,30 @@ def main():
         return dict(ttft_wall_ms=(w1 - w0) * 1e3, prefill_dev_ms=pre_ms, decode_dev_ms=dec_ms,
                     decode_wall_ms=(w2 - w1) * 1e3, total_wall_ms=(w2 - w0) * 1e3, last=int(toks[0, -1]))
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         one_request()
     eng.timing_reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     recs = [one_request() for _ in range(args.steps)]
-    torch.cuda.synchronize()
+    barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    if world > 1:  # the slowest rank defines every time (device-timed per rank, MAX over ranks)
+        from substratus_b200 import tp
+
+        wall = tp.max_over_ranks(wall)
+        for r in recs:
+            for k in ("ttft_wall_ms", "prefill_dev_ms", "decode_dev_ms", "decode_wall_ms", "total_wall_ms"):
+                r[k] = tp.max_over_ranks(r[k])
     tm = eng.timing()
     ntok = B * (NEW_TOKENS - 1)
     dec_dev_s = sum(r["decode_dev_ms"] for r in recs) / 1e3
@@ -272,7 +292,7 @@ def main():
     # time over all layers' weights (CUDA events on the engine stream); the largest class (gate/up) is reported.
     kern = {}
     for k in ("gate_up", "qkv", "down", "o", "lm_head", "attn"):
-        ms, by = eng.bench_kernel(k, rows=B, ctx=int(ctx_mean), iters=64)
+        ms, by = eng.bench_kernel(k, rows=min(B, 4), ctx=int(ctx_mean), iters=64)
         kern[k] = {"ms": ms, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9}
     dom = kern["gate_up"]
     roofline = {"bound": "hbm", "kernel": "gemv_kernel (gate/up projection + SwiGLU)", "achieved": dom["gbs"],
@@ -286,8 +306,8 @@ def main():
         "metric": "decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload} bf16 decode, batch {B}, {PROMPT_LEN}-token prompt + {NEW_TOKENS} new tokens, 1xB200",
-                   "batch": B, "prompt_len": PROMPT_LEN, "new_tokens": NEW_TOKENS, "parallelism": f"tp{world}",
+        "config": {"workload": f"{args.workload} bf16 decode, batch {B}, {PROMPT_LEN}-token prompt + {NEW_TOKENS} new tokens, {world}xB200",
+                   "batch": B, "prompt_len": PROMPT_LEN, "new_tokens": NEW_TOKENS, "parallelism": f"tp{world}", "allreduce": "one-shot over NVLink peer memory (CUDA IPC)" if world > 1 else "none",
                    "l2": "inputs larger than L2 (13.2 GB of weights per decode step)", "pdl": args.pdl, "graph": args.graph},
         "ttft_ms_p50": statistics.median(r["ttft_wall_ms"] for r in recs),
         "prefill_device_ms_p50": statistics.median(r["prefill_dev_ms"] for r in recs),
@@ -299,6 +319,9 @@ def main():
         "load_s": t_load, "hbm_gb": info.hbm_bytes_allocated / 1e9,
     }
     eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0 and B == 1 and not args.no_batch32 and args.workload == "llama2-7b":
         pass  # batch-32 numbers are reported by a second invocation (--batch 32); see BASELINE.md
     if rank == 0 and not args.no_cpu_baseline:
