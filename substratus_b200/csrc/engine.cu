@@ -306,8 +306,8 @@ int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
   const int ctas = M * (Hl_ / gc);
-  int s = (4 * n_sm_ + ctas - 1) / ctas;
-  return std::max(1, std::min(s, 32));
+  int s = ((gc >= 4 ? 2 : 4) * n_sm_ + ctas - 1) / ctas;
+  return std::max(1, std::min(s, gc >= 4 ? 16 : 32));
 }
 
 int Engine::alloc_runtime(const Json& params) {
@@ -346,13 +346,26 @@ int Engine::alloc_runtime(const Json& params) {
   TRY(dmalloc(&xn_, (size_t)m_max_ * h));
   TRY(dmalloc(&tp_step_, 1));
   CK(cudaMemset(tp_step_, 0, sizeof(int)));
+  TRY(dmalloc(&tp_push_step_, 1));
+  CK(cudaMemset(tp_push_step_, 0, sizeof(int)));
   if (tp_size_ > 1) {
-    // plain cudaMalloc (not a pool) so the buffers can be exported with cudaIpcGetMemHandle
-    TRY(dmalloc(&tp_partials_, 2 * (size_t)m_max_ * h));
-    TRY(dmalloc(&tp_flags_, 8));
-    CK(cudaMemset(tp_flags_, 0, 8 * sizeof(uint32_t)));
+    // one plain cudaMalloc (not a pool) so the whole exchange area is exported with a single cudaIpcGetMemHandle
+    const size_t b_part = 2 * (size_t)m_max_ * h * sizeof(float);
+    const size_t b_recv = 2 * 8 * (size_t)max_batch_ * h * sizeof(float);
+    tp_off_recv_ = b_part;
+    tp_off_flags_ = b_part + b_recv;
+    tp_off_pflags_ = tp_off_flags_ + 64;
+    tp_pool_bytes_ = tp_off_pflags_ + 64;
+    TRY(dmalloc(&tp_pool_, tp_pool_bytes_));
+    CK(cudaMemset(tp_pool_ + tp_off_flags_, 0, 128));
+    tp_partials_ = (float*)tp_pool_;
+    tp_recv_ = (float*)(tp_pool_ + tp_off_recv_);
+    tp_flags_ = (uint32_t*)(tp_pool_ + tp_off_flags_);
+    tp_pflags_ = (unsigned long long*)(tp_pool_ + tp_off_pflags_);
     TRY(dmalloc(&d_peer_partials_, 8));
     TRY(dmalloc(&d_peer_flags_, 8));
+    TRY(dmalloc(&d_peer_recv_, 8));
+    TRY(dmalloc(&d_peer_pflags_, 8));
   }
   TRY(dmalloc(&logits_, (size_t)max_batch_ * cfg_.vocab));
   const int max_splits = 32;
@@ -566,8 +579,11 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
   const int h = cfg_.hidden, D = cfg_.head_dim;
   const int group = cfg_.heads / cfg_.kv_heads;
   int launches = 0;
-  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, lc(true)));
   const bool tp = tp_size_ > 1;
+  // push-model allreduce (decode-sized forwards on the GEMV path): partials are written straight into every rank's
+  // receive slots by the projection epilogue; pull model otherwise (prefill / tensor-core path)
+  const bool tp_push = tp && M <= 4 && M < tc_min_rows_ && M <= max_batch_;
+  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, tp_push ? tp_push_step_ : nullptr, lc(true)));
   TpArgs ta = {};
   if (tp) {
     ta.rank = tp_rank_;
@@ -582,6 +598,29 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     ta.resid = h_;
     ta.out = h_;
   }
+  TpPushArgs tpa = {};
+  if (tp_push) {
+    tpa.size = tp_size_;
+    tpa.recv = tp_recv_;
+    tpa.flags = tp_pflags_;
+    tpa.tp_step = tp_push_step_;
+    tpa.n_per_step = 2 * cfg_.layers;
+    tpa.parity_stride = 8LL * max_batch_ * h;
+    tpa.src_stride = (long long)max_batch_ * h;
+    tpa.M = M;
+    tpa.hidden = h;
+    tpa.resid = h_;
+    tpa.out = h_;
+  }
+  auto set_push = [&](GemvArgs& g, int seq) {
+    g.push_dst = d_peer_recv_;
+    g.push_flags = d_peer_pflags_;
+    g.push_n = tp_size_;
+    g.push_rank = tp_rank_;
+    g.push_off = (long long)(seq & 1) * 8LL * max_batch_ * h + (long long)tp_rank_ * max_batch_ * h;
+    tpa.seq_in_step = seq;
+    tpa.arrivals_per_epoch = (unsigned long long)gemv_grid_ctas(g.M, g.N, g.K, n_sm_);
+  };
   ++launches;
   const int n_splits = (M <= max_batch_) ? decode_splits_(M) : 1;
   // projections: CUDA-core GEMV (weights streamed once, M <= 4 rows per pass) or tcgen05 GEMM (tokens = UMMA N)
@@ -661,13 +700,17 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     o.out_bf16 = h_;
     o.resid = h_;
     o.ld_out = h;
-    const int epi_rowpar = tp ? EPI_F32 : EPI_RESID;  // row-parallel under TP: raw fp32 partial -> allreduce + residual
+    const int epi_rowpar = tp_push ? EPI_F32_PUSH : tp ? EPI_F32 : EPI_RESID;  // row-parallel under TP: fp32 partial -> allreduce + residual
     if (tp) o.out_f32 = tp_partials_ + (size_t)((2 * l) & 1) * m_max_ * h;
+    if (tp_push) set_push(o, 2 * l);
     if (tc)
       CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(o, epi_rowpar, NORM_NONE, lc(true)));
-    if (tp) {
+    if (tp_push) {
+      CK(launch_tp_reduce_push(tpa, lc(true)));
+      ++launches;
+    } else if (tp) {
       ta.seq_in_step = 2 * l;
       CK(launch_tp_allreduce_resid(ta, lc(true)));
       ++launches;
@@ -703,11 +746,15 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     d.resid = h_;
     d.ld_out = h;
     if (tp) d.out_f32 = tp_partials_ + (size_t)((2 * l + 1) & 1) * m_max_ * h;
+    if (tp_push) set_push(d, 2 * l + 1);
     if (tc)
       CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(d, epi_rowpar, NORM_NONE, lc(true)));
-    if (tp) {
+    if (tp_push) {
+      CK(launch_tp_reduce_push(tpa, lc(true)));
+      ++launches;
+    } else if (tp) {
       ta.seq_in_step = 2 * l + 1;
       CK(launch_tp_allreduce_resid(ta, lc(true)));
       ++launches;
@@ -1074,11 +1121,33 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       a.scale = 1.0f / sqrtf((float)D);
       bytes = 2LL * rows * ctx * KVHl_ * D * 2;
       CK(launch_attn_decode(a, lc(true)));
+    } else if (w == "allreduce") {
+      // collective: every rank must run the same bench_kernel("allreduce", ...) call at the same time
+      if (tp_size_ < 2 || !tp_connected_) RET(SSB_ESTATE, "allreduce bench needs a connected tensor-parallel engine");
+      TpArgs ta = {};
+      ta.rank = tp_rank_;
+      ta.size = tp_size_;
+      ta.peer_partials = d_peer_partials_;
+      ta.peer_flags = d_peer_flags_;
+      ta.tp_step = tp_step_;
+      ta.n_per_step = iters + 3;
+      ta.seq_in_step = l;
+      ta.parity_stride = m_max_ * h;
+      ta.M = rows;
+      ta.hidden = h;
+      ta.resid = h_;
+      ta.out = h_;
+      bytes = (int64_t)(tp_size_ - 1) * rows * h * 4;
+      CK(launch_tp_allreduce_resid(ta, lc(true)));
     } else {
-      RET(SSB_EINVAL, "unknown kernel '" + w + "' (qkv|o|gate_up|down|lm_head|attn)");
+      RET(SSB_EINVAL, "unknown kernel '" + w + "' (qkv|o|gate_up|down|lm_head|attn|allreduce)");
     }
     return SSB_OK;
   };
+  if (w == "allreduce") {  // a fresh epoch range for this run: one forward-counter tick, sequence numbers 0..iters+2
+    CK(launch_embed(embed_, row_tok_, h_, rows, h, nullptr, tp_step_, nullptr, lc(false)));
+    cudaMemsetAsync(tp_partials_, 0, 2 * (size_t)m_max_ * h * sizeof(float), stream_);
+  }
   for (int i = 0; i < 3 && rc == SSB_OK; ++i) rc = one(i);
   if (rc == SSB_OK) {
     cudaEventRecord(ev0_, stream_);
@@ -1106,8 +1175,8 @@ struct TpHandle {
   uint32_t magic;
   int32_t rank, size, device;
   int64_t pid;
-  cudaIpcMemHandle_t partials, flags;
-  uint64_t raw_partials, raw_flags;
+  cudaIpcMemHandle_t pool;
+  uint64_t raw_pool, pool_bytes;
 };
 static_assert(sizeof(TpHandle) <= 256, "ssb_tp_handle_size");
 
@@ -1121,10 +1190,9 @@ int Engine::tp_export(void* out) {
   hd.size = tp_size_;
   hd.device = device_;
   hd.pid = (int64_t)getpid();
-  CK(cudaIpcGetMemHandle(&hd.partials, tp_partials_));
-  CK(cudaIpcGetMemHandle(&hd.flags, tp_flags_));
-  hd.raw_partials = (uint64_t)(uintptr_t)tp_partials_;
-  hd.raw_flags = (uint64_t)(uintptr_t)tp_flags_;
+  CK(cudaIpcGetMemHandle(&hd.pool, tp_pool_));
+  hd.raw_pool = (uint64_t)(uintptr_t)tp_pool_;
+  hd.pool_bytes = (uint64_t)tp_pool_bytes_;
   memset(out, 0, 256);
   memcpy(out, &hd, sizeof hd);
   return SSB_OK;
@@ -1134,35 +1202,41 @@ int Engine::tp_connect(const void* all, int n) {
   if (tp_size_ < 2) RET(SSB_ESTATE, "engine is not tensor parallel");
   if (n != tp_size_) RET(SSB_EINVAL, "n_ranks != tp_size");
   CK(cudaSetDevice(device_));
-  std::vector<float*> pp(8, nullptr);
-  std::vector<uint32_t*> pf(8, nullptr);
+  std::vector<uint8_t*> pool(8, nullptr);
   for (int r = 0; r < n; ++r) {
     TpHandle hd;
     memcpy(&hd, (const char*)all + (size_t)r * 256, sizeof hd);
-    if (hd.magic != 0x53534254u || hd.rank != r || hd.size != tp_size_) RET(SSB_EINVAL, "bad TP handle for rank " + std::to_string(r));
+    if (hd.magic != 0x53534254u || hd.rank != r || hd.size != tp_size_ || hd.pool_bytes != (uint64_t)tp_pool_bytes_)
+      RET(SSB_EINVAL, "bad TP handle for rank " + std::to_string(r) + " (ranks must be created with identical params)");
     if (r == tp_rank_) {
-      pp[r] = tp_partials_;
-      pf[r] = tp_flags_;
+      pool[r] = tp_pool_;
     } else if (hd.pid == (int64_t)getpid()) {  // several ranks in one process (serve host): plain peer access
       if (hd.device != device_) {
         cudaError_t e = cudaDeviceEnablePeerAccess(hd.device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
         cudaGetLastError();
       }
-      pp[r] = (float*)(uintptr_t)hd.raw_partials;
-      pf[r] = (uint32_t*)(uintptr_t)hd.raw_flags;
+      pool[r] = (uint8_t*)(uintptr_t)hd.raw_pool;
     } else {
-      void *a = nullptr, *b = nullptr;
-      CK(cudaIpcOpenMemHandle(&a, hd.partials, cudaIpcMemLazyEnablePeerAccess));
+      void* a = nullptr;
+      CK(cudaIpcOpenMemHandle(&a, hd.pool, cudaIpcMemLazyEnablePeerAccess));
       ipc_opened_.push_back(a);
-      CK(cudaIpcOpenMemHandle(&b, hd.flags, cudaIpcMemLazyEnablePeerAccess));
-      ipc_opened_.push_back(b);
-      pp[r] = (float*)a;
-      pf[r] = (uint32_t*)b;
+      pool[r] = (uint8_t*)a;
     }
+  }
+  std::vector<float*> pp(8, nullptr), pr(8, nullptr);
+  std::vector<uint32_t*> pf(8, nullptr);
+  std::vector<unsigned long long*> pq(8, nullptr);
+  for (int r = 0; r < n; ++r) {
+    pp[r] = (float*)pool[r];
+    pr[r] = (float*)(pool[r] + tp_off_recv_);
+    pf[r] = (uint32_t*)(pool[r] + tp_off_flags_);
+    pq[r] = (unsigned long long*)(pool[r] + tp_off_pflags_);
   }
   CK(cudaMemcpy(d_peer_partials_, pp.data(), 8 * sizeof(float*), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_peer_flags_, pf.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_peer_recv_, pr.data(), 8 * sizeof(float*), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_peer_pflags_, pq.data(), 8 * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
   tp_connected_ = true;
   return SSB_OK;
 }

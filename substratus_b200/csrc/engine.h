@@ -98,11 +98,19 @@ class Engine {
   int *next_tok_ = nullptr, *hist_ = nullptr, *step_ = nullptr, *block_table_ = nullptr;
   int max_steps_ = 0;
   // tensor parallel exchange (peer-mapped over NVLink; see tp_allreduce_resid_kernel)
-  float* tp_partials_ = nullptr;       // [2][m_max][hidden] fp32 partial sums of this rank
-  uint32_t* tp_flags_ = nullptr;       // [8] epoch flags written by the peers
+  // one exported pool per rank: [partials 2*m_max*h f32 | recv 2*8*max_batch*h f32 | flags 8 u32 (64 B) | pflags 8 u64]
+  uint8_t* tp_pool_ = nullptr;
+  size_t tp_pool_bytes_ = 0, tp_off_recv_ = 0, tp_off_flags_ = 0, tp_off_pflags_ = 0;
+  float* tp_partials_ = nullptr;       // pull model (prefill / tensor-core path): fp32 partial sums of this rank
+  float* tp_recv_ = nullptr;           // push model (decode): [2 parity][8 src][max_batch][hidden]
+  uint32_t* tp_flags_ = nullptr;       // [8] epoch flags written by the peers (pull model)
+  unsigned long long* tp_pflags_ = nullptr;  // [8] arrival counters, one per source rank (push model)
   int* tp_step_ = nullptr;             // forwards executed (device counter)
+  int* tp_push_step_ = nullptr;        // push-model forwards executed (device counter)
   float** d_peer_partials_ = nullptr;  // [tp_size] device array of peer-mapped pointers
   uint32_t** d_peer_flags_ = nullptr;
+  float** d_peer_recv_ = nullptr;
+  unsigned long long** d_peer_pflags_ = nullptr;
   std::vector<void*> ipc_opened_;
   bool tp_connected_ = false;
   // taps

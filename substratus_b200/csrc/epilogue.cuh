@@ -13,6 +13,10 @@ SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, floa
   if constexpr (EPI == EPI_F32) {
     a.out_f32[(size_t)m * a.ld_out + 2 * pair] = v0;
     a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = v1;
+  } else if constexpr (EPI == EPI_F32_PUSH) {
+    const long long o = a.push_off + (long long)m * a.ld_out + 2 * pair;
+    const float2 v = make_float2(v0, v1);
+    for (int r = 0; r < a.push_n; ++r) *reinterpret_cast<float2*>(a.push_dst[r] + o) = v;  // posted remote stores
   } else if constexpr (EPI == EPI_F32_BF16R) {
     a.out_f32[(size_t)m * a.ld_out + 2 * pair] = bf16r(v0);
     a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = bf16r(v1);

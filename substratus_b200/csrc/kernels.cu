@@ -28,7 +28,13 @@ constexpr int GV_KC = 1024;                     // K elements per stage
 constexpr int GV_STAGES = 3;                    // 3 x 32 KiB in flight per SM
 constexpr int GV_TILE_BYTES = GV_STAGES * GV_ROWS * GV_KC * 2;
 
+int gemv_pick_bt(int M, int K);
 static size_t gemv_smem_bytes(int bt, int K) { return (size_t)GV_TILE_BYTES + (size_t)bt * K * 2 + 2 * GV_STAGES * 8 + 64; }
+
+int gemv_grid_ctas(int M, int N, int K, int n_sm) {
+  const int bt = gemv_pick_bt(M, K), P = N / 2;
+  return (n_sm < P ? n_sm : P) * ((M + bt - 1) / bt);
+}
 
 int gemv_pick_bt(int M, int K) {
   int bt = M >= 4 ? 4 : (M >= 2 ? 2 : 1);
@@ -185,6 +191,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
         if (lane < BT && m0 + lane < a.M) gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
       }
     }
+    if constexpr (EPI == EPI_F32_PUSH) {
+      // all pushes of this CTA are issued: make them visible system-wide, then count this CTA in at every rank
+      named_bar_sync(1, GV_CW * 32);
+      if (tid == 0) {
+        __threadfence_system();
+        for (int r = 0; r < a.push_n; ++r)
+          asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(a.push_flags[r] + a.push_rank), "l"(1ull) : "memory");
+      }
+    }
   }
 }
 
@@ -240,6 +255,7 @@ cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& l
   switch (epi) {
     case EPI_RESID: return launch_gemv_bt<EPI_RESID, NORM_NONE>(a, lc);
     case EPI_F32: return launch_gemv_bt<EPI_F32, NORM_NONE>(a, lc);
+    case EPI_F32_PUSH: return launch_gemv_bt<EPI_F32_PUSH, NORM_NONE>(a, lc);
     case EPI_BF16: return launch_gemv_bt<EPI_BF16, NORM_NONE>(a, lc);
     default: return cudaErrorInvalidValue;
   }
@@ -419,8 +435,11 @@ static cudaError_t launch_attn_t(const AttnArgs& a, const LaunchCfg& lc) {
   return launch_ex(attn_decode_kernel<D, G>, grid, dim3(AT_THREADS), 0, lc, a);
 }
 
+cudaError_t launch_attn_gqa(const AttnArgs& a, int gc, const LaunchCfg& lc);  // attn_gqa.cu
+
 cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc) {
   const int gc = (a.group % 8 == 0) ? 8 : (a.group % 4 == 0) ? 4 : (a.group % 2 == 0) ? 2 : 1;
+  if (gc >= 4) return launch_attn_gqa(a, gc, lc);  // grouped-query models: K/V staged once in smem, warp per q head
   if (a.head_dim == 128) {
     switch (gc) {
       case 1: return launch_attn_t<128, 1>(a, lc);
@@ -443,13 +462,14 @@ cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc) {
 // embedding gather, greedy argmax
 // =====================================================================================================================
 __global__ void __launch_bounds__(128) embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ row_tok,
-                                                    bf16* __restrict__ h, int hidden, int* step_counter, int* fwd_counter) {
+                                                    bf16* __restrict__ h, int hidden, int* step_counter, int* fwd_counter, int* push_counter) {
   pdl_wait();
   pdl_launch_dependents();
   const int m = blockIdx.x;
   if (m == 0 && threadIdx.x == 0) {
     if (step_counter) *step_counter += 1;
     if (fwd_counter) *fwd_counter += 1;
+    if (push_counter) *push_counter += 1;
   }
   const bf16* src = embed + (size_t)row_tok[m] * hidden;
   bf16* dst = h + (size_t)m * hidden;
@@ -458,8 +478,8 @@ __global__ void __launch_bounds__(128) embed_kernel(const bf16* __restrict__ emb
 }
 
 cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
-                         int* fwd_counter, const LaunchCfg& lc) {
-  return launch_ex(embed_kernel, dim3(M), dim3(128), 0, lc, embed, row_tok, h, hidden, step_counter, fwd_counter);
+                         int* fwd_counter, int* push_counter, const LaunchCfg& lc) {
+  return launch_ex(embed_kernel, dim3(M), dim3(128), 0, lc, embed, row_tok, h, hidden, step_counter, fwd_counter, push_counter);
 }
 
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int n_rows,
@@ -665,6 +685,53 @@ __global__ void __launch_bounds__(TP_THREADS) tp_allreduce_resid_kernel(const Tp
     o.y = pack_bf16(bf16r(s.z) + bf_lo(rv.y), bf16r(s.w) + bf_hi(rv.y));
     *reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = o;
   }
+}
+
+__global__ void __launch_bounds__(TP_THREADS) tp_reduce_push_kernel(const TpPushArgs a) {
+  // no griddepcontrol.wait on purpose: the data dependency is carried by the arrival counters (every producing CTA of
+  // every rank, including this one, counts itself in after its pushes), so this kernel may start while the GEMV runs
+  pdl_launch_dependents();
+  // arrival counters accumulate: allreduces completed before this one = (push forwards before this one) * n_per_step
+  // + seq_in_step (the forward counter was already incremented for the current forward, hence the -1)
+  const unsigned long long target =
+      ((unsigned long long)((unsigned)(*a.tp_step) - 1u) * (unsigned)a.n_per_step + (unsigned)a.seq_in_step + 1ull) * a.arrivals_per_epoch;
+  if (threadIdx.x < a.size) {
+    const unsigned long long* f = a.flags + threadIdx.x;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+  const int parity = a.seq_in_step & 1;
+  const float* base = a.recv + (long long)parity * a.parity_stride;
+  const int total4 = a.M * a.hidden / 4;
+  for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < total4; i += gridDim.x * TP_THREADS) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {
+      if (r < a.size) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (long long)r * a.src_stride) + i);
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
+      }
+    }
+    const uint2 rv = __ldcg(reinterpret_cast<const uint2*>(a.resid) + i);
+    uint2 o;
+    o.x = pack_bf16(bf16r(s.x) + bf_lo(rv.x), bf16r(s.y) + bf_hi(rv.x));
+    o.y = pack_bf16(bf16r(s.z) + bf_lo(rv.y), bf16r(s.w) + bf_hi(rv.y));
+    reinterpret_cast<uint2*>(a.out)[i] = o;
+  }
+}
+
+cudaError_t launch_tp_reduce_push(const TpPushArgs& a, const LaunchCfg& lc) {
+  if (a.size > TP_MAX || (a.hidden & 3)) return cudaErrorInvalidValue;
+  const int total4 = a.M * a.hidden / 4;
+  int grid = (total4 + TP_THREADS - 1) / TP_THREADS;
+  grid = grid < 1 ? 1 : (grid > 32 ? 32 : grid);
+  return launch_ex(tp_reduce_push_kernel, dim3(grid), dim3(TP_THREADS), 0, lc, a);
 }
 
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc) {

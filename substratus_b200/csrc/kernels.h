@@ -13,6 +13,7 @@ enum GemvEpi : int {
   EPI_SWIGLU = 3,    // rows (2i,2i+1) = (gate_i, up_i): out_bf16[m][i] = bf16(bf16(silu(bf16 g)) * bf16 u)
   EPI_QKV_ROPE = 4,  // pair-interleaved q|k|v rows: RoPE on q,k; q -> q_out, k/v -> paged KV cache at (slot,pos)
   EPI_BF16 = 5,      // out_bf16[m][n] = bf16(acc + bias)
+  EPI_F32_PUSH = 6,  // tensor parallel, decode: raw fp32 partial PUSHED into every rank's receive slot over NVLink
 };
 
 enum NormKind : int { NORM_NONE = 0, NORM_RMS = 1 };
@@ -45,6 +46,11 @@ struct GemvArgs {
   const uint32_t* rope_cs; // [max_pos][head_dim/2] packed (cos bf16 | sin bf16 << 16)
   int block_size;
   int kvh;                 // KVH_local
+  // EPI_F32_PUSH (row-parallel projection under tensor parallelism)
+  float* const* push_dst;                 // [push_n] peer-mapped base of each rank's receive buffer
+  unsigned long long* const* push_flags;  // [push_n] peer-mapped arrival counters, [push_n] entries each (one per source)
+  long long push_off;                     // element offset of (parity, this rank)'s slot inside a receive buffer
+  int push_n, push_rank;
 };
 
 struct AttnArgs {
@@ -71,10 +77,11 @@ struct LaunchCfg {
 
 cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& lc);
 int gemv_pick_bt(int M, int K);
+int gemv_grid_ctas(int M, int N, int K, int n_sm);  // CTAs launch_gemv will use (arrival count of the push allreduce)
 cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc);
 // h[m][:] = embed[row_tok[m]][:]; thread 0 of block 0 also does (*step_counter)++ when non-null
 cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
-                         int* fwd_counter, const LaunchCfg& lc);
+                         int* fwd_counter, int* push_counter, const LaunchCfg& lc);
 // greedy pick per row (lowest index wins ties, as torch.argmax on CPU): tok_out[r] = argmax logits[r][:]
 // hist != null: hist[(*step) * n_rows + r] = tok ; pos_inc != null: pos_inc[r] += 1
 cudaError_t launch_argmax(const float* logits, int V, int n_rows, int* tok_out, int* hist, const int* step,
@@ -103,6 +110,22 @@ struct TpArgs {
   bf16* out;                     // [M][hidden] (may alias resid)
 };
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);
+
+// push-model reduce (decode): partials were pushed into recv[parity][src][M][hidden] by the GEMV epilogues of all
+// ranks; wait until every source's arrival counter reached `target`, sum the slots in rank order, add the residual.
+struct TpPushArgs {
+  int size;
+  const float* recv;                   // this rank's receive buffer
+  const unsigned long long* flags;     // this rank's arrival counters [size]
+  const int* tp_step;
+  int seq_in_step, n_per_step;
+  unsigned long long arrivals_per_epoch;  // CTAs of the producing GEMV grid (each adds 1 per allreduce)
+  long long parity_stride, src_stride;    // elements
+  int M, hidden;
+  const bf16* resid;
+  bf16* out;
+};
+cudaError_t launch_tp_reduce_push(const TpPushArgs& a, const LaunchCfg& lc);
 
 // GGUF block dequantisation (dequant.cu): src = raw tensor bytes on the device, dtype = ssb::DType, n elements
 cudaError_t launch_dequant(const void* src, int dtype, int64_t n, bf16* dst, cudaStream_t s);
