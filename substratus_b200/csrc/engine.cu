@@ -470,6 +470,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   CK(cudaEventCreate(&ev0_));
   CK(cudaEventCreate(&ev1_));
   use_pdl_ = params.get_int("use_pdl", 1) != 0;
+  tp_push_ = params.get_int("tp_push", 0) != 0;  // push-model allreduce: measured slower than pull on B200
   use_graph_ = params.get_int("use_graph", 1) != 0;
   if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
   TRY(alloc_weights());
@@ -582,7 +583,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
   const bool tp = tp_size_ > 1;
   // push-model allreduce (decode-sized forwards on the GEMV path): partials are written straight into every rank's
   // receive slots by the projection epilogue; pull model otherwise (prefill / tensor-core path)
-  const bool tp_push = tp && M <= 4 && M < tc_min_rows_ && M <= max_batch_;
+  const bool tp_push = tp && tp_push_ && M <= 4 && M < tc_min_rows_ && M <= max_batch_;
   CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, tp_push ? tp_push_step_ : nullptr, lc(true)));
   TpArgs ta = {};
   if (tp) {
@@ -597,6 +598,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     ta.hidden = h;
     ta.resid = h_;
     ta.out = h_;
+    ta.variant = 1;  // st.release.sys alone orders the partials before the flag (measured 1.4 us faster than fence + store)
   }
   TpPushArgs tpa = {};
   if (tp_push) {
@@ -1006,6 +1008,13 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
     same_layer = true;
     w.resize(w.size() - 3);
   }
+  int variant = 0;       // "allreduce@v<bits>[n]": latency experiments, trailing 'n' = no PDL
+  bool bench_pdl = true;
+  if (w.rfind("allreduce@v", 0) == 0) {
+    variant = atoi(w.c_str() + 11);
+    if (w.back() == 'n') bench_pdl = false;
+    w = "allreduce";
+  }
   const int h = cfg_.hidden, D = cfg_.head_dim;
   // stage a decode-like batch: rows sequences of length ctx (slots 0..rows-1 must be free)
   std::vector<int> sl(rows), tok(rows, 1), pos(rows, ctx - 1);
@@ -1137,8 +1146,9 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       ta.hidden = h;
       ta.resid = h_;
       ta.out = h_;
+      ta.variant = variant;
       bytes = (int64_t)(tp_size_ - 1) * rows * h * 4;
-      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      CK(launch_tp_allreduce_resid(ta, lc(bench_pdl)));
     } else {
       RET(SSB_EINVAL, "unknown kernel '" + w + "' (qkv|o|gate_up|down|lm_head|attn|allreduce)");
     }

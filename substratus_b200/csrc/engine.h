@@ -112,7 +112,7 @@ class Engine {
   float** d_peer_recv_ = nullptr;
   unsigned long long** d_peer_pflags_ = nullptr;
   std::vector<void*> ipc_opened_;
-  bool tp_connected_ = false;
+  bool tp_connected_ = false, tp_push_ = false;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;

@@ -650,29 +650,58 @@ SSB_DEVINL float4 ld_relaxed_sys_f4(const float* p) {
 constexpr int TP_MAX = 8;
 constexpr int TP_THREADS = 256;
 
+SSB_DEVINL uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(TP_THREADS) tp_allreduce_resid_kernel(const TpArgs a) {
   pdl_wait();  // this rank's partials (previous kernel) are complete and visible
   pdl_launch_dependents();
   const uint32_t epoch = (uint32_t)(*a.tp_step) * (uint32_t)a.n_per_step + (uint32_t)a.seq_in_step + 1u;
   const int parity = a.seq_in_step & 1;
+  const int total4 = a.M * a.hidden / 4;
+  const size_t poff = (size_t)parity * a.parity_stride;
+  const bool push = a.variant & 4;
+  if (push) {
+    // push model: copy this rank's partial into slot [parity][rank] of every peer (posted stores), then flag.
+    // slots live in the upper part of the partial buffers: (8 + parity*8 + src) * M * hidden  (M <= 4)
+    const size_t slot = (size_t)(8 + parity * 8 + a.rank) * a.M * a.hidden;
+    if (blockIdx.x == 0) {
+      for (int i = threadIdx.x; i < total4; i += TP_THREADS) {
+        const float4 v = reinterpret_cast<const float4*>(a.peer_partials[a.rank] + poff)[i];
+        for (int r = 0; r < a.size; ++r) reinterpret_cast<float4*>(a.peer_partials[r] + slot)[i] = v;
+      }
+      __syncthreads();
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x < a.size && threadIdx.x != a.rank) {
-    __threadfence_system();
+    if (!(a.variant & 1) || push) __threadfence_system();
     st_release_sys(a.peer_flags[threadIdx.x] + a.rank, epoch);  // "rank's partials for `epoch` are ready"
   }
   if (threadIdx.x < a.size && threadIdx.x != a.rank) {
     const uint32_t* f = a.peer_flags[a.rank] + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    if (a.variant & 2) {
+      while ((int32_t)(ld_relaxed_sys_u32(f) - epoch) < 0) {
+      }
+      __threadfence_system();
+    } else {
+      while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      }
     }
   }
   __syncthreads();
-  const int total4 = a.M * a.hidden / 4;
-  const size_t poff = (size_t)parity * a.parity_stride;
   for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < total4; i += gridDim.x * TP_THREADS) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < TP_MAX; ++r) {
       if (r < a.size) {
-        const float4 v = ld_relaxed_sys_f4(a.peer_partials[r] + poff + (size_t)i * 4);
+        float4 v;
+        if (push)
+          v = __ldcg(reinterpret_cast<const float4*>(a.peer_partials[a.rank] + (size_t)(8 + parity * 8 + r) * a.M * a.hidden) + i);
+        else
+          v = ld_relaxed_sys_f4(a.peer_partials[r] + poff + (size_t)i * 4);
         s.x += v.x;
         s.y += v.y;
         s.z += v.z;

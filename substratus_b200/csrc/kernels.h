@@ -108,6 +108,9 @@ struct TpArgs {
   int M, hidden;
   const bf16* resid;             // [M][hidden] local residual stream
   bf16* out;                     // [M][hidden] (may alias resid)
+  int variant;                   // latency experiments (tools/tp_bench.py): bit0 no fence.sys before the flag store,
+                                 // bit1 poll with relaxed loads + one acquire fence, bit2 push model (write partials
+                                 // into the peers' slots, read locally)
 };
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);
 
