@@ -100,16 +100,26 @@ int Engine::load_config(const std::string& dir, const Json& params) {
     RET(SSB_EINVAL, std::string("config.json: ") + e.what());
   }
   cfg_.model_type = c.get_str("model_type", "llama");
-  if (cfg_.model_type != "llama") RET(SSB_EINVAL, "unsupported model_type '" + cfg_.model_type + "' (llama family only in this build)");
+  if (cfg_.model_type != "llama" && cfg_.model_type != "falcon")
+    RET(SSB_EINVAL, "unsupported model_type '" + cfg_.model_type + "' (llama and falcon families)");
+  cfg_.falcon = cfg_.model_type == "falcon";
   cfg_.hidden = (int)c.get_int("hidden_size", 0);
   cfg_.inter = (int)c.get_int("intermediate_size", 0);
   cfg_.layers = (int)c.get_int("num_hidden_layers", 0);
   cfg_.heads = (int)c.get_int("num_attention_heads", 0);
   cfg_.kv_heads = (int)c.get_int("num_key_value_heads", cfg_.heads);
+  if (cfg_.falcon) {
+    // examples/falcon-40b: new_decoder_architecture (two LayerNorms, grouped fused QKV, parallel block), no biases, RoPE
+    if (c.get_num("new_decoder_architecture", 0) == 0) RET(SSB_EINVAL, "falcon: only new_decoder_architecture=true (falcon-40b class) is supported");
+    if (c.get_num("alibi", 0) != 0 || c.get_num("bias", 0) != 0) RET(SSB_EINVAL, "falcon: alibi / linear biases are not supported");
+    if (c.has("num_ln_in_parallel_attn") && c.get_int("num_ln_in_parallel_attn", 2) != 2) RET(SSB_EINVAL, "falcon: num_ln_in_parallel_attn must be 2");
+    cfg_.kv_heads = (int)c.get_int("num_kv_heads", cfg_.heads);
+    cfg_.inter = (int)c.get_int("ffn_hidden_size", 4 * cfg_.hidden);
+  }
   cfg_.head_dim = (int)c.get_int("head_dim", cfg_.heads ? cfg_.hidden / cfg_.heads : 0);
   cfg_.vocab = (int)c.get_int("vocab_size", 0);
   cfg_.max_pos = (int)c.get_int("max_position_embeddings", 2048);
-  cfg_.eps = (float)c.get_num("rms_norm_eps", 1e-6);
+  cfg_.eps = (float)c.get_num(cfg_.falcon ? "layer_norm_epsilon" : "rms_norm_eps", cfg_.falcon ? 1e-5 : 1e-6);
   cfg_.theta = (float)c.get_num("rope_theta", 10000.0);
   if (const Json* rp = c.find("rope_parameters"))
     if (rp->kind == Json::Obj) cfg_.theta = (float)rp->get_num("rope_theta", cfg_.theta);
@@ -142,18 +152,24 @@ int Engine::alloc_weights() {
   for (auto& w : lw_) {
     TRY(dmalloc(&w.wqkv, qkv_rows * h));
     TRY(dmalloc(&w.wo, h * (size_t)Hl_ * D));
-    TRY(dmalloc(&w.wgu, 2 * (size_t)Il_ * h));
+    TRY(dmalloc(&w.wgu, (cfg_.falcon ? 1 : 2) * (size_t)Il_ * h));
     TRY(dmalloc(&w.wdown, h * (size_t)Il_));
     TRY(dmalloc(&w.ln1, h));
     TRY(dmalloc(&w.ln2, h));
+    if (cfg_.falcon) {
+      TRY(dmalloc(&w.ln1_b, h));
+      TRY(dmalloc(&w.ln2_b, h));
+    }
   }
+  if (cfg_.falcon) TRY(dmalloc(&final_norm_b_, h));
   TRY(dmalloc(&embed_, (size_t)cfg_.vocab * h));
   if (cfg_.tie_embeddings)
     lm_head_ = embed_;
   else
     TRY(dmalloc(&lm_head_, (size_t)cfg_.vocab * h));
   TRY(dmalloc(&final_norm_, h));
-  weight_bytes_step_ = 2 * ((int64_t)cfg_.layers * (int64_t)(qkv_rows * h + h * Hl_ * D + 3 * (size_t)Il_ * h) + (int64_t)cfg_.vocab * h);
+  weight_bytes_step_ = 2 * ((int64_t)cfg_.layers * (int64_t)(qkv_rows * h + h * Hl_ * D + (cfg_.falcon ? 2 : 3) * (size_t)Il_ * h) +
+                            (int64_t)cfg_.vocab * h);
   return SSB_OK;
 }
 
@@ -188,7 +204,52 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
     }
     return v;
   };
-  for (int l = 0; l < cfg_.layers; ++l) {
+  if (cfg_.falcon) {
+    // fused query_key_value rows are grouped per KV head: [G query heads | k | v] x KVH  (modeling_falcon.py:259-270)
+    const int G = cfg_.heads / cfg_.kv_heads, gs = (G + 2) * D;
+    auto q_rows = [&]() {
+      std::vector<int> v((size_t)Hl_ * D);
+      for (int r = 0; r < Hl_ * D; ++r) {
+        const int pp = r >> 1, hd = pp / half, j = pp % half, head = h0 + hd;
+        v[r] = (head / G) * gs + (head % G) * D + j + (r & 1) * half;
+      }
+      return v;
+    };
+    auto k_rows = [&]() {
+      std::vector<int> v((size_t)KVHl_ * D);
+      for (int r = 0; r < KVHl_ * D; ++r) {
+        const int pp = r >> 1, hd = pp / half, j = pp % half;
+        v[r] = (kv0 + hd) * gs + G * D + j + (r & 1) * half;
+      }
+      return v;
+    };
+    auto v_rows = [&]() {
+      std::vector<int> v((size_t)KVHl_ * D);
+      for (int r = 0; r < KVHl_ * D; ++r) v[r] = (kv0 + r / D) * gs + (G + 1) * D + r % D;
+      return v;
+    };
+    for (int l = 0; l < cfg_.layers; ++l) {
+      const std::string p = "transformer.h." + std::to_string(l) + ".";
+      const uint32_t t = (uint32_t)l * 16;
+      LayerW& w = lw_[l];
+      const std::string qkv = p + "self_attention.query_key_value.weight";
+      jobs.push_back({w.wqkv, h, q_rows(), Hl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
+      jobs.push_back({w.wqkv + (size_t)Hl_ * D * h, h, k_rows(), KVHl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
+      jobs.push_back({w.wqkv + (size_t)(Hl_ + KVHl_) * D * h, h, v_rows(), KVHl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
+      jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, (int64_t)cfg_.heads * D, p + "self_attention.dense.weight", t + K_O, kWAmp, 0.f});
+      jobs.push_back({w.wgu, h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.dense_h_to_4h.weight", t + 9, kWAmp, 0.f});
+      jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, cfg_.inter, p + "mlp.dense_4h_to_h.weight", t + 10, kWAmp, 0.f});
+      jobs.push_back({w.ln1, h, {}, 1, 0, h, h, p + "ln_attn.weight", t + K_LN1, kNormAmp, 1.f});
+      jobs.push_back({w.ln1_b, h, {}, 1, 0, h, h, p + "ln_attn.bias", t + 12, kNormAmp, 0.f});
+      jobs.push_back({w.ln2, h, {}, 1, 0, h, h, p + "ln_mlp.weight", t + K_LN2, kNormAmp, 1.f});
+      jobs.push_back({w.ln2_b, h, {}, 1, 0, h, h, p + "ln_mlp.bias", t + 13, kNormAmp, 0.f});
+    }
+    jobs.push_back({embed_, h, {}, cfg_.vocab, 0, h, h, "transformer.word_embeddings.weight", kGlobal + 0, kWAmp, 0.f});
+    if (!cfg_.tie_embeddings) jobs.push_back({lm_head_, h, {}, cfg_.vocab, 0, h, h, "lm_head.weight", kGlobal + 2, kWAmp * kLmHeadGain, 0.f});
+    jobs.push_back({final_norm_, h, {}, 1, 0, h, h, "transformer.ln_f.weight", kGlobal + 1, kNormAmp, 1.f});
+    jobs.push_back({final_norm_b_, h, {}, 1, 0, h, h, "transformer.ln_f.bias", kGlobal + 3, kNormAmp, 0.f});
+  }
+  for (int l = 0; l < (cfg_.falcon ? 0 : cfg_.layers); ++l) {
     const std::string p = "model.layers." + std::to_string(l) + ".";
     const uint32_t t = (uint32_t)l * 16;
     LayerW& w = lw_[l];
@@ -203,9 +264,11 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
     jobs.push_back({w.ln1, h, {}, 1, 0, h, h, p + "input_layernorm.weight", t + K_LN1, kNormAmp, 1.f});
     jobs.push_back({w.ln2, h, {}, 1, 0, h, h, p + "post_attention_layernorm.weight", t + K_LN2, kNormAmp, 1.f});
   }
-  jobs.push_back({embed_, h, {}, cfg_.vocab, 0, h, h, "model.embed_tokens.weight", kGlobal + 0, kWAmp, 0.f});
-  if (!cfg_.tie_embeddings) jobs.push_back({lm_head_, h, {}, cfg_.vocab, 0, h, h, "lm_head.weight", kGlobal + 2, kWAmp * kLmHeadGain, 0.f});
-  jobs.push_back({final_norm_, h, {}, 1, 0, h, h, "model.norm.weight", kGlobal + 1, kNormAmp, 1.f});
+  if (!cfg_.falcon) {
+    jobs.push_back({embed_, h, {}, cfg_.vocab, 0, h, h, "model.embed_tokens.weight", kGlobal + 0, kWAmp, 0.f});
+    if (!cfg_.tie_embeddings) jobs.push_back({lm_head_, h, {}, cfg_.vocab, 0, h, h, "lm_head.weight", kGlobal + 2, kWAmp * kLmHeadGain, 0.f});
+    jobs.push_back({final_norm_, h, {}, 1, 0, h, h, "model.norm.weight", kGlobal + 1, kNormAmp, 1.f});
+  }
 
   ModelFiles& files = files_;
   size_t max_src = 0, max_deq = 0;
@@ -344,6 +407,8 @@ int Engine::alloc_runtime(const Json& params) {
   TRY(dmalloc(&attn_, (size_t)m_max_ * Hl_ * D));
   TRY(dmalloc(&act_, (size_t)m_max_ * Il_));
   TRY(dmalloc(&xn_, (size_t)m_max_ * h));
+  if (cfg_.falcon) TRY(dmalloc(&ao_, (size_t)m_max_ * h));
+  if (cfg_.falcon && tp_size_ > 1) TRY(dmalloc(&falcon_scratch_, (size_t)m_max_ * h));
   TRY(dmalloc(&tp_step_, 1));
   CK(cudaMemset(tp_step_, 0, sizeof(int)));
   TRY(dmalloc(&tp_push_step_, 1));
@@ -405,7 +470,7 @@ int Engine::alloc_runtime(const Json& params) {
   for (int i = 0; i < n_blocks_; ++i) free_blocks_[i] = n_blocks_ - 1 - i;
   slots_.assign(max_batch_, SeqSlot());
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
-  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1;
+  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1 && !cfg_.falcon;
   if (use_mega_) {
     const int group = cfg_.heads / cfg_.kv_heads, ag = mega_attn_group(group);
     const int ch = mega_attn_chunk(D, ag);
@@ -490,7 +555,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
     for (auto& w : lw_) {
       CK(tc_make_tmap(&w.tm_qkv, w.wqkv, (int64_t)(Hl_ + 2 * KVHl_) * D, h, h, br));
       CK(tc_make_tmap(&w.tm_o, w.wo, h, (int64_t)Hl_ * D, (int64_t)Hl_ * D, br));
-      CK(tc_make_tmap(&w.tm_gu, w.wgu, 2 * (int64_t)Il_, h, h, br));
+      CK(tc_make_tmap(&w.tm_gu, w.wgu, (cfg_.falcon ? 1 : 2) * (int64_t)Il_, h, h, br));
       CK(tc_make_tmap(&w.tm_down, w.wdown, h, Il_, Il_, br));
     }
   }
@@ -577,6 +642,7 @@ int Engine::upload_block_rows(const std::vector<int>& slots) {
 // n_logit_rows rows listed in logit_rows_ go to logits_; greedy picks to next_tok_.  decode_mode: rows == batch,
 // argmax feeds row_tok_ back, appends to hist_ and advances row_pos_ (device-resident loop, graph-capturable).
 int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
+  if (cfg_.falcon) return forward_falcon(M, n_logit_rows, decode_mode);
   const int h = cfg_.hidden, D = cfg_.head_dim;
   const int group = cfg_.heads / cfg_.kv_heads;
   int launches = 0;
@@ -867,6 +933,190 @@ int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, 
   return SSB_OK;
 }
 
+// Falcon (new decoder architecture) forward: per layer
+//   a = LN_attn(x), m = LN_mlp(x);  attn = dense(attention(rope(qkv(a))));  out = x + (dense_4h_to_h(gelu(dense_h_to_4h(m))) + attn)
+// (HF:models/falcon/modeling_falcon.py:594-636).  Same kernels as Llama with the LayerNorm prologue and the GELU /
+// two-addend residual epilogues; under tensor parallelism the two row-parallel partials are summed locally first, so
+// there is ONE allreduce per layer.
+int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
+  const int h = cfg_.hidden, D = cfg_.head_dim, group = cfg_.heads / cfg_.kv_heads;
+  int launches = 0;
+  const bool tp = tp_size_ > 1;
+  CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, nullptr, lc(true)));
+  ++launches;
+  const int n_splits = (M <= max_batch_) ? decode_splits_(M) : 1;
+  const bool tc = M >= tc_min_rows_;
+  const int tn = tc_pick_tn(M);
+  TcTensorMap tm_xn, tm_attn, tm_act;
+  if (tc) {
+    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn));
+    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn));
+    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn));
+  }
+  TpArgs ta = {};
+  if (tp) {
+    ta.rank = tp_rank_;
+    ta.size = tp_size_;
+    ta.peer_partials = d_peer_partials_;
+    ta.peer_flags = d_peer_flags_;
+    ta.tp_step = tp_step_;
+    ta.n_per_step = cfg_.layers;
+    ta.parity_stride = m_max_ * h;
+    ta.M = M;
+    ta.hidden = h;
+    ta.resid = h_;
+    ta.out = h_;
+    ta.variant = 1;
+  }
+  for (int l = 0; l < cfg_.layers; ++l) {
+    const LayerW& w = lw_[l];
+    GemvArgs g = {};
+    g.W = w.wqkv;
+    g.N = (Hl_ + 2 * KVHl_) * D;
+    g.K = h;
+    g.x = h_;
+    g.ldx = h;
+    g.M = M;
+    g.norm_w = w.ln1;
+    g.norm_b = w.ln1_b;
+    g.eps = cfg_.eps;
+    g.q_out = q_;
+    g.q_rows = Hl_ * D;
+    g.kv_rows = KVHl_ * D;
+    g.head_dim = D;
+    g.kcache = kpool_ + (size_t)l * kv_layer_elems_;
+    g.vcache = vpool_ + (size_t)l * kv_layer_elems_;
+    g.block_table = block_table_;
+    g.bt_stride = max_blocks_per_seq_;
+    g.row_slot = row_slot_;
+    g.row_pos = row_pos_;
+    g.rope_cs = rope_cs_;
+    g.block_size = block_size_;
+    g.kvh = KVHl_;
+    if (tc) {
+      CK(launch_layernorm(h_, w.ln1, w.ln1_b, xn_, M, h, cfg_.eps, lc(true)));
+      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn, g, EPI_QKV_ROPE, lc(true)));
+      ++launches;
+    } else {
+      CK(launch_gemv(g, EPI_QKV_ROPE, NORM_LN, lc(true)));
+    }
+    AttnArgs a = {};
+    a.q = q_;
+    a.kcache = g.kcache;
+    a.vcache = g.vcache;
+    a.block_table = block_table_;
+    a.bt_stride = max_blocks_per_seq_;
+    a.row_slot = row_slot_;
+    a.row_pos = row_pos_;
+    a.out = attn_;
+    a.part_o = part_o_;
+    a.part_ml = part_ml_;
+    a.counters = counters_;
+    a.M = M;
+    a.n_heads = Hl_;
+    a.kvh = KVHl_;
+    a.group = group;
+    a.head_dim = D;
+    a.block_size = block_size_;
+    a.n_splits = n_splits;
+    a.scale = 1.0f / sqrtf((float)D);
+    CK(launch_attn_decode(a, lc(true)));
+    if (taps_ && l == 0) {
+      CK(cudaMemcpyAsync(tap_q0_, q_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
+      CK(cudaMemcpyAsync(tap_attn0_, attn_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
+    }
+    // attention branch output (row-parallel): bf16 ao_ (TP1) or fp32 partial (TP)
+    GemvArgs o = {};
+    o.W = w.wo;
+    o.N = h;
+    o.K = Hl_ * D;
+    o.x = attn_;
+    o.ldx = Hl_ * D;
+    o.M = M;
+    o.out_bf16 = ao_;
+    o.ld_out = h;
+    float* part_attn = tp ? falcon_scratch_ : nullptr;  // local fp32 scratch (the exchange buffers may still be read by peers)
+    if (tp) o.out_f32 = part_attn;
+    const int epi_o = tp ? EPI_F32 : EPI_BF16;
+    if (tc)
+      CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_o, lc(true)));
+    else
+      CK(launch_gemv(o, epi_o, NORM_NONE, lc(true)));
+    // MLP branch on LN_mlp(x)
+    GemvArgs u = {};
+    u.W = w.wgu;
+    u.N = Il_;
+    u.K = h;
+    u.x = h_;
+    u.ldx = h;
+    u.M = M;
+    u.norm_w = w.ln2;
+    u.norm_b = w.ln2_b;
+    u.eps = cfg_.eps;
+    u.out_bf16 = act_;
+    u.ld_out = Il_;
+    if (tc) {
+      CK(launch_layernorm(h_, w.ln2, w.ln2_b, xn_, M, h, cfg_.eps, lc(true)));
+      CK(launch_tc_gemm(w.tm_gu, tm_xn, tn, u, EPI_GELU, lc(true)));
+      ++launches;
+    } else {
+      CK(launch_gemv(u, EPI_GELU, NORM_LN, lc(true)));
+    }
+    GemvArgs d = {};
+    d.W = w.wdown;
+    d.N = h;
+    d.K = Il_;
+    d.x = act_;
+    d.ldx = Il_;
+    d.M = M;
+    d.out_bf16 = h_;
+    d.resid = h_;
+    d.resid2 = ao_;
+    d.ld_out = h;
+    if (tp) {
+      d.out_f32 = tp_partials_ + (size_t)(l & 1) * m_max_ * h;
+      d.f32_add = part_attn;
+    }
+    const int epi_d = tp ? EPI_F32 : EPI_RESID2;
+    if (tc)
+      CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_d, lc(true)));
+    else
+      CK(launch_gemv(d, epi_d, NORM_NONE, lc(true)));
+    launches += 5;
+    if (tp) {
+      ta.seq_in_step = l;
+      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      ++launches;
+    }
+    if (taps_ && l == 0) {
+      CK(cudaMemcpyAsync(tap_h0_, h_, (size_t)M * h * 2, cudaMemcpyDeviceToDevice, stream_));
+      tap_rows_ = M;
+    }
+  }
+  if (n_logit_rows > 0) {
+    GemvArgs g = {};
+    g.W = lm_head_;
+    g.N = cfg_.vocab;
+    g.K = h;
+    g.x = h_;
+    g.ldx = h;
+    g.M = n_logit_rows;
+    g.row_map = decode_mode ? nullptr : logit_rows_;
+    g.norm_w = final_norm_;
+    g.norm_b = final_norm_b_;
+    g.eps = cfg_.eps;
+    g.out_f32 = logits_;
+    g.ld_out = cfg_.vocab;
+    CK(launch_gemv(g, EPI_F32_BF16R, NORM_LN, lc(true)));
+    CK(launch_argmax(logits_, cfg_.vocab, n_logit_rows, decode_mode ? row_tok_ : next_tok_, decode_mode ? hist_ : nullptr,
+                     step_, decode_mode ? row_pos_ : nullptr, lc(true)));
+    launches += 2;
+  }
+  launches_per_forward_ = launches;
+  timing_.kernel_launches += launches;
+  return SSB_OK;
+}
+
 int Engine::forward_mega(int B) {
   const int D = cfg_.head_dim, group = cfg_.heads / cfg_.kv_heads;
   MegaArgs a = {};
@@ -1067,16 +1317,18 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.rope_cs = rope_cs_;
       g.block_size = block_size_;
       g.kvh = KVHl_;
+      g.norm_b = lwv.ln1_b;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
+      CK(launch_gemv(g, EPI_QKV_ROPE, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
     } else if (w == "gate_up") {
       g.W = lwv.wgu;
-      g.N = 2 * Il_;
+      g.N = (cfg_.falcon ? 1 : 2) * Il_;
       g.norm_w = lwv.ln2;
+      g.norm_b = lwv.ln2_b;
       g.out_bf16 = act_;
       g.ld_out = Il_;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_SWIGLU, NORM_RMS, lc(true)));
+      CK(launch_gemv(g, cfg_.falcon ? EPI_GELU : EPI_SWIGLU, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
     } else if (w == "o") {
       g.W = lwv.wo;
       g.N = h;
@@ -1103,10 +1355,11 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.W = lm_head_;
       g.N = cfg_.vocab;
       g.norm_w = final_norm_;
+      g.norm_b = final_norm_b_;
       g.out_f32 = logits_;
       g.ld_out = cfg_.vocab;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_F32_BF16R, NORM_RMS, lc(true)));
+      CK(launch_gemv(g, EPI_F32_BF16R, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
     } else if (w == "attn") {
       AttnArgs a = {};
       a.q = q_;

@@ -21,10 +21,13 @@ struct ModelCfg {
   int hidden = 0, inter = 0, layers = 0, heads = 0, kv_heads = 0, head_dim = 0, vocab = 0, max_pos = 0;
   float eps = 1e-5f, theta = 10000.f;
   bool tie_embeddings = false;
+  bool falcon = false;  // Falcon new_decoder_architecture: LayerNorm(+bias) x2 on the same input, fused grouped QKV,
+                        // GELU MLP, parallel block (HF:models/falcon/modeling_falcon.py:572-636)
 };
 
 struct LayerW {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  bf16 *ln1_b = nullptr, *ln2_b = nullptr;  // Falcon LayerNorm biases (wgu = dense_h_to_4h, wdown = dense_4h_to_h)
   TcTensorMap tm_qkv, tm_o, tm_gu, tm_down;  // TMA descriptors of the four projection matrices (tcgen05 path)
 };
 
@@ -65,7 +68,8 @@ class Engine {
   int upload_block_rows(const std::vector<int>& slots);
   int forward(int M, int n_logit_rows, bool decode_mode);  // enqueue one forward over the staged rows
   int build_graph(int B);
-  int forward_mega(int B);  // one persistent kernel for the whole decode step (B <= 4, single rank)
+  int forward_mega(int B);
+  int forward_falcon(int M, int n_logit_rows, bool decode_mode);  // one persistent kernel for the whole decode step (B <= 4, single rank)
   LaunchCfg lc(bool pdl) const { return LaunchCfg{stream_, pdl && use_pdl_, n_sm_}; }
 
   ModelCfg cfg_;
@@ -86,7 +90,9 @@ class Engine {
 
   // weights
   std::vector<LayerW> lw_;
-  bf16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr;
+  bf16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr, *final_norm_b_ = nullptr;
+  bf16* ao_ = nullptr;  // Falcon: attention-branch output of the parallel block
+  float* falcon_scratch_ = nullptr;  // Falcon TP: local fp32 partial of the attention branch
   uint32_t* rope_cs_ = nullptr;
   // KV pool: per layer [n_blocks][KVHl][block][D]
   bf16 *kpool_ = nullptr, *vpool_ = nullptr;

@@ -11,8 +11,27 @@ template <int BT, int EPI>
 SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, float v1) {
   // v0/v1: fp32 dot products of physical rows (2*pair, 2*pair+1) for tile row m (global row index)
   if constexpr (EPI == EPI_F32) {
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair] = v0;
-    a.out_f32[(size_t)m * a.ld_out + 2 * pair + 1] = v1;
+    const size_t o = (size_t)m * a.ld_out + 2 * pair;
+    if (a.f32_add) {
+      const float2 ad = __ldcg(reinterpret_cast<const float2*>(a.f32_add + o));
+      v0 += ad.x;
+      v1 += ad.y;
+    }
+    a.out_f32[o] = v0;
+    a.out_f32[o + 1] = v1;
+  } else if constexpr (EPI == EPI_GELU) {
+    // nn.GELU() (erf form) on the bf16 Linear output, result bf16   HF:models/falcon/modeling_falcon.py:539-541
+    const float g0 = bf16r(v0), g1 = bf16r(v1);
+    const float y0 = 0.5f * g0 * (1.0f + erff(g0 * 0.70710678118654752440f));
+    const float y1 = 0.5f * g1 * (1.0f + erff(g1 * 0.70710678118654752440f));
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)m * a.ld_out + 2 * pair) = pack_bf16(y0, y1);
+  } else if constexpr (EPI == EPI_RESID2) {
+    // mlp_output += attention_output; output = mlp_output + residual   (bf16 adds)  HF:...modeling_falcon.py:628-636
+    const size_t o = (size_t)m * a.ld_out + 2 * pair;
+    const uint32_t r2 = __ldcg(reinterpret_cast<const uint32_t*>(a.resid2 + o));
+    const uint32_t r = __ldcg(reinterpret_cast<const uint32_t*>(a.resid + o));
+    const float t0 = bf16r(bf16r(v0) + bf_lo(r2)), t1 = bf16r(bf16r(v1) + bf_hi(r2));
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(t0 + bf_lo(r), t1 + bf_hi(r));
   } else if constexpr (EPI == EPI_F32_PUSH) {
     const long long o = a.push_off + (long long)m * a.ld_out + 2 * pair;
     const float2 v = make_float2(v0, v1);

@@ -146,6 +146,56 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
           }
           *reinterpret_cast<uint4*>(xrow + k) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+      } else if constexpr (NORM == NORM_LN) {
+        // torch.nn.LayerNorm on bf16: fp32 statistics, y = (x - mean) * rstd * w + b in fp32, ONE rounding to bf16
+        // (HF:models/falcon/modeling_falcon.py:572-576,594-596 ln_attn / ln_mlp / ln_f)
+        float sm = 0.f;
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sm += bf_lo(u[i]) + bf_hi(u[i]);
+        }
+        sm = warp_sum(sm);
+        if (lane == 0) red[warp] = sm;
+        named_bar_sync(1, GV_CW * 32);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < GV_CW; ++w) tot += red[w];
+        named_bar_sync(1, GV_CW * 32);
+        const float mean = tot / (float)K;
+        float sq = 0.f;
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float lo = bf_lo(u[i]) - mean, hi = bf_hi(u[i]) - mean;
+            sq += lo * lo + hi * hi;
+          }
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        named_bar_sync(1, GV_CW * 32);
+        tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < GV_CW; ++w) tot += red[w];
+        named_bar_sync(1, GV_CW * 32);
+        const float rstd = rsqrtf(tot / (float)K + a.eps);
+        for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+          const uint4 w = ldg128(a.norm_w + k);
+          const uint4 bb = ldg128(a.norm_b + k);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+          const uint32_t bu[4] = {bb.x, bb.y, bb.z, bb.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = pack_bf16((bf_lo(u[i]) - mean) * rstd * bf_lo(wu[i]) + bf_lo(bu[i]),
+                             (bf_hi(u[i]) - mean) * rstd * bf_hi(wu[i]) + bf_hi(bu[i]));
+          *reinterpret_cast<uint4*>(xrow + k) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       } else {
         for (int k = ctid * 8; k < K; k += GV_CW * 32 * 8)
           *reinterpret_cast<uint4*>(xrow + k) = *reinterpret_cast<const uint4*>(src + k);
@@ -252,7 +302,16 @@ cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& l
       default: return cudaErrorInvalidValue;
     }
   }
+  if (norm == NORM_LN) {
+    switch (epi) {
+      case EPI_QKV_ROPE: return launch_gemv_bt<EPI_QKV_ROPE, NORM_LN>(a, lc);
+      case EPI_GELU: return launch_gemv_bt<EPI_GELU, NORM_LN>(a, lc);
+      case EPI_F32_BF16R: return launch_gemv_bt<EPI_F32_BF16R, NORM_LN>(a, lc);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (epi) {
+    case EPI_RESID2: return launch_gemv_bt<EPI_RESID2, NORM_NONE>(a, lc);
     case EPI_RESID: return launch_gemv_bt<EPI_RESID, NORM_NONE>(a, lc);
     case EPI_F32: return launch_gemv_bt<EPI_F32, NORM_NONE>(a, lc);
     case EPI_F32_PUSH: return launch_gemv_bt<EPI_F32_PUSH, NORM_NONE>(a, lc);

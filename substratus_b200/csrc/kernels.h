@@ -14,9 +14,12 @@ enum GemvEpi : int {
   EPI_QKV_ROPE = 4,  // pair-interleaved q|k|v rows: RoPE on q,k; q -> q_out, k/v -> paged KV cache at (slot,pos)
   EPI_BF16 = 5,      // out_bf16[m][n] = bf16(acc + bias)
   EPI_F32_PUSH = 6,  // tensor parallel, decode: raw fp32 partial PUSHED into every rank's receive slot over NVLink
+  EPI_GELU = 7,      // out_bf16[m][n] = bf16(gelu_erf(bf16(acc)))                       (Falcon dense_h_to_4h + act)
+  EPI_RESID2 = 8,    // out_bf16[m][n] = bf16(bf16(bf16(acc) + resid2[m][n]) + resid[m][n]) (Falcon parallel block:
+                     //                  mlp_out += attn_out; out = mlp_out + residual)
 };
 
-enum NormKind : int { NORM_NONE = 0, NORM_RMS = 1 };
+enum NormKind : int { NORM_NONE = 0, NORM_RMS = 1, NORM_LN = 2 };  // LN = LayerNorm with weight and bias (Falcon)
 
 struct GemvArgs {
   // y[M, N] = x[M, K] * W[N, K]^T ; W bf16 row-major (physical row order, see DESIGN.md "weight layout")
@@ -25,12 +28,15 @@ struct GemvArgs {
   const bf16* x;  // [*, ldx]
   int ldx, M;
   const int* row_map;  // optional: tile row m reads x row row_map[m]
-  const bf16* norm_w;  // NORM_RMS: weight[K]
+  const bf16* norm_w;  // NORM_RMS / NORM_LN: weight[K]
+  const bf16* norm_b;  // NORM_LN: bias[K]
   float eps;
   // outputs
   float* out_f32;
   bf16* out_bf16;
   const bf16* resid;
+  const bf16* resid2;    // EPI_RESID2
+  const float* f32_add;  // EPI_F32: optional fp32 addend with the layout of out_f32 (Falcon TP: attn partial + mlp partial)
   int ld_out;
   // EPI_QKV_ROPE
   bf16* q_out;       // [M, q_rows]

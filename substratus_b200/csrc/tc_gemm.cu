@@ -284,8 +284,78 @@ cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int t
     case EPI_RESID: return launch_tc_e<EPI_RESID>(tn, tmA, tmB, a, lc);
     case EPI_BF16: return launch_tc_e<EPI_BF16>(tn, tmA, tmB, a, lc);
     case EPI_F32: return launch_tc_e<EPI_F32>(tn, tmA, tmB, a, lc);
+    case EPI_GELU: return launch_tc_e<EPI_GELU>(tn, tmA, tmB, a, lc);
+    case EPI_RESID2: return launch_tc_e<EPI_RESID2>(tn, tmA, tmB, a, lc);
   }
   return cudaErrorInvalidValue;
+}
+
+// LayerNorm (prefill): y = bf16((x - mean) * rstd * w + b), fp32 statistics   HF:models/falcon/modeling_falcon.py:572-576
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                        bf16* __restrict__ out, int K, float eps) {
+  __shared__ float red[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const bf16* src = x + (size_t)m * K;
+  float sm = 0.f;
+  for (int k = tid * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm += bf_lo(u[i]) + bf_hi(u[i]);
+  }
+  sm = warp_sum(sm);
+  if ((tid & 31) == 0) red[tid >> 5] = sm;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  __syncthreads();
+  const float mean = tot / (float)K;
+  float sq = 0.f;
+  for (int k = tid * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = bf_lo(u[i]) - mean, hi = bf_hi(u[i]) - mean;
+      sq += lo * lo + hi * hi;
+    }
+  }
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)K + eps);
+  for (int k = tid * 8; k < K; k += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+    const uint4 wv = ldg128(w + k);
+    const uint4 bv = ldg128(b + k);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+    const uint32_t bu[4] = {bv.x, bv.y, bv.z, bv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = pack_bf16((bf_lo(u[i]) - mean) * rstd * bf_lo(wu[i]) + bf_lo(bu[i]), (bf_hi(u[i]) - mean) * rstd * bf_hi(wu[i]) + bf_hi(bu[i]));
+    *reinterpret_cast<uint4*>(out + (size_t)m * K + k) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_layernorm(const bf16* x, const bf16* w, const bf16* b, bf16* out, int M, int K, float eps, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M);
+  cfg.blockDim = dim3(256);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, layernorm_kernel, x, w, b, out, K, eps);
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm (prefill)

@@ -13,3 +13,4 @@ int tc_weight_box_rows();       // 128
 // Y = X * W^T with the fused epilogue `epi` (GemvEpi); tmA = weights (box 128 rows), tmB = activations (box tn rows)
 cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc);
 cudaError_t launch_rmsnorm(const bf16* x, const bf16* w, bf16* out, int M, int K, float eps, const LaunchCfg& lc);
+cudaError_t launch_layernorm(const bf16* x, const bf16* w, const bf16* b, bf16* out, int M, int K, float eps, const LaunchCfg& lc);

@@ -48,6 +48,24 @@ def test_oracle_matches_hf_live():
         assert torch.equal(got, want)
 
 
+def test_falcon_oracle_matches_hf_live():
+    """oracle/falcon_ref.py == HF FalconForCausalLM (eager, new decoder architecture) bit-for-bit, bf16 and fp32,
+    for GQA (kv=2) and MQA-like (kv=1) groupings, forward and greedy generation."""
+    from oracle import falcon_ref as fr
+
+    for kv in (2, 1):
+        cfg = dict(fr.TINY_FALCON, num_kv_heads=kv)
+        sd = fr.falcon_state_dict(cfg, 5)
+        ids = torch.randint(0, cfg["vocab_size"], (2, 13), generator=torch.Generator().manual_seed(1))
+        for dt in (torch.bfloat16, torch.float32):
+            hf = fr.hf_model(cfg, sd, dt)
+            with torch.no_grad():
+                want = hf(ids).logits
+                out = hf.generate(ids, max_new_tokens=5, do_sample=False, pad_token_id=0)[:, 13:]
+            assert torch.equal(fr.FalconRef(cfg, sd, dt).forward(ids), want)
+            assert torch.equal(fr.FalconRef(cfg, sd, dt).generate(ids, 5)[0], out)
+
+
 def test_oracle_incremental_equals_full():
     """KV-cache decode of the restatement equals a full re-forward (property the CUDA path is also held to)."""
     cfg = synth.TINY_MHA
