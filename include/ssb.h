@@ -112,6 +112,10 @@ int ssb_tp_connect(ssb_engine* e, const void* all_handles, int n_ranks);
 int ssb_bench_kernel(ssb_engine* e, const char* which, int rows, int ctx, int iters, double* ms_per_launch,
                      int64_t* algorithmic_bytes);
 
+/* Per-kernel-class device time (ms, JSON object) accumulated over the forwards since the last call, for engines
+ * created with params.profile_forward=1 (CUDA events between plain stream-ordered launches; no graph, no PDL). */
+const char* ssb_debug_profile(ssb_engine* e);
+
 /* Debug/parity taps (tests only): copy an internal activation of the LAST forward
  * to host as fp32.  name: "h" (residual stream after the last layer), "q0", "attn0",
  * "h0" (layer-0 taps).  rows/cols returned through the out params. */

@@ -189,3 +189,140 @@ cudaError_t launch_attn_gqa(const AttnArgs& a, int gc, const LaunchCfg& lc) {
   }
   return cudaErrorInvalidValue;
 }
+
+// =====================================================================================================================
+// prefill attention: a CTA owns a tile of up to 16 consecutive query rows of one sequence and one query head; the
+// causal key range [0, pos_last] is streamed through shared memory in 64-token chunks (K and V staged once per chunk
+// for all 16 queries instead of once per query), each warp carries two query rows with fp32 online softmax.
+// Same rounding points as the decode kernels (scores rounded to bf16, scaled in bf16, fp32 softmax, fp32 P.V).
+// HF:models/llama/modeling_llama.py:199-221 with the causal mask of :399-406.
+// =====================================================================================================================
+constexpr int PF_ROWS = 16, PF_WARPS = 8;
+
+template <int D>
+__global__ void __launch_bounds__(PF_WARPS * 32) attn_prefill_kernel(const AttnArgs a) {
+  constexpr int LPR = D / 8, RPW = 32 / LPR;
+  __shared__ __align__(16) bf16 sK[GQ_TOK][D];
+  __shared__ __align__(16) bf16 sV[GQ_TOK][D];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int kvh = head / a.group;
+  const int row0 = a.tile_row0[tile], nrows = a.tile_nrows[tile];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int slot = a.row_slot[row0];
+  const int BS = a.block_size;
+  const int HD = a.n_heads * D;
+  const int* bt = a.block_table + (size_t)slot * a.bt_stride;
+  const int ctx = a.row_pos[row0 + nrows - 1] + 1;  // keys needed by the last row of the tile
+
+  int pos[2];
+  float q[2][8], m[2], l[2], acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int rr = warp * 2 + r;
+    pos[r] = rr < nrows ? a.row_pos[row0 + rr] : -1;
+    m[r] = -1e30f;
+    l[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f, q[r][i] = 0.f;
+    if (rr < nrows) {
+      const uint4 v = *reinterpret_cast<const uint4*>(a.q + (size_t)(row0 + rr) * HD + head * D + li * 8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        q[r][2 * i] = bf_lo(u[i]);
+        q[r][2 * i + 1] = bf_hi(u[i]);
+      }
+    }
+  }
+  for (int p0 = 0; p0 < ctx; p0 += GQ_TOK) {
+    const int np = min(GQ_TOK, ctx - p0);
+    if (p0) __syncthreads();
+    for (int i = tid; i < np * LPR; i += PF_WARPS * 32) {
+      const int tt = i / LPR, c = i % LPR;
+      const int t = p0 + tt;
+      const size_t off = (((size_t)bt[t / BS] * a.kvh + kvh) * BS + (t % BS)) * D + c * 8;
+      cp_async16(&sK[tt][c * 8], a.kcache + off);
+      cp_async16(&sV[tt][c * 8], a.vcache + off);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int lim = min(np, pos[r] - p0 + 1);  // keys of this chunk visible to row r (<= 0: none); warp-uniform
+      for (int tb = 0; tb < lim; tb += RPW) {
+        const int tt = tb + sub;
+        const bool tv = tt < lim;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (tv) {
+          kv = *reinterpret_cast<const uint4*>(&sK[tt][li * 8]);
+          vv = *reinterpret_cast<const uint4*>(&sV[tt][li * 8]);
+        }
+        const uint32_t ku[4] = {kv.x, kv.y, kv.z, kv.w};
+        const uint32_t vu[4] = {vv.x, vv.y, vv.z, vv.w};
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          d = fmaf(q[r][2 * i], bf_lo(ku[i]), d);
+          d = fmaf(q[r][2 * i + 1], bf_hi(ku[i]), d);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (!tv) continue;
+        const float s = bf16r(bf16r(d) * a.scale);
+        const float mn = fmaxf(m[r], s);
+        const float corr = __expf(m[r] - mn), p = __expf(s - mn);
+        m[r] = mn;
+        l[r] = l[r] * corr + p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[r][2 * i] = fmaf(p, bf_lo(vu[i]), acc[r][2 * i] * corr);
+          acc[r][2 * i + 1] = fmaf(p, bf_hi(vu[i]), acc[r][2 * i + 1] * corr);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m[r], o);
+      const float ol = __shfl_xor_sync(0xffffffffu, l[r], o);
+      const float mn = fmaxf(m[r], om);
+      const float wa = __expf(m[r] - mn), wb = __expf(om - mn);
+      l[r] = l[r] * wa + ol * wb;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float oa = __shfl_xor_sync(0xffffffffu, acc[r][i], o);
+        acc[r][i] = acc[r][i] * wa + oa * wb;
+      }
+      m[r] = mn;
+    }
+    const int rr = warp * 2 + r;
+    if (rr < nrows && sub == 0) {
+      const float inv = 1.0f / l[r];
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = pack_bf16(acc[r][2 * i] * inv, acc[r][2 * i + 1] * inv);
+      *reinterpret_cast<uint4*>(a.out + (size_t)(row0 + rr) * HD + head * D + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+cudaError_t launch_attn_prefill(const AttnArgs& a, const LaunchCfg& lc) {
+  if (a.n_tiles <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.n_tiles, a.n_heads);
+  cfg.blockDim = dim3(PF_WARPS * 32);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  if (a.head_dim == 128) return cudaLaunchKernelEx(&cfg, attn_prefill_kernel<128>, a);
+  if (a.head_dim == 64) return cudaLaunchKernelEx(&cfg, attn_prefill_kernel<64>, a);
+  return cudaErrorInvalidValue;
+}

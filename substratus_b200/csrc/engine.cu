@@ -365,6 +365,32 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
   return rc;
 }
 
+void Engine::prof_mark(const char* label) {
+  if (!prof_fwd_) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, stream_);
+  prof_marks_.emplace_back(label, e);
+}
+void Engine::prof_collect() {
+  if (!prof_fwd_ || prof_marks_.empty()) return;
+  cudaStreamSynchronize(stream_);
+  for (size_t i = 1; i < prof_marks_.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, prof_marks_[i - 1].second, prof_marks_[i].second);
+    prof_ms_[prof_marks_[i].first] += ms;  // time since the previous mark is attributed to the kernel that just ran
+  }
+  for (auto& m : prof_marks_) cudaEventDestroy(m.second);
+  prof_marks_.clear();
+}
+std::string Engine::prof_report() {
+  prof_collect();
+  std::string s = "{";
+  for (auto& kv : prof_ms_) s += (s.size() > 1 ? "," : "") + std::string("\"") + kv.first + "\":" + std::to_string(kv.second);
+  prof_ms_.clear();
+  return s + "}";
+}
+
 int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
@@ -442,6 +468,8 @@ int Engine::alloc_runtime(const Json& params) {
   TRY(dmalloc(&row_slot_, (size_t)m_max_));
   TRY(dmalloc(&row_pos_, (size_t)m_max_));
   TRY(dmalloc(&logit_rows_, (size_t)max_batch_));
+  TRY(dmalloc(&tile_row0_, (size_t)m_max_));
+  TRY(dmalloc(&tile_nrows_, (size_t)m_max_));
   TRY(dmalloc(&next_tok_, (size_t)max_batch_));
   TRY(dmalloc(&hist_, (size_t)max_steps_ * max_batch_));
   TRY(dmalloc(&step_, 1));
@@ -469,8 +497,18 @@ int Engine::alloc_runtime(const Json& params) {
   free_blocks_.resize(n_blocks_);
   for (int i = 0; i < n_blocks_; ++i) free_blocks_[i] = n_blocks_ - 1 - i;
   slots_.assign(max_batch_, SeqSlot());
+  {  // stream-K workspace of the tensor-core decode projections
+    float* skp = nullptr;
+    unsigned* skf = nullptr;
+    const int slots = 2 * n_sm_;
+    TRY(dmalloc(&skp, (size_t)slots * 64 * 128));
+    TRY(dmalloc(&skf, (size_t)slots));
+    CK(cudaMemset(skf, 0, slots * sizeof(unsigned)));
+    if (params.get_int("tc_streamk", 1) != 0) tc_set_streamk_workspace(skp, skf, slots);
+    else tc_set_streamk_workspace(nullptr, nullptr, 0);
+  }
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
-  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1 && !cfg_.falcon;
+  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1 && !cfg_.falcon && !prof_fwd_;
   if (use_mega_) {
     const int group = cfg_.heads / cfg_.kv_heads, ag = mega_attn_group(group);
     const int ch = mega_attn_chunk(D, ag);
@@ -534,9 +572,11 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ev0_));
   CK(cudaEventCreate(&ev1_));
+  prof_fwd_ = params.get_int("profile_forward", 0) != 0;
   use_pdl_ = params.get_int("use_pdl", 1) != 0;
   tp_push_ = params.get_int("tp_push", 0) != 0;  // push-model allreduce: measured slower than pull on B200
   use_graph_ = params.get_int("use_graph", 1) != 0;
+  if (prof_fwd_) use_pdl_ = use_graph_ = false;  // event marks between launches need plain stream order
   if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
   TRY(alloc_weights());
   TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0)));
@@ -558,6 +598,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
       CK(tc_make_tmap(&w.tm_gu, w.wgu, (cfg_.falcon ? 1 : 2) * (int64_t)Il_, h, h, br));
       CK(tc_make_tmap(&w.tm_down, w.wdown, h, Il_, Il_, br));
     }
+    CK(tc_make_tmap(&tm_lm_head_, lm_head_, cfg_.vocab, h, h, br));
   }
   CK(cudaStreamSynchronize(stream_));
   timing_reset();
@@ -650,7 +691,9 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
   // push-model allreduce (decode-sized forwards on the GEMV path): partials are written straight into every rank's
   // receive slots by the projection epilogue; pull model otherwise (prefill / tensor-core path)
   const bool tp_push = tp && tp_push_ && M <= 4 && M < tc_min_rows_ && M <= max_batch_;
+  prof_mark("start");
   CK(launch_embed(embed_, row_tok_, h_, M, h, decode_mode ? step_ : nullptr, tp_step_, tp_push ? tp_push_step_ : nullptr, lc(true)));
+  prof_mark("embed");
   TpArgs ta = {};
   if (tp) {
     ta.rank = tp_rank_;
@@ -726,11 +769,13 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     g.kvh = KVHl_;
     if (tc) {
       CK(launch_rmsnorm(h_, w.ln1, xn_, M, h, cfg_.eps, lc(true)));
+      prof_mark("norm");
       CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn, g, EPI_QKV_ROPE, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
     }
+    prof_mark("qkv");
 
     AttnArgs a = {};
     a.q = q_;
@@ -752,7 +797,14 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     a.block_size = block_size_;
     a.n_splits = n_splits;
     a.scale = 1.0f / sqrtf((float)D);
-    CK(launch_attn_decode(a, lc(true)));
+    a.tile_row0 = tile_row0_;
+    a.tile_nrows = tile_nrows_;
+    a.n_tiles = n_pf_tiles_;
+    if (n_pf_tiles_ > 0)
+      CK(launch_attn_prefill(a, lc(true)));
+    else
+      CK(launch_attn_decode(a, lc(true)));
+    prof_mark("attn");
     if (taps_ && l == 0) {
       CK(cudaMemcpyAsync(tap_q0_, q_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
       CK(cudaMemcpyAsync(tap_attn0_, attn_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
@@ -775,6 +827,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
       CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(o, epi_rowpar, NORM_NONE, lc(true)));
+    prof_mark("o");
     if (tp_push) {
       CK(launch_tp_reduce_push(tpa, lc(true)));
       ++launches;
@@ -795,13 +848,16 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     u.eps = cfg_.eps;
     u.out_bf16 = act_;
     u.ld_out = Il_;
+    prof_mark("allreduce");
     if (tc) {
       CK(launch_rmsnorm(h_, w.ln2, xn_, M, h, cfg_.eps, lc(true)));
+      prof_mark("norm");
       CK(launch_tc_gemm(w.tm_gu, tm_xn, tn, u, EPI_SWIGLU, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(u, EPI_SWIGLU, NORM_RMS, lc(true)));
     }
+    prof_mark("gate_up");
 
     GemvArgs d = {};
     d.W = w.wdown;
@@ -819,6 +875,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
       CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(d, epi_rowpar, NORM_NONE, lc(true)));
+    prof_mark("down");
     if (tp_push) {
       CK(launch_tp_reduce_push(tpa, lc(true)));
       ++launches;
@@ -828,6 +885,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
       ++launches;
     }
     launches += 5;
+    prof_mark("allreduce");
     if (taps_ && l == 0) {
       CK(cudaMemcpyAsync(tap_h0_, h_, (size_t)M * h * 2, cudaMemcpyDeviceToDevice, stream_));
       tap_rows_ = M;
@@ -846,13 +904,21 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     g.eps = cfg_.eps;
     g.out_f32 = logits_;
     g.ld_out = cfg_.vocab;
-    CK(launch_gemv(g, EPI_F32_BF16R, NORM_RMS, lc(true)));
+    if (tc && decode_mode && n_logit_rows == M) {  // batched decode: lm_head on the tensor cores too (stream-K)
+      CK(launch_rmsnorm(h_, final_norm_, xn_, M, h, cfg_.eps, lc(true)));
+      CK(launch_tc_gemm(tm_lm_head_, tm_xn, tn, g, EPI_F32_BF16R, lc(true)));
+      ++launches;
+    } else {
+      CK(launch_gemv(g, EPI_F32_BF16R, NORM_RMS, lc(true)));
+    }
     CK(launch_argmax(logits_, cfg_.vocab, n_logit_rows, decode_mode ? row_tok_ : next_tok_, decode_mode ? hist_ : nullptr,
                      step_, decode_mode ? row_pos_ : nullptr, lc(true)));
     launches += 2;
+    prof_mark("lm_head+argmax");
   }
   launches_per_forward_ = launches;
   timing_.kernel_launches += launches;
+  prof_collect();
   return SSB_OK;
 }
 
@@ -902,7 +968,24 @@ int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, 
       CK(cudaMemcpyAsync(logit_rows_, lrows.data(), lrows.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
       timing_.h2d_bytes += (int64_t)(lrows.size() * sizeof(int));
     }
-    TRY(forward(M, (int)lrows.size(), false));
+    // query tiles for the tiled prefill attention: <= 16 consecutive rows of one sequence (rows are (slot, pos)-ordered)
+    std::vector<int> t0, tn_;
+    if (M > max_batch_ || M >= 16) {
+      for (int r = 0; r < M;) {
+        int n = 1;
+        while (n < 16 && r + n < M && r_slot[base + r + n] == r_slot[base + r]) ++n;
+        t0.push_back(r);
+        tn_.push_back(n);
+        r += n;
+      }
+      CK(cudaMemcpyAsync(tile_row0_, t0.data(), t0.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      CK(cudaMemcpyAsync(tile_nrows_, tn_.data(), tn_.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+      timing_.h2d_bytes += (int64_t)(2 * t0.size() * sizeof(int));
+    }
+    n_pf_tiles_ = (int)t0.size();
+    int frc = forward(M, (int)lrows.size(), false);
+    n_pf_tiles_ = 0;
+    TRY(frc);
     if (!lrows.empty()) {
       std::vector<int> tmp(lrows.size());
       CK(cudaMemcpyAsync(tmp.data(), next_tok_, lrows.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -1020,7 +1103,13 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     a.block_size = block_size_;
     a.n_splits = n_splits;
     a.scale = 1.0f / sqrtf((float)D);
-    CK(launch_attn_decode(a, lc(true)));
+    a.tile_row0 = tile_row0_;
+    a.tile_nrows = tile_nrows_;
+    a.n_tiles = n_pf_tiles_;
+    if (n_pf_tiles_ > 0)
+      CK(launch_attn_prefill(a, lc(true)));
+    else
+      CK(launch_attn_decode(a, lc(true)));
     if (taps_ && l == 0) {
       CK(cudaMemcpyAsync(tap_q0_, q_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
       CK(cudaMemcpyAsync(tap_attn0_, attn_, (size_t)M * Hl_ * D * 2, cudaMemcpyDeviceToDevice, stream_));
@@ -1291,6 +1380,15 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
     cudaMemsetAsync(q_, 0, (size_t)rows * Hl_ * D * 2, stream_);
   }
   int64_t bytes = 0;
+  const bool btc = rows >= tc_min_rows_ && !cfg_.falcon;  // mirror forward(): tensor-core projections from tc_min_rows up
+  const int btn = tc_pick_tn(rows);
+  TcTensorMap btm_xn, btm_attn, btm_act;
+  if (btc) {
+    CK(tc_make_tmap(&btm_xn, xn_, rows, h, h, btn));
+    CK(tc_make_tmap(&btm_attn, attn_, rows, (int64_t)Hl_ * D, (int64_t)Hl_ * D, btn));
+    CK(tc_make_tmap(&btm_act, act_, rows, Il_, Il_, btn));
+    cudaMemsetAsync(xn_, 0, (size_t)rows * h * 2, stream_);
+  }
   auto one = [&](int l) -> int {
     if (same_layer) l = 0;
     const LayerW& lwv = lw_[l % cfg_.layers];
@@ -1319,7 +1417,10 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.kvh = KVHl_;
       g.norm_b = lwv.ln1_b;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_QKV_ROPE, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
+      if (btc)
+        CK(launch_tc_gemm(lwv.tm_qkv, btm_xn, btn, g, EPI_QKV_ROPE, lc(true)));
+      else
+        CK(launch_gemv(g, EPI_QKV_ROPE, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
     } else if (w == "gate_up") {
       g.W = lwv.wgu;
       g.N = (cfg_.falcon ? 1 : 2) * Il_;
@@ -1328,7 +1429,10 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.out_bf16 = act_;
       g.ld_out = Il_;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, cfg_.falcon ? EPI_GELU : EPI_SWIGLU, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
+      if (btc)
+        CK(launch_tc_gemm(lwv.tm_gu, btm_xn, btn, g, EPI_SWIGLU, lc(true)));
+      else
+        CK(launch_gemv(g, cfg_.falcon ? EPI_GELU : EPI_SWIGLU, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
     } else if (w == "o") {
       g.W = lwv.wo;
       g.N = h;
@@ -1339,7 +1443,10 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.resid = h_;
       g.ld_out = h;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
+      if (btc)
+        CK(launch_tc_gemm(lwv.tm_o, btm_attn, btn, g, EPI_RESID, lc(true)));
+      else
+        CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
     } else if (w == "down") {
       g.W = lwv.wdown;
       g.N = h;
@@ -1350,7 +1457,10 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.resid = h_;
       g.ld_out = h;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
+      if (btc)
+        CK(launch_tc_gemm(lwv.tm_down, btm_act, btn, g, EPI_RESID, lc(true)));
+      else
+        CK(launch_gemv(g, EPI_RESID, NORM_NONE, lc(true)));
     } else if (w == "lm_head") {
       g.W = lm_head_;
       g.N = cfg_.vocab;
@@ -1664,6 +1774,12 @@ int ssb_tp_export(ssb_engine* e, void* handle_out) {
 int ssb_tp_connect(ssb_engine* e, const void* all_handles, int n_ranks) {
   GUARD(e);
   return all_handles ? e->impl.tp_connect(all_handles, n_ranks) : SSB_EINVAL;
+}
+const char* ssb_debug_profile(ssb_engine* e) {
+  static thread_local std::string rep;
+  if (!e) return "{}";
+  rep = e->impl.prof_report();
+  return rep.c_str();
 }
 int ssb_bench_kernel(ssb_engine* e, const char* which, int rows, int ctx, int iters, double* ms_per_launch,
                      int64_t* algorithmic_bytes) {

@@ -91,6 +91,7 @@ class Engine {
   // weights
   std::vector<LayerW> lw_;
   bf16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr, *final_norm_b_ = nullptr;
+  TcTensorMap tm_lm_head_;
   bf16* ao_ = nullptr;  // Falcon: attention-branch output of the parallel block
   float* falcon_scratch_ = nullptr;  // Falcon TP: local fp32 partial of the attention branch
   uint32_t* rope_cs_ = nullptr;
@@ -103,6 +104,8 @@ class Engine {
   int *counters_ = nullptr, *row_tok_ = nullptr, *row_slot_ = nullptr, *row_pos_ = nullptr, *logit_rows_ = nullptr;
   int *next_tok_ = nullptr, *hist_ = nullptr, *step_ = nullptr, *block_table_ = nullptr;
   int max_steps_ = 0;
+  int *tile_row0_ = nullptr, *tile_nrows_ = nullptr;  // prefill attention query tiles of the current forward
+  int n_pf_tiles_ = 0;                                 // 0 => decode-style attention
   // tensor parallel exchange (peer-mapped over NVLink; see tp_allreduce_resid_kernel)
   // one exported pool per rank: [partials 2*m_max*h f32 | recv 2*8*max_batch*h f32 | flags 8 u32 (64 B) | pflags 8 u64]
   uint8_t* tp_pool_ = nullptr;
@@ -132,6 +135,15 @@ class Engine {
   size_t hbm_bytes_ = 0;
   int64_t weight_bytes_step_ = 0;
   int launches_per_forward_ = 0;
+  // per-kernel-class event timing of one forward (params.profile_forward=1; tools/fwd_prof.py)
+  bool prof_fwd_ = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> prof_marks_;
+  std::map<std::string, double> prof_ms_;
+  void prof_mark(const char* label);
+  void prof_collect();
+ public:
+  std::string prof_report();
+ private:
   // stats
   mutable ssb_timing timing_ = {};
   int decode_splits_(int M) const;

@@ -85,3 +85,83 @@ SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, floa
   }
 }
 
+
+// Eight tokens at once for one row pair (tensor-core kernels: a thread owns a weight row across the token tile).
+// The per-token epilogue above does dependent global loads (residual, position, rope table, block table) followed by a
+// store; out_bf16 may alias resid, so the compiler cannot hoist the next token's loads above the previous store and
+// the tile epilogue degenerates into ~TN serialized L2 round trips (measured: 20 us per 128x32 tile).  Here all loads of
+// the eight tokens are issued first.
+template <int EPI>
+SSB_DEVINL void tc_epilogue8(const GemvArgs& a, int pair, int m0, const float (&v0)[8], const float (&v1)[8]) {
+  if constexpr (EPI == EPI_RESID || EPI == EPI_RESID2) {
+    uint32_t r[8], r2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r[j] = r2[j] = 0;
+      if (m0 + j < a.M) {
+        const size_t o = (size_t)(m0 + j) * a.ld_out + 2 * pair;
+        r[j] = __ldcg(reinterpret_cast<const uint32_t*>(a.resid + o));
+        if constexpr (EPI == EPI_RESID2) r2[j] = __ldcg(reinterpret_cast<const uint32_t*>(a.resid2 + o));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (m0 + j < a.M) {
+        const size_t o = (size_t)(m0 + j) * a.ld_out + 2 * pair;
+        float t0 = bf16r(v0[j]), t1 = bf16r(v1[j]);
+        if constexpr (EPI == EPI_RESID2) {
+          t0 = bf16r(t0 + bf_lo(r2[j]));
+          t1 = bf16r(t1 + bf_hi(r2[j]));
+        }
+        *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(t0 + bf_lo(r[j]), t1 + bf_hi(r[j]));
+      }
+    }
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int hd = a.head_dim, half = hd >> 1;
+    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+    int pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pos[j] = (m0 + j < a.M) ? __ldcg(a.row_pos + m0 + j) : 0;
+    const bool is_q = pair < q_pairs, is_k = !is_q && pair < q_pairs + k_pairs;
+    int blk[8];
+    if (!is_q) {
+      int slot[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) slot[j] = (m0 + j < a.M) ? a.row_slot[m0 + j] : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) blk[j] = (m0 + j < a.M) ? a.block_table[(size_t)slot[j] * a.bt_stride + pos[j] / a.block_size] : 0;
+    }
+    if (is_q || is_k) {
+      const int pp = is_q ? pair : pair - q_pairs;
+      const int head = pp / half, jj = pp - head * half;
+      uint32_t cs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] = a.rope_cs[(size_t)pos[j] * half + jj];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (m0 + j >= a.M) continue;
+        const float c = bf_lo(cs[j]), s = bf_hi(cs[j]);
+        const float x0 = bf16r(v0[j]), x1 = bf16r(v1[j]);
+        const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
+        const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
+        bf16* dst = is_q ? a.q_out + (size_t)(m0 + j) * a.q_rows + head * hd + jj
+                         : a.kcache + (((size_t)blk[j] * a.kvh + head) * a.block_size + (pos[j] % a.block_size)) * hd + jj;
+        dst[0] = __float2bfloat16_rn(y0);
+        dst[half] = __float2bfloat16_rn(y1);
+      }
+    } else {
+      const int e = 2 * (pair - q_pairs - k_pairs);
+      const int head = e / hd, jj = e - head * hd;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (m0 + j >= a.M) continue;
+        bf16* v = a.vcache + (((size_t)blk[j] * a.kvh + head) * a.block_size + (pos[j] % a.block_size)) * hd + jj;
+        *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0[j], v1[j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (m0 + j < a.M) gemv_epilogue<1, EPI>(a, pair, m0 + j, v0[j], v1[j]);
+  }
+}

@@ -185,17 +185,227 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[8];
         tc_ld8(taddr + c, v);
         tc_wait_ld();
+        float mine[8], other[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float mine = __uint_as_float(v[j]);
-          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-          const int m = mt * TN + c + j;
-          if (!(lane & 1) && row < a.N && m < a.M) gemv_epilogue<1, EPI>(a, row >> 1, m, mine, other);
+          mine[j] = __uint_as_float(v[j]);
+          other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
         }
+        if (!(lane & 1) && row < a.N) tc_epilogue8<EPI>(a, row >> 1, mt * TN + c, mine, other);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ====================================================================================================================
+// stream-K variant for ONE token tile (batched decode, M <= TN <= 64): the (weight tile, k-block) units of the whole
+// matrix are laid end to end and every CTA streams an equal contiguous share, so all SMs pull the same number of weight
+// bytes no matter how many 128-row tiles N has (a 4096-row matrix is only 32 tiles for 148 SMs).  A tile whose k-range
+// is split over several CTAs is reduced through a small fp32 workspace: the parts that do not start at k = 0 are
+// written out ("contributors"), the CTA holding the k = 0 part ("owner" — it reaches that part LAST in its own range,
+// when the others are already done) adds them to its TMEM accumulator in registers and runs the fused epilogue.
+// Dependencies only point from higher to lower CTA index ranges that are processed earlier, so there is no cycle.
+// ====================================================================================================================
+struct SkWs {
+  float* part;      // [slots][TN/8][128][8] fp32
+  unsigned* flags;  // [slots], zero on entry and on exit
+};
+
+template <int TN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemvArgs a, const SkWs ws) {
+  using Cfg = TcCfg<TN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ntiles = (a.N + TC_BM - 1) / TC_BM;
+  const int nkb = (a.K + TC_BK - 1) / TC_BK;
+  const long long U = (long long)n_ntiles * nkb;
+  const long long G = gridDim.x;
+  const long long u0 = (long long)blockIdx.x * U / G, u1 = (long long)(blockIdx.x + 1) * U / G;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer.  The weight (A) stream does not
+    // depend on the previous kernel: it starts before griddepcontrol.wait; the activation (B) loads wait for it.
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool waited = false;
+      for (long long u = u0; u < u1; ++u) {
+        const int nt = (int)(u / nkb), kb = (int)(u % nkb);
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_2d(sa, &tmA, kb * TC_BK, nt * TC_BM, &full[stage]);
+        if (!waited) {
+          pdl_wait();
+          waited = true;
+        }
+        tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * TC_BK, 0, &full[stage]);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (long long u = u0; u < u1; ++it) {
+      const int kb0 = (int)(u % nkb);
+      const int kb1 = (int)min((long long)nkb, kb0 + (u1 - u));
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint64_t ad = umma_desc_k_sw128(sa);
+          const uint64_t bd = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma_bf16(tmem_base + acc * TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > kb0) || k != 0);
+          tc_commit(&empty[stage]);
+          if (kb == kb1 - 1) tc_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      u += kb1 - kb0;
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    pdl_wait();  // residuals / positions written by the previous kernel
+    const int quad = warp & 3;
+    const int erow = quad * 32 + lane;  // row inside the 128-row tile
+    int it = 0;
+    for (long long u = u0; u < u1; ++it) {
+      const int nt = (int)(u / nkb), kb0 = (int)(u % nkb);
+      const int kb1 = (int)min((long long)nkb, kb0 + (u1 - u));
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const bool is_first_seg = (u == u0);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN;
+      const int row = nt * TC_BM + erow;
+      if (kb0 != 0) {
+        // contributor: dump the partial accumulator to this CTA's slot (slot 0 = first segment of the range, else 1)
+        const int slot = blockIdx.x * 2 + (is_first_seg ? 0 : 1);
+        float* dst = ws.part + (size_t)slot * (TN * 128);
+#pragma unroll 1
+        for (int c = 0; c < TN; c += 8) {
+          uint32_t v[8];
+          tc_ld8(taddr + c, v);
+          tc_wait_ld();
+          float4* d4 = reinterpret_cast<float4*>(dst + ((size_t)(c / 8) * 128 + erow) * 8);
+          d4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        }
+        tc_fence_before();
+        __threadfence();
+        named_bar_sync(2, 128);
+        if (warp == 2 && lane == 0) {
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.flags + slot), "r"(1u) : "memory");
+          mbar_arrive(&tempty[acc]);
+        } else if (lane == 0) {
+          mbar_arrive(&tempty[acc]);
+        }
+      } else {
+        // owner: the part starting at k = 0.  Contributors = the CTAs whose ranges cover the rest of this tile.
+        const long long t_end = (long long)(nt + 1) * nkb;          // first unit after this tile
+        long long cu = u + (kb1 - kb0);                               // first unit not covered by this CTA
+        int n_contrib = 0;
+        int cslot[12];  // the launcher sizes the grid so that a tile is never split over more than 10 CTAs
+        for (long long c = blockIdx.x + 1; cu < t_end && c < G && n_contrib < 12; ++c) {
+          const long long c0 = c * U / G, c1 = (c + 1) * U / G;
+          if (c1 <= c0) continue;
+          // CTA c's segment inside this tile starts at max(c0, cu) == c0 (ranges are contiguous) and is its FIRST segment
+          cslot[n_contrib++] = (int)c * 2 + 0;
+          cu = c1;
+        }
+        for (int i = 0; i < n_contrib; ++i) {
+          unsigned f;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(ws.flags + cslot[i]) : "memory");
+          } while (f == 0u);
+        }
+#pragma unroll 1
+        for (int c = 0; c < TN; c += 8) {
+          if (c >= a.M) break;
+          uint32_t v[8];
+          tc_ld8(taddr + c, v);
+          tc_wait_ld();
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]);
+          for (int i = 0; i < n_contrib; ++i) {
+            const float4* p4 = reinterpret_cast<const float4*>(ws.part + (size_t)cslot[i] * (TN * 128) + ((size_t)(c / 8) * 128 + erow) * 8);
+            const float4 x = __ldcg(p4), y = __ldcg(p4 + 1);
+            f[0] += x.x; f[1] += x.y; f[2] += x.z; f[3] += x.w;
+            f[4] += y.x; f[5] += y.y; f[6] += y.z; f[7] += y.w;
+          }
+          float other[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) other[j] = __shfl_xor_sync(0xffffffffu, f[j], 1);
+          if (!(lane & 1) && row < a.N) tc_epilogue8<EPI>(a, row >> 1, c, f, other);
+        }
+        tc_fence_before();
+        named_bar_sync(2, 128);  // every epilogue thread has consumed the partials
+        if (warp == 2 && lane == 0)
+          for (int i = 0; i < n_contrib; ++i) ws.flags[cslot[i]] = 0;  // clean for the next launch
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      u += kb1 - kb0;
     }
   }
   tc_fence_before();
@@ -275,9 +485,71 @@ static cudaError_t launch_tc_e(int tn, const TcTensorMap& tmA, const TcTensorMap
   return cudaErrorInvalidValue;
 }
 
+static SkWs g_sk_ws = {nullptr, nullptr};
+static int g_sk_slots = 0;
+void tc_set_streamk_workspace(float* part, unsigned* flags, int slots) {
+  g_sk_ws.part = part;
+  g_sk_ws.flags = flags;
+  g_sk_slots = slots;
+}
+
+template <int TN, int EPI>
+static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
+  using Cfg = TcCfg<TN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_sk_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int nkb = (a.K + TC_BK - 1) / TC_BK;
+  const long long U = (long long)((a.N + TC_BM - 1) / TC_BM) * nkb;
+  const long long min_units = (nkb + 7) / 8;  // >= nkb/8 units per CTA: a tile spans at most 8 full + 2 partial ranges
+  long long gmax = U / min_units;
+  int grid = (int)(gmax < 1 ? 1 : (gmax < lc.n_sm ? gmax : lc.n_sm));
+  if (grid * 2 > g_sk_slots) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, tc_gemm_sk_kernel<TN, EPI>, *reinterpret_cast<const CUtensorMap*>(&tmA),
+                            *reinterpret_cast<const CUtensorMap*>(&tmB), a, g_sk_ws);
+}
+
+template <int EPI>
+static cudaError_t launch_sk_e(int tn, const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
+  switch (tn) {
+    case 16: return launch_sk_t<16, EPI>(tmA, tmB, a, lc);
+    case 32: return launch_sk_t<32, EPI>(tmA, tmB, a, lc);
+    case 64: return launch_sk_t<64, EPI>(tmA, tmB, a, lc);
+  }
+  return cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_tc_streamk(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc) {
+  switch (epi) {
+    case EPI_QKV_ROPE: return launch_sk_e<EPI_QKV_ROPE>(tn, tmA, tmB, a, lc);
+    case EPI_SWIGLU: return launch_sk_e<EPI_SWIGLU>(tn, tmA, tmB, a, lc);
+    case EPI_RESID: return launch_sk_e<EPI_RESID>(tn, tmA, tmB, a, lc);
+    case EPI_BF16: return launch_sk_e<EPI_BF16>(tn, tmA, tmB, a, lc);
+    case EPI_F32: return launch_sk_e<EPI_F32>(tn, tmA, tmB, a, lc);
+    case EPI_GELU: return launch_sk_e<EPI_GELU>(tn, tmA, tmB, a, lc);
+    case EPI_RESID2: return launch_sk_e<EPI_RESID2>(tn, tmA, tmB, a, lc);
+    case EPI_F32_BF16R: return launch_sk_e<EPI_F32_BF16R>(tn, tmA, tmB, a, lc);
+  }
+  return cudaErrorInvalidValue;
+}
+
 // tmB must have been built with box_rows == tn
 cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc) {
   if ((a.N & 1) || (a.K & 7)) return cudaErrorInvalidValue;
+  if (a.M <= tn && tn <= 64 && g_sk_ws.part && !a.row_map) return launch_tc_streamk(tmA, tmB, tn, a, epi, lc);  // batched decode
   switch (epi) {
     case EPI_QKV_ROPE: return launch_tc_e<EPI_QKV_ROPE>(tn, tmA, tmB, a, lc);
     case EPI_SWIGLU: return launch_tc_e<EPI_SWIGLU>(tn, tmA, tmB, a, lc);
@@ -286,6 +558,7 @@ cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int t
     case EPI_F32: return launch_tc_e<EPI_F32>(tn, tmA, tmB, a, lc);
     case EPI_GELU: return launch_tc_e<EPI_GELU>(tn, tmA, tmB, a, lc);
     case EPI_RESID2: return launch_tc_e<EPI_RESID2>(tn, tmA, tmB, a, lc);
+    case EPI_F32_BF16R: return launch_tc_e<EPI_F32_BF16R>(tn, tmA, tmB, a, lc);
   }
   return cudaErrorInvalidValue;
 }

@@ -45,7 +45,7 @@ class SsbTiming(C.Structure):
 EXPORTS = [
     "ssb_engine_create", "ssb_engine_destroy", "ssb_engine_info", "ssb_seq_create", "ssb_seq_free", "ssb_seq_len",
     "ssb_prefill", "ssb_decode", "ssb_last_timing", "ssb_timing_reset", "ssb_tp_handle_size", "ssb_tp_export",
-    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version",
+    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_profile", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version",
 ]
 
 
@@ -77,6 +77,8 @@ def load_library(path: str | None = None):
     lib.ssb_tp_connect.argtypes = [vp, vp, C.c_int]
     lib.ssb_bench_kernel.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                                      C.POINTER(C.c_int64)]
+    lib.ssb_debug_profile.argtypes = [vp]
+    lib.ssb_debug_profile.restype = C.c_char_p
     lib.ssb_debug_read.argtypes = [vp, C.c_char_p, fp, C.c_int64, ip, ip]
     lib.ssb_debug_dequant.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint16)]
     lib.ssb_synth_fill_host.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_float, C.c_float,
@@ -210,6 +212,10 @@ class Engine:
         ms, by = C.c_double(), C.c_int64()
         _check(self._lib, self._lib.ssb_bench_kernel(self._h, which.encode(), rows, ctx, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def profile(self) -> dict:
+        """Per-kernel-class device ms since the last call (engines created with profile_forward=1)."""
+        return json.loads(self._lib.ssb_debug_profile(self._h).decode())
 
     def debug_read(self, name: str) -> np.ndarray:
         r, c = C.c_int(), C.c_int()
