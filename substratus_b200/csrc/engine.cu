@@ -968,12 +968,13 @@ int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, 
       CK(cudaMemcpyAsync(logit_rows_, lrows.data(), lrows.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
       timing_.h2d_bytes += (int64_t)(lrows.size() * sizeof(int));
     }
-    // query tiles for the tiled prefill attention: <= 16 consecutive rows of one sequence (rows are (slot, pos)-ordered)
+    // query tiles of the tensor-pipe prefill attention: <= 64 consecutive rows of one sequence (rows are (slot, pos)-ordered)
     std::vector<int> t0, tn_;
     if (M > max_batch_ || M >= 16) {
+      const int tq = attn_prefill_tile_rows();
       for (int r = 0; r < M;) {
         int n = 1;
-        while (n < 16 && r + n < M && r_slot[base + r + n] == r_slot[base + r]) ++n;
+        while (n < tq && r + n < M && r_slot[base + r + n] == r_slot[base + r]) ++n;
         t0.push_back(r);
         tn_.push_back(n);
         r += n;

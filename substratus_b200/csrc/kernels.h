@@ -73,7 +73,7 @@ struct AttnArgs {
   int* counters;  // [M][H_local/GC], zero on entry, zero on exit
   int M, n_heads, kvh, group, head_dim, block_size, n_splits;
   float scale;
-  // prefill (attn_prefill_kernel): query tiles of <= 16 consecutive rows of ONE sequence, positions increasing
+  // prefill (attn_prefill_kernel): query tiles of <= 64 consecutive rows of ONE sequence, consecutive positions
   const int* tile_row0;
   const int* tile_nrows;
   int n_tiles;
@@ -90,6 +90,7 @@ int gemv_pick_bt(int M, int K);
 int gemv_grid_ctas(int M, int N, int K, int n_sm);  // CTAs launch_gemv will use (arrival count of the push allreduce)
 cudaError_t launch_attn_decode(const AttnArgs& a, const LaunchCfg& lc);
 cudaError_t launch_attn_prefill(const AttnArgs& a, const LaunchCfg& lc);
+int attn_prefill_tile_rows();  // query rows per prefill-attention tile (64)
 // h[m][:] = embed[row_tok[m]][:]; thread 0 of block 0 also does (*step_counter)++ when non-null
 cudaError_t launch_embed(const bf16* embed, const int* row_tok, bf16* h, int M, int hidden, int* step_counter,
                          int* fwd_counter, int* push_counter, const LaunchCfg& lc);
