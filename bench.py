@@ -209,7 +209,6 @@ def main():
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    import numpy as np
     import torch
 
     from substratus_b200 import Engine
@@ -217,17 +216,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the serving path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = WORKLOADS[args.workload]
-    B = args.batch
     peak_gbs, peak_src = load_peaks()
     tmp = tempfile.mkdtemp(prefix="ssb_bench_")
     with open(os.path.join(tmp, "config.json"), "w") as f:
         json.dump(cfg, f)
-    params = {"weights": "synthetic", "seed": 0, "max_batch": max(B, 32), "max_seq_len": PROMPT_LEN + NEW_TOKENS + 16,
+    params = {"weights": "synthetic", "seed": 0, "max_batch": max(args.batch, 32), "max_seq_len": PROMPT_LEN + NEW_TOKENS + 16,
               "use_pdl": args.pdl, "use_graph": args.graph, "device": local_rank, "tp_size": world, "tp_rank": rank}
     t_load = time.time()
     eng = Engine(tmp, params)
@@ -237,21 +236,7 @@ def main():
         tp.connect(eng)  # all-gather the CUDA-IPC handles of the exchange buffers; allreduce then runs over NVLink
     t_load = time.time() - t_load
     info = eng.info
-    prompts = synthetic_prompts(cfg["vocab_size"], B, PROMPT_LEN)
-
-    def one_request():
-        sids = [eng.seq_create() for _ in range(B)]
-        w0 = time.perf_counter()
-        first, _ = eng.prefill(sids, prompts)
-        w1 = time.perf_counter()
-        pre_ms = eng.timing().prefill_ms
-        toks, _ = eng.decode(sids, first, NEW_TOKENS - 1)
-        w2 = time.perf_counter()
-        dec_ms = eng.timing().decode_ms
-        for s in sids:
-            eng.seq_free(s)
-        return dict(ttft_wall_ms=(w1 - w0) * 1e3, prefill_dev_ms=pre_ms, decode_dev_ms=dec_ms,
-                    decode_wall_ms=(w2 - w1) * 1e3, total_wall_ms=(w2 - w0) * 1e3, last=int(toks[0, -1]))
+    ctx_mean = PROMPT_LEN + (NEW_TOKENS - 1) / 2.0 + 0.5
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,71 +244,105 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_request()
-    eng.timing_reset()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    recs = [one_request() for _ in range(args.steps)]
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    if world > 1:  # the slowest rank defines every time (device-timed per rank, MAX over ranks)
-        from substratus_b200 import tp
+    def measure(B, steps, warmup):
+        """K timed request batches of size B after W warm-ups; device times are MAX over ranks."""
+        prompts = synthetic_prompts(cfg["vocab_size"], B, PROMPT_LEN)
 
-        wall = tp.max_over_ranks(wall)
-        for r in recs:
-            for k in ("ttft_wall_ms", "prefill_dev_ms", "decode_dev_ms", "decode_wall_ms", "total_wall_ms"):
-                r[k] = tp.max_over_ranks(r[k])
-    tm = eng.timing()
-    ntok = B * (NEW_TOKENS - 1)
-    dec_dev_s = sum(r["decode_dev_ms"] for r in recs) / 1e3
-    dec_wall_s = sum(r["decode_wall_ms"] for r in recs) / 1e3
-    value = args.steps * ntok / dec_dev_s
-    e2e = args.steps * ntok / dec_wall_s
-    ctx_mean = PROMPT_LEN + (NEW_TOKENS - 1) / 2.0 + 0.5
-    bytes_step = info.weight_bytes_per_step + B * ctx_mean * info.kv_bytes_per_token
-    step_ms = dec_dev_s * 1e3 / (args.steps * (NEW_TOKENS - 1))
-    step_gbs = bytes_step / (step_ms * 1e-3) / 1e9
+        def one_request():
+            sids = [eng.seq_create() for _ in range(B)]
+            w0 = time.perf_counter()
+            first, _ = eng.prefill(sids, prompts)  # host ids in (H2D inside), first token id back on the host
+            w1 = time.perf_counter()
+            pre_ms = eng.timing().prefill_ms
+            eng.decode(sids, first, NEW_TOKENS - 1)  # 127 device-resident steps, ids back on the host (D2H inside)
+            w2 = time.perf_counter()
+            dec_ms = eng.timing().decode_ms
+            for s in sids:
+                eng.seq_free(s)
+            return dict(ttft_wall_ms=(w1 - w0) * 1e3, prefill_dev_ms=pre_ms, decode_dev_ms=dec_ms,
+                        decode_wall_ms=(w2 - w1) * 1e3, total_wall_ms=(w2 - w0) * 1e3)
 
-    # dominant kernel: gemv_kernel (all dense projections; ~97% of the step's bytes).  Timed live, one class at a
-    # time over all layers' weights (CUDA events on the engine stream); the largest class (gate/up) is reported.
+        for _ in range(warmup):
+            one_request()
+        eng.timing_reset()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        recs = [one_request() for _ in range(steps)]
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        if world > 1:
+            from substratus_b200 import tp
+
+            wall = tp.max_over_ranks(wall)
+            for r in recs:
+                for k in r:
+                    r[k] = tp.max_over_ranks(r[k])
+        tm = eng.timing()
+        ntok = B * (NEW_TOKENS - 1)
+        dec_dev_s = sum(r["decode_dev_ms"] for r in recs) / 1e3
+        dec_wall_s = sum(r["decode_wall_ms"] for r in recs) / 1e3
+        bytes_step = info.weight_bytes_per_step + B * ctx_mean * info.kv_bytes_per_token
+        step_ms = dec_dev_s * 1e3 / (steps * (NEW_TOKENS - 1))
+        step_gbs = bytes_step / (step_ms * 1e-3) / 1e9
+        return dict(value=steps * ntok / dec_dev_s, e2e=steps * ntok / dec_wall_s, wall=wall, clocks=clocks, tm=tm,
+                    ttft_ms_p50=statistics.median(r["ttft_wall_ms"] for r in recs),
+                    prefill_device_ms_p50=statistics.median(r["prefill_dev_ms"] for r in recs),
+                    request_tok_s=steps * B * NEW_TOKENS / (sum(r["total_wall_ms"] for r in recs) / 1e3),
+                    step_ms=step_ms, bytes_step=bytes_step, step_gbs=step_gbs)
+
+    B = args.batch
+    m = measure(B, args.steps, args.warmup)
+    launches = int(m["tm"].kernel_launches)
+    h2d, d2h = m["tm"].h2d_bytes // args.steps, m["tm"].d2h_bytes // args.steps
+
+    # Dominant kernel.  At batch <= 4 on one GPU the whole decode step IS one kernel (decode_mega_kernel): its
+    # achieved bandwidth is the step's algorithmic bytes over its CUDA-event duration.  Otherwise the dominant kernel is
+    # the gate/up projection (44% of the weight bytes), timed live per launch with ssb_bench_kernel.
     kern = {}
     for k in ("gate_up", "qkv", "down", "o", "lm_head", "attn"):
-        ms, by = eng.bench_kernel(k, rows=min(B, 4), ctx=int(ctx_mean), iters=64)
+        ms, by = eng.bench_kernel(k, rows=B, ctx=int(ctx_mean), iters=64)
         kern[k] = {"ms": ms, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9}
-    dom = kern["gate_up"]
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel (gate/up projection + SwiGLU)", "achieved": dom["gbs"],
-                "peak": peak_gbs, "unit": "GB/s", "frac": dom["gbs"] / peak_gbs, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
-                "per_kernel_class_gbs": {k: round(v["gbs"], 1) for k, v in kern.items()},
-                "decode_step": {"bytes": bytes_step, "ms": step_ms, "achieved": step_gbs, "frac": step_gbs / peak_gbs,
-                                "roofline_tok_s": B * peak_gbs * 1e9 / bytes_step}}
+    mega = world == 1 and B <= 4
+    if mega:
+        roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent single-kernel decode step: all projections, attention, pick)",
+                    "achieved": m["step_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": m["step_gbs"] / peak_gbs,
+                    "traffic": MEGA_TRAFFIC_BYTES.get((args.workload, B)), "algorithmic_bytes_per_launch": m["bytes_step"],
+                    "ms_per_launch": m["step_ms"]}
+    else:
+        dom = kern["gate_up"]
+        roofline = {"bound": "hbm", "kernel": "gate/up projection (gemv_kernel for <= 4 rows, tc_gemm_sk_kernel tcgen05 stream-K above)",
+                    "achieved": dom["gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": dom["gbs"] / peak_gbs, "traffic": None,
+                    "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
+    roofline.update({"peak_source": peak_src, "per_kernel_class_gbs": {k: round(v["gbs"], 1) for k, v in kern.items()},
+                     "decode_step": {"bytes": m["bytes_step"], "ms": m["step_ms"], "achieved": m["step_gbs"],
+                                     "frac": m["step_gbs"] / peak_gbs, "roofline_tok_s": B * peak_gbs * 1e9 / m["bytes_step"]}})
 
     line = {
-        "metric": "decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
+        "metric": "decode_tokens_per_sec", "value": m["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["wall"] * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload} bf16 decode, batch {B}, {PROMPT_LEN}-token prompt + {NEW_TOKENS} new tokens, {world}xB200",
-                   "batch": B, "prompt_len": PROMPT_LEN, "new_tokens": NEW_TOKENS, "parallelism": f"tp{world}", "allreduce": "one-shot over NVLink peer memory (CUDA IPC)" if world > 1 else "none",
-                   "l2": "inputs larger than L2 (13.2 GB of weights per decode step)", "pdl": args.pdl, "graph": args.graph},
-        "ttft_ms_p50": statistics.median(r["ttft_wall_ms"] for r in recs),
-        "prefill_device_ms_p50": statistics.median(r["prefill_dev_ms"] for r in recs),
-        "decode_ms_per_token": step_ms,
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": tm.h2d_bytes // args.steps,
-                "d2h_bytes_per_step": tm.d2h_bytes // args.steps,
-                "request_tokens_per_sec": args.steps * B * NEW_TOKENS / (sum(r["total_wall_ms"] for r in recs) / 1e3)},
-        "gpu_launches": int(tm.kernel_launches), "clocks": clocks, "roofline": roofline,
-        "load_s": t_load, "hbm_gb": info.hbm_bytes_allocated / 1e9,
+                   "batch": B, "prompt_len": PROMPT_LEN, "new_tokens": NEW_TOKENS, "parallelism": f"tp{world}",
+                   "allreduce": "one-shot over NVLink peer memory (CUDA IPC)" if world > 1 else "none",
+                   "l2": "inputs larger than L2 (weights streamed per decode step >> 126 MB)", "pdl": args.pdl, "graph": args.graph},
+        "ttft_ms_p50": m["ttft_ms_p50"], "prefill_device_ms_p50": m["prefill_device_ms_p50"], "decode_ms_per_token": m["step_ms"],
+        "e2e": {"value": m["e2e"], "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "request_tokens_per_sec": m["request_tok_s"]},
+        "gpu_launches": launches, "clocks": m["clocks"], "roofline": roofline, "load_s": t_load,
+        "hbm_gb": info.hbm_bytes_allocated / 1e9,
     }
+    if B == 1 and not args.no_batch32:  # the metric is quoted at batch 1 AND 32: same engine, second measurement
+        m32 = measure(32, max(2, args.steps // 2), 2)
+        line["batch32"] = {"value": m32["value"], "unit": "tokens/s", "e2e": m32["e2e"], "ttft_ms_p50": m32["ttft_ms_p50"],
+                           "decode_ms_per_step": m32["step_ms"], "bytes_per_step": m32["bytes_step"],
+                           "hbm_roofline_frac": m32["step_gbs"] / peak_gbs}
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0 and B == 1 and not args.no_batch32 and args.workload == "llama2-7b":
-        pass  # batch-32 numbers are reported by a second invocation (--batch 32); see BASELINE.md
     if rank == 0 and not args.no_cpu_baseline:
         try:
             r = hf_cpu_generate(cfg, args.ref_prompt_len, args.ref_new_tokens, batch=1)
@@ -336,6 +355,10 @@ def main():
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch (ncu --set full, profiles/)
+MEGA_TRAFFIC_BYTES = {("llama2-7b", 1): 13.494e9}
 
 
 if __name__ == "__main__":
