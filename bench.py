@@ -156,7 +156,10 @@ def hf_cpu_generate(cfg, prompt_len, new_tokens, batch=1, threads=None, dtype="f
     (measured on the GPU box's host: 38 s per token in bf16).  dtype float32 = HF's default for CPU serving."""
     import torch
 
-    threads = threads or os.cpu_count()
+    # cores this process may actually use (cgroup / affinity), capped: torch's CPU GEMV collapses when oversubscribed
+    # (measured on the GPU box: 128 threads -> 0.04 tok/s, 25 s per token)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = threads or max(1, min(avail, 32))
     torch.set_num_threads(threads)
     dt = getattr(torch, dtype)
     t0 = time.time()
@@ -212,8 +215,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch32", action="store_true")
-    ap.add_argument("--ref-prompt-len", type=int, default=32)
-    ap.add_argument("--ref-new-tokens", type=int, default=9)
+    ap.add_argument("--ref-prompt-len", type=int, default=16)
+    ap.add_argument("--ref-new-tokens", type=int, default=5)
     ap.add_argument("--ref-reuse", action="store_true", default=True)
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1)
