@@ -40,6 +40,7 @@ static std::mutex g_engine_mu;  // ssb_* calls on one engine are not re-entrant
 static std::atomic<long long> g_requests{0}, g_tokens{0}, g_errors{0};
 static std::atomic<double> g_ttft_ms_sum{0}, g_decode_ms_sum{0};
 static std::string g_load_error;
+static ssb_tokenizer* g_tok = nullptr;  // <model_dir>/tokenizer.json, if present and supported (text prompts)
 
 static std::string getenv_or(const char* k, const char* d) {
   const char* v = getenv(k);
@@ -190,14 +191,32 @@ static void handle(int fd) {
       std::string err;
       std::vector<int32_t> prompt;
       int max_new = 16;
-      bool ok = true;
+      bool ok = true, text_mode = false;
       try {
         Json j = ssb::json_parse(body);
         const bool oai = path == "/v1/completions";
         const Json* p = j.find(oai ? "prompt" : "tokens");
-        if (oai && p && p->kind == Json::Str) {
-          ok = false;
-          err = "text prompts need a tokenizer, which this build does not ship; pass \"prompt\" as an array of token ids";
+        const Json* ptxt = oai ? p : j.find("prompt");  // /generate also takes {"prompt": "text"}
+        if (ptxt && ptxt->kind == Json::Str && (oai || !p)) {
+          if (!g_tok) {
+            ok = false;
+            err = "text prompts need <model_dir>/tokenizer.json (Llama-2 or GPT-2 style BPE); pass the prompt as an array of token ids";
+          } else {
+            std::vector<int32_t> ids(4 * ptxt->str.size() + 16);
+            int n = 0;
+            if (ssb_tok_encode(g_tok, ptxt->str.c_str(), 1, ids.data(), (int)ids.size(), &n) != SSB_OK || n < 1) {
+              ok = false;
+              err = std::string("tokenizer: ") + ssb_last_error();
+            } else {
+              prompt.assign(ids.begin(), ids.begin() + n);
+              for (int32_t t : prompt)
+                if (t < 0 || t >= g_info.vocab_size) {
+                  ok = false;
+                  err = "tokenizer produced an id outside the model's vocabulary";
+                }
+              text_mode = true;
+            }
+          }
         } else {
           ok = parse_ids(p, g_info.vocab_size, &prompt, &err);
         }
@@ -225,12 +244,19 @@ static void handle(int fd) {
           char tail[256];
           const double tps = r.decode_ms > 0 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
           snprintf(tail, sizeof tail, "\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f", r.ttft_ms, r.decode_ms, tps);
+          std::string text;
+          if (text_mode && g_tok) {
+            std::vector<char> buf(16 * r.tokens.size() + 64);
+            int len = 0;
+            if (ssb_tok_decode(g_tok, r.tokens.data(), (int)r.tokens.size(), 1, buf.data(), (int)buf.size(), &len) == SSB_OK)
+              text.assign(buf.data(), (size_t)len);
+          }
           if (path == "/generate")
-            respond(fd, 200, "OK", "{\"tokens\":" + ids_json(r.tokens) + "," + tail + "}");
+            respond(fd, 200, "OK", "{\"tokens\":" + ids_json(r.tokens) + ",\"text\":\"" + ssb::json_escape(text) + "\"," + tail + "}");
           else
             respond(fd, 200, "OK",
                     "{\"object\":\"text_completion\",\"model\":\"" + std::string(g_info.model_type) +
-                        "\",\"choices\":[{\"index\":0,\"text\":\"\",\"tokens\":" + ids_json(r.tokens) +
+                        "\",\"choices\":[{\"index\":0,\"text\":\"" + ssb::json_escape(text) + "\",\"tokens\":" + ids_json(r.tokens) +
                         ",\"finish_reason\":\"length\"}],\"usage\":{\"prompt_tokens\":" + std::to_string(prompt.size()) +
                         ",\"completion_tokens\":" + std::to_string(r.tokens.size()) + "}," + tail + "}");
         }
@@ -276,6 +302,10 @@ int main(int argc, char** argv) {
       _exit(rc == SSB_ENODEV ? 3 : 1);
     }
     ssb_engine_info(g_engine, &g_info);
+    if (ssb_tok_load((model_dir + "/tokenizer.json").c_str(), &g_tok) != SSB_OK) {
+      fprintf(stderr, "serve: no usable tokenizer.json (%s): text prompts disabled, token-id prompts only\n", ssb_last_error());
+      g_tok = nullptr;
+    }
     fprintf(stderr, "serve: ready (%s, %d layers, %.2f GB HBM)\n", g_info.model_type, g_info.n_layers,
             g_info.hbm_bytes_allocated / 1e9);
     g_ready = 1;

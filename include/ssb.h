@@ -130,6 +130,16 @@ int ssb_debug_dequant(int ggml_type, const void* blocks, int64_t nbytes, int64_t
  * (tests/: bit-exact against oracle/synth.py).  Fills dst (host, uint16 bf16 bits). */
 int ssb_synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst);
 
+/* Text path (the reference's one request carries text: test/system.sh:73-78).  Native reader of HF
+ * `tokenizer.json` (Llama-2 SentencePiece-style BPE with byte fallback, GPT-2/OPT byte-level BPE); CPU only, no GPU
+ * needed.  Unsupported tokenizer components fail at load (SSB_EINVAL) instead of tokenising approximately.
+ * encode: returns the id count through n_out (even when > cap, so the caller can retry); decode: bytes through len_out. */
+typedef struct ssb_tokenizer ssb_tokenizer;
+int ssb_tok_load(const char* tokenizer_json_path, ssb_tokenizer** out);
+void ssb_tok_free(ssb_tokenizer* t);
+int ssb_tok_encode(ssb_tokenizer* t, const char* text_utf8, int add_special, int32_t* ids, int cap, int* n_out);
+int ssb_tok_decode(ssb_tokenizer* t, const int32_t* ids, int n, int skip_special, char* buf, int cap, int* len_out);
+
 const char* ssb_last_error(void);
 const char* ssb_version(void);
 

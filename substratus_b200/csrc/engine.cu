@@ -6,6 +6,7 @@
 // 355-500); greedy loop = HF:generation/utils.py:2658-2800.  No CPU fallback anywhere: init() fails with
 // SSB_ENODEV when there is no sm_100 device.
 #include "engine.h"
+#include "tokenizer.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1829,6 +1830,52 @@ int ssb_debug_dequant(int ggml_type, const void* blocks, int64_t nbytes, int64_t
 int ssb_synth_fill_host(uint64_t seed, uint32_t tid, int64_t start, int64_t n, float amp, float base, uint16_t* dst) {
   if (!dst || n < 0) return SSB_EINVAL;
   synth_fill_host(seed, tid, start, n, amp, base, dst);
+  return SSB_OK;
+}
+struct ssb_tokenizer {
+  ssb::Tokenizer impl;
+};
+int ssb_tok_load(const char* path, ssb_tokenizer** out) {
+  if (!path || !out) return SSB_EINVAL;
+  *out = nullptr;
+  ssb_tokenizer* t = new (std::nothrow) ssb_tokenizer();
+  if (!t) return SSB_ENOMEM;
+  std::string err;
+  bool ok = false;
+  try {
+    ok = t->impl.load(path, &err);
+  } catch (std::exception& ex) {
+    err = ex.what();
+  }
+  if (!ok) {
+    delete t;
+    ssb::set_error(err);
+    return err.rfind("cannot read", 0) == 0 ? SSB_EIO : SSB_EINVAL;
+  }
+  *out = t;
+  return SSB_OK;
+}
+void ssb_tok_free(ssb_tokenizer* t) { delete t; }
+int ssb_tok_encode(ssb_tokenizer* t, const char* text, int add_special, int32_t* ids, int cap, int* n_out) {
+  if (!t || !text || !n_out || (cap > 0 && !ids)) return SSB_EINVAL;
+  const std::vector<int32_t> v = t->impl.encode(text, add_special != 0);
+  *n_out = (int)v.size();
+  if ((int)v.size() > cap) {
+    ssb::set_error("id buffer too small");
+    return SSB_ENOMEM;
+  }
+  if (!v.empty()) memcpy(ids, v.data(), v.size() * sizeof(int32_t));
+  return SSB_OK;
+}
+int ssb_tok_decode(ssb_tokenizer* t, const int32_t* ids, int n, int skip_special, char* buf, int cap, int* len_out) {
+  if (!t || (n > 0 && !ids) || !len_out || (cap > 0 && !buf)) return SSB_EINVAL;
+  const std::string s = t->impl.decode(std::vector<int32_t>(ids, ids + n), skip_special != 0);
+  *len_out = (int)s.size();
+  if ((int)s.size() > cap) {
+    ssb::set_error("text buffer too small");
+    return SSB_ENOMEM;
+  }
+  if (!s.empty()) memcpy(buf, s.data(), s.size());
   return SSB_OK;
 }
 const char* ssb_last_error(void) { return ssb::get_error(); }

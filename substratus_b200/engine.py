@@ -45,7 +45,8 @@ class SsbTiming(C.Structure):
 EXPORTS = [
     "ssb_engine_create", "ssb_engine_destroy", "ssb_engine_info", "ssb_seq_create", "ssb_seq_free", "ssb_seq_len",
     "ssb_prefill", "ssb_decode", "ssb_last_timing", "ssb_timing_reset", "ssb_tp_handle_size", "ssb_tp_export",
-    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_profile", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version",
+    "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_profile", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version", "ssb_tok_load", "ssb_tok_free", "ssb_tok_encode",
+    "ssb_tok_decode",
 ]
 
 
@@ -83,6 +84,11 @@ def load_library(path: str | None = None):
     lib.ssb_debug_dequant.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint16)]
     lib.ssb_synth_fill_host.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_float, C.c_float,
                                         C.POINTER(C.c_uint16)]
+    lib.ssb_tok_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.ssb_tok_free.argtypes = [vp]
+    lib.ssb_tok_free.restype = None
+    lib.ssb_tok_encode.argtypes = [vp, C.c_char_p, C.c_int, i32p, C.c_int, ip]
+    lib.ssb_tok_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_char_p, C.c_int, ip]
     lib.ssb_last_error.restype = C.c_char_p
     lib.ssb_version.restype = C.c_char_p
     if path is None:
@@ -242,3 +248,33 @@ def debug_dequant(ggml_type: int, blocks: np.ndarray, n_elems: int) -> np.ndarra
     _check(lib, lib.ssb_debug_dequant(ggml_type, raw.ctypes.data_as(C.c_void_p), raw.size, n_elems,
                                       out.ctypes.data_as(C.POINTER(C.c_uint16))))
     return out
+
+
+class NativeTokenizer:
+    """ctypes view of the serve host's native `tokenizer.json` reader (CPU only)."""
+
+    def __init__(self, path: str):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib, self._lib.ssb_tok_load(path.encode(), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.ssb_tok_free(self._h)
+            self._h = C.c_void_p()
+
+    def encode(self, text: str, add_special: bool = True):
+        raw = text.encode("utf-8")
+        cap = 4 * len(raw) + 16
+        ids = np.zeros(cap, dtype=np.int32)
+        n = C.c_int()
+        _check(self._lib, self._lib.ssb_tok_encode(self._h, raw, int(add_special), ids.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(n)))
+        return ids[: n.value].tolist()
+
+    def decode(self, ids, skip_special: bool = True) -> str:
+        a = _i32(ids)
+        cap = 16 * len(a) + 64
+        buf = C.create_string_buffer(cap)
+        n = C.c_int()
+        _check(self._lib, self._lib.ssb_tok_decode(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), len(a), int(skip_special), buf, cap, C.byref(n)))
+        return buf.raw[: n.value].decode("utf-8", "replace")

@@ -100,3 +100,40 @@ def test_serve_contract_and_generate(tmp_path):
         assert st == 404
     finally:
         p.kill()
+
+
+@pytest.mark.gpu
+def test_serve_text_prompt_through_native_tokenizer(tmp_path):
+    """With <model_dir>/tokenizer.json present the reference's own request shape works: a TEXT prompt in
+    /v1/completions (test/system.sh:73-78); ids must equal tokenizers-encode -> engine, text = tokenizers-decode."""
+    from test_tokenizer import _llama_like
+
+    ref = _llama_like(str(tmp_path / "tokenizer.json"))
+    cfg = dict(synth.TINY_GQA, vocab_size=ref.get_vocab_size() + (ref.get_vocab_size() & 1))
+    sd = synth.llama_state_dict(cfg, 3)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    port = _free_port()
+    p = _spawn(str(tmp_path), {"max_batch": 2, "max_seq_len": 128}, port)
+    base = f"http://127.0.0.1:{port}"
+    try:
+        deadline = time.time() + 120
+        st = None
+        while time.time() < deadline:
+            try:
+                st, _ = _get(base + "/", timeout=2)
+                if st == 200:
+                    break
+            except (urllib.error.URLError, ConnectionError, socket.timeout):
+                pass
+            time.sleep(0.2)
+        assert st == 200
+        text = "Who was the first president of the United States?"
+        ids = ref.encode(text).ids
+        st, by_ids = _get(base + "/v1/completions", {"prompt": ids, "max_tokens": 4})
+        st2, by_text = _get(base + "/v1/completions", {"prompt": text, "max_tokens": 4})
+        assert st == 200 and st2 == 200
+        assert by_text["usage"]["prompt_tokens"] == len(ids)
+        assert by_text["choices"][0]["tokens"] == by_ids["choices"][0]["tokens"]
+        assert by_text["choices"][0]["text"] == ref.decode(by_ids["choices"][0]["tokens"])
+    finally:
+        p.kill()
