@@ -187,7 +187,7 @@ struct FillJob {
   float amp, base;
 };
 
-int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) {
+int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed, bool validate_only) {
   const int h = cfg_.hidden, D = cfg_.head_dim, half = D / 2;
   const int h0 = tp_rank_ * Hl_, kv0 = tp_rank_ * KVHl_, i0 = tp_rank_ * Il_;
   std::vector<FillJob> jobs;
@@ -313,6 +313,9 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
       if (!tv) RET(SSB_EIO, "checkpoint is missing tensor " + j.name);
       if (tv->dtype == DT_OTHER || (!gguf && tv->dtype > DT_F32)) RET(SSB_EINVAL, "unsupported dtype for " + j.name);
       if (tv->cols() != j.full_cols) RET(SSB_EINVAL, "unexpected shape for " + j.name);
+      int64_t max_row = j.rows.empty() ? j.n_rows - 1 : 0;
+      for (int r : j.rows) max_row = std::max<int64_t>(max_row, r);
+      if (max_row >= tv->rows()) RET(SSB_EINVAL, "tensor " + j.name + " has too few rows for this config");
       max_src = std::max(max_src, tv->nbytes);
       if (tv->dtype >= DT_Q4_0) {
         int64_t n = 1;
@@ -321,6 +324,7 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed) 
       }
     }
   }
+  if (validate_only) return SSB_OK;  // host-side inventory check only (runs before any device is touched)
   int* d_rows = nullptr;
   size_t max_rows = 0;
   for (auto& j : jobs) max_rows = std::max(max_rows, j.rows.size());
@@ -499,14 +503,12 @@ int Engine::alloc_runtime(const Json& params) {
   for (int i = 0; i < n_blocks_; ++i) free_blocks_[i] = n_blocks_ - 1 - i;
   slots_.assign(max_batch_, SeqSlot());
   {  // stream-K workspace of the tensor-core decode projections
-    float* skp = nullptr;
-    unsigned* skf = nullptr;
-    const int slots = 2 * n_sm_;
-    TRY(dmalloc(&skp, (size_t)slots * 64 * 128));
-    TRY(dmalloc(&skf, (size_t)slots));
-    CK(cudaMemset(skf, 0, slots * sizeof(unsigned)));
-    if (params.get_int("tc_streamk", 1) != 0) tc_set_streamk_workspace(skp, skf, slots);
-    else tc_set_streamk_workspace(nullptr, nullptr, 0);
+    if (params.get_int("tc_streamk", 1) != 0) {
+      sk_slots_ = 2 * n_sm_;
+      TRY(dmalloc(&sk_part_, (size_t)sk_slots_ * 64 * 128));
+      TRY(dmalloc(&sk_flags_, (size_t)sk_slots_));
+      CK(cudaMemset(sk_flags_, 0, sk_slots_ * sizeof(unsigned)));
+    }
   }
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
   use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1 && !cfg_.falcon && !prof_fwd_;
@@ -548,11 +550,8 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
     RET(SSB_EINVAL, std::string("params.json: ") + e.what());
   }
   if (params.kind != Json::Obj) RET(SSB_EINVAL, "params.json must be a JSON object");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    device_ = -1;
-    RET(SSB_ENODEV, "no CUDA device: libsubstratus_b200 has no CPU fallback");
-  }
+  device_ = -1;
+  // 1. everything that needs no GPU: params, checkpoint containers, config, tensor inventory (names / dtypes / shapes)
   const std::string wmode = params.get_str("weights", "file");
   if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
   if (wmode == "file") {
@@ -560,6 +559,15 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
     if (!files_.open(model_dir, &err)) RET(SSB_EIO, err);
   }
   TRY(load_config(model_dir, params));
+  if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
+  if (wmode == "file") {
+    lw_.assign(cfg_.layers, LayerW());
+    TRY(fill_weights(model_dir, false, 0, /*validate_only=*/true));
+  }
+  // 2. the device: no CPU fallback
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    RET(SSB_ENODEV, "no CUDA device: libsubstratus_b200 has no CPU fallback");
   device_ = (int)params.get_int("device", tp_rank_ % ndev);
   if (device_ < 0 || device_ >= ndev) RET(SSB_EINVAL, "bad device index");
   cudaDeviceProp prop;
@@ -578,9 +586,8 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   tp_push_ = params.get_int("tp_push", 0) != 0;  // push-model allreduce: measured slower than pull on B200
   use_graph_ = params.get_int("use_graph", 1) != 0;
   if (prof_fwd_) use_pdl_ = use_graph_ = false;  // event marks between launches need plain stream order
-  if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");
   TRY(alloc_weights());
-  TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0)));
+  TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0), false));
   TRY(alloc_runtime(params));
   {
     const std::string gp = params.get_str("gemm_path", "auto");  // "auto" | "gemv" (CUDA cores only) | "tc" (tcgen05 always)

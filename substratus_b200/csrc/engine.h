@@ -59,7 +59,7 @@ class Engine {
   // setup
   int load_config(const std::string& dir, const Json& params);
   int alloc_weights();
-  int fill_weights(const std::string& dir, bool synthetic, uint64_t seed);
+  int fill_weights(const std::string& dir, bool synthetic, uint64_t seed, bool validate_only);
   int alloc_runtime(const Json& params);
   template <typename T>
   int dmalloc(T** p, size_t n);
@@ -70,7 +70,16 @@ class Engine {
   int build_graph(int B);
   int forward_mega(int B);
   int forward_falcon(int M, int n_logit_rows, bool decode_mode);  // one persistent kernel for the whole decode step (B <= 4, single rank)
-  LaunchCfg lc(bool pdl) const { return LaunchCfg{stream_, pdl && use_pdl_, n_sm_}; }
+  LaunchCfg lc(bool pdl) const {
+    LaunchCfg c{stream_, pdl && use_pdl_, n_sm_};
+    c.sk_part = sk_part_;
+    c.sk_flags = sk_flags_;
+    c.sk_slots = sk_slots_;
+    return c;
+  }
+  float* sk_part_ = nullptr;  // stream-K workspace of the tensor-core decode projections
+  unsigned* sk_flags_ = nullptr;
+  int sk_slots_ = 0;
 
   ModelCfg cfg_;
   int tp_size_ = 1, tp_rank_ = 0, device_ = 0, n_sm_ = 148;

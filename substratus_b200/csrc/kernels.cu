@@ -271,11 +271,10 @@ static cudaError_t launch_ex(KernelT kernel, dim3 grid, dim3 block, size_t smem,
 template <int BT, int EPI, int NORM>
 static cudaError_t launch_gemv_t(const GemvArgs& a, const LaunchCfg& lc) {
   const size_t smem = gemv_smem_bytes(BT, a.K);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int P = a.N / 2;
   int gx = lc.n_sm < P ? lc.n_sm : P;

@@ -83,7 +83,20 @@ struct LaunchCfg {
   cudaStream_t stream;
   bool pdl;
   int n_sm;
+  // per-engine fp32 partial-tile workspace of the stream-K decode GEMM (tc_gemm.cu); null => one CTA per 128-row tile
+  float* sk_part = nullptr;
+  unsigned* sk_flags = nullptr;  // [sk_slots], zero on entry and on exit
+  int sk_slots = 0;
 };
+
+// cudaFuncSetAttribute is per device: returns true the first time it is called for `mask` on the current device
+inline bool first_launch_on_device(unsigned long long& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  if ((mask >> d) & 1ull) return false;
+  mask |= 1ull << d;
+  return true;
+}
 
 cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& lc);
 int gemv_pick_bt(int M, int K);

@@ -555,11 +555,10 @@ int mega_pick_stages(int bt, int k_max) {
 template <int BT, int D, int G>
 static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
   const size_t smem = mega_smem_bytes(BT, a.k_max, a.n_stages);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(lc.n_sm);

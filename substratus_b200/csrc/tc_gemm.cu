@@ -453,11 +453,10 @@ int tc_weight_box_rows() { return TC_BM; }
 template <int TN, int EPI>
 static cudaError_t launch_tc_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
   using Cfg = TcCfg<TN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int n_tiles = ((a.N + TC_BM - 1) / TC_BM) * ((a.M + TN - 1) / TN);
   cudaLaunchConfig_t cfg = {};
@@ -485,29 +484,21 @@ static cudaError_t launch_tc_e(int tn, const TcTensorMap& tmA, const TcTensorMap
   return cudaErrorInvalidValue;
 }
 
-static SkWs g_sk_ws = {nullptr, nullptr};
-static int g_sk_slots = 0;
-void tc_set_streamk_workspace(float* part, unsigned* flags, int slots) {
-  g_sk_ws.part = part;
-  g_sk_ws.flags = flags;
-  g_sk_slots = slots;
-}
-
 template <int TN, int EPI>
 static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
   using Cfg = TcCfg<TN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_sk_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int nkb = (a.K + TC_BK - 1) / TC_BK;
   const long long U = (long long)((a.N + TC_BM - 1) / TC_BM) * nkb;
   const long long min_units = (nkb + 7) / 8;  // >= nkb/8 units per CTA: a tile spans at most 8 full + 2 partial ranges
   long long gmax = U / min_units;
   int grid = (int)(gmax < 1 ? 1 : (gmax < lc.n_sm ? gmax : lc.n_sm));
-  if (grid * 2 > g_sk_slots) return cudaErrorInvalidValue;
+  if (grid * 2 > lc.sk_slots) return cudaErrorInvalidValue;
+  const SkWs ws = {lc.sk_part, lc.sk_flags};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -519,7 +510,7 @@ static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, c
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, tc_gemm_sk_kernel<TN, EPI>, *reinterpret_cast<const CUtensorMap*>(&tmA),
-                            *reinterpret_cast<const CUtensorMap*>(&tmB), a, g_sk_ws);
+                            *reinterpret_cast<const CUtensorMap*>(&tmB), a, ws);
 }
 
 template <int EPI>
@@ -549,7 +540,7 @@ static cudaError_t launch_tc_streamk(const TcTensorMap& tmA, const TcTensorMap& 
 // tmB must have been built with box_rows == tn
 cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc) {
   if ((a.N & 1) || (a.K & 7)) return cudaErrorInvalidValue;
-  if (a.M <= tn && tn <= 64 && g_sk_ws.part && !a.row_map) return launch_tc_streamk(tmA, tmB, tn, a, epi, lc);  // batched decode
+  if (a.M <= tn && tn <= 64 && lc.sk_part && !a.row_map) return launch_tc_streamk(tmA, tmB, tn, a, epi, lc);  // batched decode
   switch (epi) {
     case EPI_QKV_ROPE: return launch_tc_e<EPI_QKV_ROPE>(tn, tmA, tmB, a, lc);
     case EPI_SWIGLU: return launch_tc_e<EPI_SWIGLU>(tn, tmA, tmB, a, lc);

@@ -14,6 +14,5 @@ int tc_weight_box_rows();       // 128
 cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc);
 cudaError_t launch_rmsnorm(const bf16* x, const bf16* w, bf16* out, int M, int K, float eps, const LaunchCfg& lc);
 cudaError_t launch_layernorm(const bf16* x, const bf16* w, const bf16* b, bf16* out, int M, int K, float eps, const LaunchCfg& lc);
-// fp32 partial-tile workspace of the stream-K decode kernel: part = slots * 64 * 128 floats, flags = slots (zeroed);
-// slots >= 2 * SM count.  Without a workspace launch_tc_gemm falls back to one CTA per 128-row tile.
-void tc_set_streamk_workspace(float* part, unsigned* flags, int slots);
+// The stream-K decode kernel takes its fp32 partial-tile workspace from LaunchCfg (sk_part = sk_slots * 64 * 128 floats,
+// sk_flags = sk_slots zeroed words, sk_slots >= 2 * SM count); without one launch_tc_gemm uses one CTA per 128-row tile.
