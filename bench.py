@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 PROMPT_LEN, NEW_TOKENS = 512, 128
 
 WORKLOADS = {
+    # "tiny" exists for the CPU contract test of the reference arm (tests/test_bench_contract.py), not for benchmarking
+    "tiny": dict(model_type="llama", hidden_size=256, intermediate_size=688, num_hidden_layers=8, num_attention_heads=2,
+                 num_key_value_heads=2, vocab_size=512, max_position_embeddings=512, rms_norm_eps=1e-5, rope_theta=10000.0,
+                 tie_word_embeddings=False, torch_dtype="bfloat16"),
     "llama2-7b": dict(model_type="llama", hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
                       num_attention_heads=32, num_key_value_heads=32, vocab_size=32000, max_position_embeddings=4096,
                       rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
