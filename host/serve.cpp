@@ -18,6 +18,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -41,6 +42,10 @@ static std::atomic<long long> g_requests{0}, g_tokens{0}, g_errors{0};
 static std::atomic<double> g_ttft_ms_sum{0}, g_decode_ms_sum{0};
 static std::string g_load_error;
 static ssb_tokenizer* g_tok = nullptr;  // <model_dir>/tokenizer.json, if present and supported (text prompts)
+// Tensor parallel inside the ONE container the reconciler grants N GPUs to (resources.gpu.count -> nvidia.com/gpu: N,
+// internal/resources/resources.go:39-47): rank 0 is g_engine, ranks 1..N-1 live here; every rank runs in its own
+// host thread per request (the ranks' kernels wait for each other over NVLink, so the calls must be concurrent).
+static std::vector<ssb_engine*> g_peers;
 
 static std::string getenv_or(const char* k, const char* d) {
   const char* v = getenv(k);
@@ -82,7 +87,57 @@ struct GenResult {
   std::string error;
 };
 
+// one rank's share of a request: identical inputs on every rank, identical greedy ids out
+static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, std::vector<int32_t>* toks, double* ttft_ms,
+                    double* decode_ms, std::string* error) {
+  int sid = -1;
+  int rc = ssb_seq_create(e, &sid);
+  if (rc != SSB_OK) {
+    *error = ssb_last_error();
+    return rc;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  int n = (int)prompt.size();
+  int32_t first = 0;
+  toks->assign(max_new, 0);
+  rc = ssb_prefill(e, &sid, prompt.data(), &n, 1, &first, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  if (rc == SSB_OK) {
+    (*toks)[0] = first;
+    if (max_new > 1) rc = ssb_decode(e, &sid, &first, 1, max_new - 1, toks->data() + 1, nullptr);
+  }
+  auto t2 = std::chrono::steady_clock::now();
+  if (rc != SSB_OK) *error = ssb_last_error();  // thread-local in the library: read it on the calling thread
+  ssb_seq_free(e, sid);
+  *ttft_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  *decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  return rc;
+}
+
+static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new) {
+  GenResult r;
+  std::lock_guard<std::mutex> lk(g_engine_mu);
+  const size_t n = g_peers.size() + 1;
+  std::vector<std::vector<int32_t>> toks(n);
+  std::vector<double> ttft(n, 0), dec(n, 0);
+  std::vector<std::string> errs(n);
+  std::vector<std::thread> th;
+  for (size_t i = 1; i < n; ++i)
+    th.emplace_back([&, i] { run_rank(g_peers[i - 1], prompt, max_new, &toks[i], &ttft[i], &dec[i], &errs[i]); });
+  run_rank(g_engine, prompt, max_new, &toks[0], &ttft[0], &dec[0], &errs[0]);
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < n; ++i) {
+    if (!errs[i].empty()) r.error = "rank " + std::to_string(i) + ": " + errs[i];
+    if (i && r.error.empty() && toks[i] != toks[0]) r.error = "tensor-parallel ranks disagree on the generated ids";
+  }
+  r.tokens = toks[0];
+  r.ttft_ms = *std::max_element(ttft.begin(), ttft.end());
+  r.decode_ms = *std::max_element(dec.begin(), dec.end());
+  return r;
+}
+
 static GenResult generate(const std::vector<int32_t>& prompt, int max_new) {
+  if (!g_peers.empty()) return generate_tp(prompt, max_new);
   GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
   int sid = -1;
@@ -291,10 +346,51 @@ int main(int argc, char** argv) {
   fprintf(stderr, "serve: listening on :%d, loading %s\n", port, model_dir.c_str());
 
   // model load runs beside the accept loop so the readiness probe sees 503 (not a refused connection) while loading
-  std::thread loader([&] {
-    int rc = ssb_engine_create(model_dir.c_str(), params.c_str(), &g_engine);
+  // tp_size from params.json: one engine rank per GPU of this container, all in this process
+  int tp = 1;
+  try {
+    tp = (int)ssb::json_parse(params).get_int("tp_size", 1);
+  } catch (std::exception&) {
+  }
+  std::thread loader([&, tp] {
+    int rc = SSB_OK;
+    if (tp <= 1) {
+      rc = ssb_engine_create(model_dir.c_str(), params.c_str(), &g_engine);
+    } else {
+      // per-rank params: {"tp_rank": r, "device": r, <the CRD's params>}  (first key wins in the engine's parser)
+      const size_t brace = params.find('{');
+      const std::string rest = brace == std::string::npos ? "}" : params.substr(brace + 1);
+      const bool empty_obj = rest.find_first_not_of(" \t\r\n") == rest.find('}');
+      std::vector<ssb_engine*> eng(tp, nullptr);
+      std::vector<int> rcs(tp, SSB_OK);
+      std::vector<std::string> errs(tp);
+      std::vector<std::thread> th;
+      for (int r = 0; r < tp; ++r)
+        th.emplace_back([&, r] {
+          const std::string pj = "{\"tp_rank\":" + std::to_string(r) + ",\"device\":" + std::to_string(r) + (empty_obj ? "" : ",") + rest;
+          rcs[r] = ssb_engine_create(model_dir.c_str(), pj.c_str(), &eng[r]);
+          if (rcs[r] != SSB_OK) errs[r] = ssb_last_error();
+        });
+      for (auto& t : th) t.join();
+      for (int r = 0; r < tp && rc == SSB_OK; ++r)
+        if (rcs[r] != SSB_OK) {
+          rc = rcs[r];
+          g_load_error = "rank " + std::to_string(r) + ": " + errs[r];
+        }
+      if (rc == SSB_OK) {
+        const int hs = ssb_tp_handle_size();
+        std::vector<char> handles((size_t)hs * tp);
+        for (int r = 0; r < tp && rc == SSB_OK; ++r) rc = ssb_tp_export(eng[r], handles.data() + (size_t)r * hs);
+        for (int r = 0; r < tp && rc == SSB_OK; ++r) rc = ssb_tp_connect(eng[r], handles.data(), tp);
+        if (rc != SSB_OK) g_load_error = ssb_last_error();
+      }
+      if (rc == SSB_OK) {
+        g_engine = eng[0];
+        g_peers.assign(eng.begin() + 1, eng.end());
+      }
+    }
     if (rc != SSB_OK) {
-      g_load_error = ssb_last_error();
+      if (g_load_error.empty()) g_load_error = ssb_last_error();
       fprintf(stderr, "serve: engine create failed (%d): %s\n", rc, g_load_error.c_str());
       g_ready = -1;
       // fatal: exit non-zero so the Deployment restarts the pod; no CPU fallback

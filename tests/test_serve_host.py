@@ -137,3 +137,40 @@ def test_serve_text_prompt_through_native_tokenizer(tmp_path):
         assert by_text["choices"][0]["text"] == ref.decode(by_ids["choices"][0]["tokens"])
     finally:
         p.kill()
+
+
+@pytest.mark.gpu
+def test_serve_tensor_parallel_in_one_container(tmp_path):
+    """params.json {"tp_size": 2}: the host starts one engine rank per GPU inside the ONE container the reconciler
+    grants N GPUs to (internal/resources/resources.go:39-47), wires them through ssb_tp_export/connect and serves the
+    same ids as the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = dict(synth.TINY_GQA, num_attention_heads=8, num_key_value_heads=4, hidden_size=1024, intermediate_size=2752)
+    sd = synth.llama_state_dict(cfg, 3)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    port = _free_port()
+    p = _spawn(str(tmp_path), {"max_batch": 2, "max_seq_len": 128, "tp_size": 2}, port)
+    base = f"http://127.0.0.1:{port}"
+    try:
+        deadline = time.time() + 120
+        st = None
+        while time.time() < deadline and p.poll() is None:
+            try:
+                st, _ = _get(base + "/", timeout=2)
+                if st == 200:
+                    break
+            except (urllib.error.URLError, ConnectionError, socket.timeout):
+                pass
+            time.sleep(0.2)
+        assert st == 200, p.stderr.read() if p.poll() is not None else "not ready"
+        prompt = torch.randint(0, cfg["vocab_size"], (1, 20), generator=torch.Generator().manual_seed(1234))
+        want, lg = llama_ref.LlamaRef(cfg, sd, torch.float32).generate(prompt, 6)
+        st, r = _get(base + "/generate", {"tokens": prompt[0].tolist(), "max_new_tokens": 6})
+        assert st == 200, r
+        from util import greedy_agree
+
+        ok, exact, msg = greedy_agree([r["tokens"]], want.numpy(), lg.numpy(), 0.05)
+        assert ok and exact >= 1, msg
+    finally:
+        p.kill()
