@@ -1,0 +1,193 @@
+// scheduler.h — continuous batching for the serve host (opt-in with params.json {"batching": 1}).
+//
+// The reference serves one request at a time per replica (Deployment `replicas := 1`, one Basaran process,
+// internal/controller/server_controller.go:115,134); the B200 engine streams its weights once per decode step no
+// matter how many sequences ride along (batch 32 costs 2.3x a batch-1 step, not 32x), so concurrent clients should
+// share steps.  This is the policy, written against the five calls of include/ssb.h so it can be unit-tested with a
+// fake engine on a CPU box (tests/test_scheduler_cpu.py) and used unchanged over the real one:
+//
+//   loop:  admit waiting requests while slots are free        -> ONE ssb_prefill over all newcomers
+//          run min(tick, min remaining) decode steps          -> ONE ssb_decode over all active sequences
+//          retire sequences that produced max_new tokens      -> fulfil their promise, free their slot
+//
+// Decode never overshoots a request (the step count is the minimum remaining), newcomers wait at most one tick, and
+// greedy decoding makes every request's ids independent of who shared its batch (checked by the test).
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ssbhost {
+
+struct Request {
+  std::vector<int32_t> prompt;
+  int max_new = 0;
+  // result
+  std::vector<int32_t> tokens;
+  std::string error;
+  double ttft_ms = 0, total_ms = 0;
+  bool done = false;
+  double t0 = 0;  // submit time (scheduler-internal)
+};
+
+// EngineT must provide (all return 0 on success, error text through last_error()):
+//   int seq_create(int* sid); int seq_free(int sid);
+//   int prefill(const int* sids, const int32_t* toks, const int* lens, int nseq, int32_t* next);
+//   int decode(const int* sids, const int32_t* last, int nseq, int nsteps, int32_t* out /*[nseq][nsteps]*/);
+//   std::string last_error();
+template <class EngineT>
+class BatchScheduler {
+ public:
+  BatchScheduler(EngineT* eng, int max_batch, int tick) : eng_(eng), max_batch_(max_batch), tick_(std::max(1, tick)) {
+    worker_ = std::thread([this] { run(); });
+  }
+  ~BatchScheduler() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    worker_.join();
+  }
+  // blocks until the request is finished (called from the per-connection threads of the host)
+  void submit(Request* r) {
+    std::unique_lock<std::mutex> lk(mu_);
+    r->t0 = now_ms();
+    waiting_.push_back(r);
+    cv_.notify_all();
+    done_cv_.wait(lk, [r] { return r->done; });
+  }
+  // statistics (for /metrics and the test)
+  long long steps() const { return steps_; }
+  long long step_rows() const { return step_rows_; }  // sum over decode calls of nseq * nsteps
+  int max_rows_seen() const { return max_rows_; }
+
+ private:
+  struct Active {
+    Request* r;
+    int sid;
+    int32_t last;
+  };
+  static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  void finish(Request* r, const std::string& err) {
+    std::lock_guard<std::mutex> lk(mu_);
+    r->error = err;
+    r->total_ms = now_ms() - r->t0;
+    r->done = true;
+    done_cv_.notify_all();
+  }
+  void run() {
+    std::vector<Active> active;
+    for (;;) {
+      std::vector<Request*> fresh;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || !waiting_.empty() || !active.empty(); });
+        if (stop_ && active.empty() && waiting_.empty()) return;
+        while (!waiting_.empty() && (int)(active.size() + fresh.size()) < max_batch_) {
+          fresh.push_back(waiting_.front());
+          waiting_.pop_front();
+        }
+      }
+      // ---- admit: one prefill over all newcomers
+      if (!fresh.empty()) {
+        std::vector<int> sids, lens;
+        std::vector<int32_t> toks;
+        std::vector<Request*> ok;
+        for (Request* r : fresh) {
+          int sid = -1;
+          if (r->prompt.empty() || r->max_new < 1) {
+            finish(r, "empty prompt or max_new < 1");
+          } else if (eng_->seq_create(&sid) != 0) {
+            finish(r, eng_->last_error());
+          } else {
+            sids.push_back(sid);
+            lens.push_back((int)r->prompt.size());
+            toks.insert(toks.end(), r->prompt.begin(), r->prompt.end());
+            ok.push_back(r);
+          }
+        }
+        if (!ok.empty()) {
+          std::vector<int32_t> next(ok.size());
+          if (eng_->prefill(sids.data(), toks.data(), lens.data(), (int)ok.size(), next.data()) != 0) {
+            const std::string e = eng_->last_error();
+            for (size_t i = 0; i < ok.size(); ++i) {
+              eng_->seq_free(sids[i]);
+              finish(ok[i], e);
+            }
+          } else {
+            for (size_t i = 0; i < ok.size(); ++i) {
+              Request* r = ok[i];
+              r->ttft_ms = now_ms() - r->t0;
+              r->tokens.assign(1, next[i]);
+              if (r->max_new == 1) {
+                eng_->seq_free(sids[i]);
+                finish(r, "");
+              } else {
+                active.push_back({r, sids[i], next[i]});
+              }
+            }
+          }
+        }
+      }
+      if (active.empty()) continue;
+      // ---- one decode tick over all active sequences, never past the shortest remaining request
+      int nsteps = tick_;
+      for (auto& a : active) nsteps = std::min(nsteps, a.r->max_new - (int)a.r->tokens.size());
+      const int n = (int)active.size();
+      std::vector<int> sids(n);
+      std::vector<int32_t> last(n), out((size_t)n * nsteps);
+      for (int i = 0; i < n; ++i) {
+        sids[i] = active[i].sid;
+        last[i] = active[i].last;
+      }
+      if (eng_->decode(sids.data(), last.data(), n, nsteps, out.data()) != 0) {
+        const std::string e = eng_->last_error();
+        for (auto& a : active) {
+          eng_->seq_free(a.sid);
+          finish(a.r, e);
+        }
+        active.clear();
+        continue;
+      }
+      ++steps_;
+      step_rows_ += (long long)n * nsteps;
+      max_rows_ = std::max(max_rows_, n);
+      std::vector<Active> still;
+      for (int i = 0; i < n; ++i) {
+        Active& a = active[i];
+        a.r->tokens.insert(a.r->tokens.end(), out.begin() + (size_t)i * nsteps, out.begin() + (size_t)(i + 1) * nsteps);
+        a.last = a.r->tokens.back();
+        if ((int)a.r->tokens.size() >= a.r->max_new) {
+          eng_->seq_free(a.sid);
+          finish(a.r, "");
+        } else {
+          still.push_back(a);
+        }
+      }
+      active.swap(still);
+    }
+  }
+
+  EngineT* eng_;
+  int max_batch_, tick_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<Request*> waiting_;
+  bool stop_ = false;
+  std::thread worker_;
+  long long steps_ = 0, step_rows_ = 0;
+  int max_rows_ = 0;
+};
+
+}  // namespace ssbhost

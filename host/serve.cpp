@@ -31,6 +31,7 @@
 
 #include "../include/ssb.h"
 #include "../substratus_b200/csrc/json.h"
+#include "scheduler.h"
 
 using ssb::Json;
 
@@ -46,6 +47,27 @@ static ssb_tokenizer* g_tok = nullptr;  // <model_dir>/tokenizer.json, if presen
 // internal/resources/resources.go:39-47): rank 0 is g_engine, ranks 1..N-1 live here; every rank runs in its own
 // host thread per request (the ranks' kernels wait for each other over NVLink, so the calls must be concurrent).
 static std::vector<ssb_engine*> g_peers;
+
+// opt-in continuous batching (params.json {"batching": 1, "batch_tick": 8}); policy and its CPU test: scheduler.h
+struct AbiEngine {
+  ssb_engine* e;
+  std::string err;
+  int seq_create(int* sid) { return note(ssb_seq_create(e, sid)); }
+  int seq_free(int sid) { return ssb_seq_free(e, sid); }
+  int prefill(const int* sids, const int32_t* toks, const int* lens, int nseq, int32_t* next) {
+    return note(ssb_prefill(e, sids, toks, lens, nseq, next, nullptr));
+  }
+  int decode(const int* sids, const int32_t* last, int nseq, int nsteps, int32_t* out) {
+    return note(ssb_decode(e, sids, last, nseq, nsteps, out, nullptr));
+  }
+  int note(int rc) {
+    if (rc != SSB_OK) err = ssb_last_error();
+    return rc;
+  }
+  std::string last_error() { return err; }
+};
+static AbiEngine g_abi;
+static ssbhost::BatchScheduler<AbiEngine>* g_sched = nullptr;
 
 static std::string getenv_or(const char* k, const char* d) {
   const char* v = getenv(k);
@@ -138,6 +160,18 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new) {
 
 static GenResult generate(const std::vector<int32_t>& prompt, int max_new) {
   if (!g_peers.empty()) return generate_tp(prompt, max_new);
+  if (g_sched) {  // concurrent clients share prefill / decode calls
+    ssbhost::Request rq;
+    rq.prompt = prompt;
+    rq.max_new = max_new;
+    g_sched->submit(&rq);
+    GenResult r;
+    r.tokens = rq.tokens;
+    r.error = rq.error;
+    r.ttft_ms = rq.ttft_ms;
+    r.decode_ms = rq.total_ms - rq.ttft_ms;
+    return r;
+  }
   GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
   int sid = -1;
@@ -398,6 +432,15 @@ int main(int argc, char** argv) {
       _exit(rc == SSB_ENODEV ? 3 : 1);
     }
     ssb_engine_info(g_engine, &g_info);
+    try {
+      const Json pj = ssb::json_parse(params);
+      if (pj.get_int("batching", 0) != 0 && g_peers.empty()) {
+        g_abi.e = g_engine;
+        g_sched = new ssbhost::BatchScheduler<AbiEngine>(&g_abi, g_info.max_batch, (int)pj.get_int("batch_tick", 8));
+        fprintf(stderr, "serve: continuous batching on (max_batch %d)\n", g_info.max_batch);
+      }
+    } catch (std::exception&) {
+    }
     if (ssb_tok_load((model_dir + "/tokenizer.json").c_str(), &g_tok) != SSB_OK) {
       fprintf(stderr, "serve: no usable tokenizer.json (%s): text prompts disabled, token-id prompts only\n", ssb_last_error());
       g_tok = nullptr;
