@@ -22,7 +22,7 @@ def test_reference_arm_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "decode_tokens_per_sec" and d["unit"] == "tokens/s"
-    assert d["higher_is_better"] is True and d["value"] > 0
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
