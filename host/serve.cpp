@@ -85,6 +85,46 @@ static bool read_file(const std::string& p, std::string* out) {
   return true;
 }
 
+// The container contract documents params both as /content/params.json and as PARAM_{UPPER(key)} environment variables
+// (docs/container-contract.md:36-48); the reconciler at this commit only mounts the file
+// (internal/controller/params_reconciler.go:78-104).  Tolerate both: env entries fill in keys the file does not set.
+extern char** environ;
+static std::string merge_param_env(const std::string& params) {
+  std::vector<std::pair<std::string, std::string>> extra;
+  Json have;
+  try {
+    have = ssb::json_parse(params.empty() ? "{}" : params);
+  } catch (std::exception&) {
+    return params;  // the engine reports the JSON error
+  }
+  if (have.kind != Json::Obj) return params;
+  for (char** e = environ; e && *e; ++e) {
+    if (strncmp(*e, "PARAM_", 6) != 0) continue;
+    const char* eq = strchr(*e, '=');
+    if (!eq || eq == *e + 6) continue;
+    std::string key((const char*)*e + 6, eq);
+    for (auto& c : key) c = (char)tolower((unsigned char)c);
+    if (have.find(key)) continue;
+    extra.emplace_back(key, eq + 1);
+  }
+  if (extra.empty()) return params;
+  std::string out = "{";
+  for (auto& kv : extra) {
+    std::string v = kv.second;
+    bool raw = false;  // numbers / true / false / null pass through, everything else becomes a JSON string
+    try {
+      const Json j = ssb::json_parse(v);
+      raw = j.kind == Json::Num || j.kind == Json::Bool || j.kind == Json::Null;
+    } catch (std::exception&) {
+    }
+    out += "\"" + ssb::json_escape(kv.first) + "\":" + (raw ? v : "\"" + ssb::json_escape(v) + "\"") + ",";
+  }
+  const size_t brace = params.find('{');
+  const std::string rest = brace == std::string::npos ? "}" : params.substr(brace + 1);
+  if (rest.find_first_not_of(" \t\r\n") == rest.find('}')) out.pop_back();  // file object is empty: drop the trailing comma
+  return out + rest;
+}
+
 static void send_all(int fd, const std::string& s) {
   size_t off = 0;
   while (off < s.size()) {
@@ -360,11 +400,16 @@ static void handle(int fd) {
 
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
-  const std::string model_dir = argc > 1 ? argv[1] : getenv_or("MODEL_DIR", "/content/model");
+  const std::string model_dir = (argc > 1 && argv[1][0] != '-') ? argv[1] : getenv_or("MODEL_DIR", "/content/model");
   const std::string params_file = getenv_or("PARAMS_FILE", "/content/params.json");
   const int port = atoi(getenv_or("PORT", "8080").c_str());
   std::string params = "{}";
   read_file(params_file, &params);  // {} if absent (params_reconciler.go mounts it only when .spec.params is set)
+  params = merge_param_env(params);
+  if (argc > 1 && strcmp(argv[1], "--print-params") == 0) {  // what the engine will be created with (no GPU needed)
+    printf("%s\n", params.c_str());
+    return 0;
+  }
 
   int ls = socket(AF_INET, SOCK_STREAM, 0);
   int one = 1;

@@ -62,6 +62,27 @@ def test_serve_without_gpu_is_not_ready_and_exits_nonzero(tmp_path):
     assert "no CUDA device" in err or "sm_" in err
 
 
+def test_param_env_fills_keys_the_file_does_not_set(tmp_path):
+    """docs/container-contract.md:36-48: params arrive as /content/params.json and as PARAM_{UPPER(key)} env vars; the
+    file wins, env fills the rest, numbers/bools stay typed.  `serve --print-params` shows what the engine would get."""
+    pf = tmp_path / "params.json"
+    pf.write_text('{"max_batch": 4}')
+    base = {k: v for k, v in os.environ.items() if not k.startswith("PARAM_")}
+
+    def run(env, file=pf):
+        r = subprocess.run([SERVE, "--print-params"], env=dict(base, PARAMS_FILE=str(file), **env), capture_output=True, text=True, timeout=20)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.strip()
+
+    assert run({}) == '{"max_batch": 4}'  # untouched without PARAM_* in the environment
+    got = json.loads(run({"PARAM_TP_SIZE": "2", "PARAM_MAX_BATCH": "9", "PARAM_NOTE": 'a "b"', "PARAM_USE_PDL": "false"}))
+    assert got == {"max_batch": 4, "tp_size": 2, "note": 'a "b"', "use_pdl": False}
+    assert json.loads(run({"PARAM_TP_SIZE": "2"}, file=tmp_path / "absent.json")) == {"tp_size": 2}
+    empty = tmp_path / "empty.json"
+    empty.write_text("{ }")
+    assert json.loads(run({"PARAM_WEIGHTS": "synthetic"}, file=empty)) == {"weights": "synthetic"}
+
+
 @pytest.mark.gpu
 def test_serve_contract_and_generate(tmp_path):
     cfg = synth.TINY_GQA
