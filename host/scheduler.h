@@ -11,7 +11,8 @@
 //          retire sequences that produced max_new tokens      -> fulfil their promise, free their slot
 //
 // Decode never overshoots a request (the step count is the minimum remaining), newcomers wait at most one tick, and
-// greedy decoding makes every request's ids independent of who shared its batch (checked by the test).
+// greedy decoding makes every request's ids independent of who shared its batch (checked by the test).  A request may
+// carry an on_tokens callback (streaming): it sees its ids once per tick and can retire the request early.
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -30,6 +31,9 @@ namespace ssbhost {
 struct Request {
   std::vector<int32_t> prompt;
   int max_new = 0;
+  // optional: fed the ids produced since the previous call (first the prefill's token, then once per tick) from the
+  // scheduler thread; returning false retires the request early and frees its slot ("stream": true, client went away)
+  std::function<bool(const int32_t*, int)> on_tokens;
   // result
   std::vector<int32_t> tokens;
   std::string error;
@@ -130,7 +134,8 @@ class BatchScheduler {
               Request* r = ok[i];
               r->ttft_ms = now_ms() - r->t0;
               r->tokens.assign(1, next[i]);
-              if (r->max_new == 1) {
+              const bool go = !r->on_tokens || r->on_tokens(&next[i], 1);
+              if (r->max_new == 1 || !go) {
                 eng_->seq_free(sids[i]);
                 finish(r, "");
               } else {
@@ -168,7 +173,8 @@ class BatchScheduler {
         Active& a = active[i];
         a.r->tokens.insert(a.r->tokens.end(), out.begin() + (size_t)i * nsteps, out.begin() + (size_t)(i + 1) * nsteps);
         a.last = a.r->tokens.back();
-        if ((int)a.r->tokens.size() >= a.r->max_new) {
+        const bool go = !a.r->on_tokens || a.r->on_tokens(a.r->tokens.data() + a.r->tokens.size() - nsteps, nsteps);
+        if ((int)a.r->tokens.size() >= a.r->max_new || !go) {
           eng_->seq_free(a.sid);
           finish(a.r, "");
         } else {

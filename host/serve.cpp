@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -125,13 +126,14 @@ static std::string merge_param_env(const std::string& params) {
   return out + rest;
 }
 
-static void send_all(int fd, const std::string& s) {
+static bool send_all(int fd, const std::string& s) {
   size_t off = 0;
   while (off < s.size()) {
     ssize_t n = send(fd, s.data() + off, s.size() - off, MSG_NOSIGNAL);
-    if (n <= 0) return;
+    if (n <= 0) return false;  // peer went away (or SO_SNDTIMEO expired)
     off += (size_t)n;
   }
+  return true;
 }
 
 static void respond(int fd, int code, const char* status, const std::string& body, const char* ctype = "application/json") {
@@ -149,9 +151,16 @@ struct GenResult {
   std::string error;
 };
 
-// one rank's share of a request: identical inputs on every rank, identical greedy ids out
-static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, std::vector<int32_t>* toks, double* ttft_ms,
-                    double* decode_ms, std::string* error) {
+// Called with the ids produced since the previous call (first call: the prefill's token).  Returning false stops the
+// generation early (client went away); only honoured where one engine serves the request (the ranks of a TP group must
+// stay in lock-step, so there the request always runs to max_new).
+using TokenSink = std::function<bool(const int32_t*, int)>;
+
+// one rank's share of a request: identical inputs on every rank, identical greedy ids out.  `chunk` = decode steps per
+// ssb_decode call: max_new-1 for a plain request (ONE call, as the bench measures it), params.json "stream_chunk" (1)
+// for "stream": true.
+static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, int chunk, const TokenSink& sink, bool may_stop,
+                    std::vector<int32_t>* toks, double* ttft_ms, double* decode_ms, std::string* error) {
   int sid = -1;
   int rc = ssb_seq_create(e, &sid);
   if (rc != SSB_OK) {
@@ -164,19 +173,30 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
   toks->assign(max_new, 0);
   rc = ssb_prefill(e, &sid, prompt.data(), &n, 1, &first, nullptr);
   auto t1 = std::chrono::steady_clock::now();
+  int done = 0;
   if (rc == SSB_OK) {
     (*toks)[0] = first;
-    if (max_new > 1) rc = ssb_decode(e, &sid, &first, 1, max_new - 1, toks->data() + 1, nullptr);
+    done = 1;
+    bool go = !sink || sink(&first, 1) || !may_stop;
+    while (rc == SSB_OK && go && done < max_new) {
+      const int steps = std::min(std::max(1, chunk), max_new - done);
+      const int32_t last = (*toks)[done - 1];
+      rc = ssb_decode(e, &sid, &last, 1, steps, toks->data() + done, nullptr);
+      if (rc != SSB_OK) break;
+      done += steps;
+      go = !sink || sink(toks->data() + done - steps, steps) || !may_stop;
+    }
   }
   auto t2 = std::chrono::steady_clock::now();
   if (rc != SSB_OK) *error = ssb_last_error();  // thread-local in the library: read it on the calling thread
+  toks->resize(done);
   ssb_seq_free(e, sid);
   *ttft_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
   *decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
   return rc;
 }
 
-static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new) {
+static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, int chunk, const TokenSink& sink) {
   GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
   const size_t n = g_peers.size() + 1;
@@ -185,8 +205,8 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new) {
   std::vector<std::string> errs(n);
   std::vector<std::thread> th;
   for (size_t i = 1; i < n; ++i)
-    th.emplace_back([&, i] { run_rank(g_peers[i - 1], prompt, max_new, &toks[i], &ttft[i], &dec[i], &errs[i]); });
-  run_rank(g_engine, prompt, max_new, &toks[0], &ttft[0], &dec[0], &errs[0]);
+    th.emplace_back([&, i] { run_rank(g_peers[i - 1], prompt, max_new, chunk, nullptr, false, &toks[i], &ttft[i], &dec[i], &errs[i]); });
+  run_rank(g_engine, prompt, max_new, chunk, sink, false, &toks[0], &ttft[0], &dec[0], &errs[0]);
   for (auto& t : th) t.join();
   for (size_t i = 0; i < n; ++i) {
     if (!errs[i].empty()) r.error = "rank " + std::to_string(i) + ": " + errs[i];
@@ -198,42 +218,23 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new) {
   return r;
 }
 
-static GenResult generate(const std::vector<int32_t>& prompt, int max_new) {
-  if (!g_peers.empty()) return generate_tp(prompt, max_new);
-  if (g_sched) {  // concurrent clients share prefill / decode calls
+static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int chunk = 1 << 30, const TokenSink& sink = nullptr) {
+  if (!g_peers.empty()) return generate_tp(prompt, max_new, chunk, sink);
+  GenResult r;
+  if (g_sched) {  // concurrent clients share prefill / decode calls; the sink is fed once per scheduler tick
     ssbhost::Request rq;
     rq.prompt = prompt;
     rq.max_new = max_new;
+    rq.on_tokens = sink;
     g_sched->submit(&rq);
-    GenResult r;
     r.tokens = rq.tokens;
     r.error = rq.error;
     r.ttft_ms = rq.ttft_ms;
     r.decode_ms = rq.total_ms - rq.ttft_ms;
     return r;
   }
-  GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
-  int sid = -1;
-  if (ssb_seq_create(g_engine, &sid) != SSB_OK) {
-    r.error = ssb_last_error();
-    return r;
-  }
-  auto t0 = std::chrono::steady_clock::now();
-  int n = (int)prompt.size();
-  int32_t first = 0;
-  r.tokens.resize(max_new);
-  int rc = ssb_prefill(g_engine, &sid, prompt.data(), &n, 1, &first, nullptr);
-  auto t1 = std::chrono::steady_clock::now();
-  if (rc == SSB_OK) {
-    r.tokens[0] = first;
-    if (max_new > 1) rc = ssb_decode(g_engine, &sid, &first, 1, max_new - 1, r.tokens.data() + 1, nullptr);
-  }
-  auto t2 = std::chrono::steady_clock::now();
-  if (rc != SSB_OK) r.error = ssb_last_error();
-  ssb_seq_free(g_engine, sid);
-  r.ttft_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-  r.decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  run_rank(g_engine, prompt, max_new, chunk, sink, true, &r.tokens, &r.ttft_ms, &r.decode_ms, &r.error);
   return r;
 }
 
@@ -256,6 +257,83 @@ static std::string ids_json(const std::vector<int32_t>& v) {
   std::string s = "[";
   for (size_t i = 0; i < v.size(); ++i) s += (i ? "," : "") + std::to_string(v[i]);
   return s + "]";
+}
+
+// Longest prefix of s[from..] that ends on a UTF-8 character boundary and not in a U+FFFD the decoder substituted for
+// a byte-fallback run that later ids may still complete.
+static size_t utf8_safe_len(const std::string& s) {
+  size_t n = s.size();
+  size_t i = n;
+  int back = 0;
+  while (i > 0 && back < 4 && ((unsigned char)s[i - 1] & 0xC0) == 0x80) {
+    --i;
+    ++back;
+  }
+  if (i > 0) {
+    const unsigned char lead = (unsigned char)s[i - 1];
+    const int need = lead >= 0xF0 ? 4 : lead >= 0xE0 ? 3 : lead >= 0xC0 ? 2 : 1;
+    if (need > 1 && back + 1 < need) n = i - 1;  // incomplete multi-byte tail: hold it back
+  }
+  while (n >= 3 && (unsigned char)s[n - 3] == 0xEF && (unsigned char)s[n - 2] == 0xBF && (unsigned char)s[n - 1] == 0xBD) n -= 3;
+  return n;
+}
+
+// "stream": true — server-sent events, one per decode chunk (params.json "stream_chunk", default 1 token), in the
+// OpenAI completions-stream shape the reference's browser UI consumes (internal/tui/serve.go:282-289 points users at
+// Basaran's streaming playground); terminated by `data: [DONE]`.  Text is detokenised incrementally: every event carries
+// the new suffix of decode(all ids so far), cut at a UTF-8 boundary, so the concatenation equals the non-streamed text.
+static int g_stream_chunk = 1;
+static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt, int max_new, bool text_mode) {
+  send_all(fd, "HTTP/1.1 200 OK\r\nContent-Type: text/event-stream\r\nCache-Control: no-cache\r\nConnection: close\r\n\r\n");
+  std::vector<int32_t> all;
+  size_t emitted = 0;
+  const std::string model = g_info.model_type;
+  auto event = [&](const int32_t* ids, int n, const std::string& piece, const char* finish, const std::string& extra) {
+    const std::string idj = ids_json(std::vector<int32_t>(ids, ids + n));
+    std::string e = "data: ";
+    if (oai)
+      e += "{\"object\":\"text_completion\",\"model\":\"" + model + "\",\"choices\":[{\"index\":0,\"text\":\"" + ssb::json_escape(piece) +
+           "\",\"tokens\":" + idj + ",\"finish_reason\":" + (finish ? "\"" + std::string(finish) + "\"" : std::string("null")) + "}]" + extra + "}";
+    else
+      e += "{\"tokens\":" + idj + ",\"text\":\"" + ssb::json_escape(piece) + "\",\"done\":" + (finish ? "true" : "false") + extra + "}";
+    return send_all(fd, e + "\n\n");
+  };
+  auto next_piece = [&](bool flush) {
+    std::string piece;
+    if (text_mode && g_tok && !all.empty()) {
+      std::vector<char> buf(16 * all.size() + 64);
+      int len = 0;
+      if (ssb_tok_decode(g_tok, all.data(), (int)all.size(), 1, buf.data(), (int)buf.size(), &len) == SSB_OK) {
+        const std::string full(buf.data(), (size_t)len);
+        const size_t upto = flush ? full.size() : utf8_safe_len(full);
+        if (upto > emitted) {
+          piece = full.substr(emitted, upto - emitted);
+          emitted = upto;
+        }
+      }
+    }
+    return piece;
+  };
+  TokenSink sink = [&](const int32_t* ids, int n) {
+    all.insert(all.end(), ids, ids + n);
+    return event(ids, n, next_piece(false), nullptr, "");
+  };
+  GenResult r = generate(prompt, max_new, g_stream_chunk, sink);
+  if (!r.error.empty()) {
+    g_errors++;
+    send_all(fd, "data: " + err_json(r.error) + "\n\n");
+  } else {
+    g_tokens += (long long)r.tokens.size();
+    g_ttft_ms_sum.store(g_ttft_ms_sum.load() + r.ttft_ms);
+    g_decode_ms_sum.store(g_decode_ms_sum.load() + r.decode_ms);
+    char tail[320];
+    const double tps = r.decode_ms > 0 && r.tokens.size() > 1 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
+    snprintf(tail, sizeof tail,
+             ",\"usage\":{\"prompt_tokens\":%zu,\"completion_tokens\":%zu},\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f",
+             prompt.size(), r.tokens.size(), r.ttft_ms, r.decode_ms, tps);
+    event(nullptr, 0, next_piece(true), (int)r.tokens.size() >= max_new ? "length" : "cancelled", tail);
+  }
+  send_all(fd, "data: [DONE]\n\n");
 }
 
 static void handle(int fd) {
@@ -320,7 +398,7 @@ static void handle(int fd) {
       std::string err;
       std::vector<int32_t> prompt;
       int max_new = 16;
-      bool ok = true, text_mode = false;
+      bool ok = true, text_mode = false, stream = false;
       try {
         Json j = ssb::json_parse(body);
         const bool oai = path == "/v1/completions";
@@ -350,6 +428,7 @@ static void handle(int fd) {
           ok = parse_ids(p, g_info.vocab_size, &prompt, &err);
         }
         max_new = (int)j.get_int(oai ? "max_tokens" : "max_new_tokens", 16);
+        if (const Json* st = j.find("stream")) stream = (st->kind == Json::Bool && st->b) || (st->kind == Json::Num && st->num != 0);
         if (ok && (max_new < 1 || (int)prompt.size() + max_new > g_info.max_seq_len)) {
           ok = false;
           err = "prompt length + max tokens exceeds max_seq_len";
@@ -361,6 +440,8 @@ static void handle(int fd) {
       if (!ok) {
         g_errors++;
         respond(fd, 400, "Bad Request", err_json(err));
+      } else if (stream) {
+        stream_response(fd, path == "/v1/completions", prompt, max_new, text_mode);
       } else {
         GenResult r = generate(prompt, max_new);
         if (!r.error.empty()) {
@@ -479,6 +560,7 @@ int main(int argc, char** argv) {
     ssb_engine_info(g_engine, &g_info);
     try {
       const Json pj = ssb::json_parse(params);
+      g_stream_chunk = std::max(1, (int)pj.get_int("stream_chunk", 1));
       if (pj.get_int("batching", 0) != 0 && g_peers.empty()) {
         g_abi.e = g_engine;
         g_sched = new ssbhost::BatchScheduler<AbiEngine>(&g_abi, g_info.max_batch, (int)pj.get_int("batch_tick", 8));
@@ -500,6 +582,8 @@ int main(int argc, char** argv) {
     int fd = accept(ls, nullptr, nullptr);
     if (fd < 0) continue;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+    timeval snd{10, 0};  // a stalled streaming client must not hold the engine (or the batch scheduler) for ever
+    setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &snd, sizeof snd);
     std::thread(handle, fd).detach();
   }
 }

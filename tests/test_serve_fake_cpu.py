@@ -1,0 +1,263 @@
+"""The serve host's HTTP surface on a CPU-only box: host/serve.cpp built against tests/fake_ssb/fake_ssb.cpp (a GPU-free
+stand-in for the C ABI; see its header) instead of libsubstratus_b200.so.  Covers what the reference's container contract
+and its one request shape need from the HOST (docs/container-contract.md:50-55, server_controller.go:156-172,
+test/system.sh:73-78): readiness 503 -> 200, request validation, /generate and /v1/completions, "stream": true (SSE),
+opt-in continuous batching, the in-container tensor-parallel rank threads, error propagation.  The same requests run
+against the real engine in tests/test_serve_host.py (-m gpu)."""
+import concurrent.futures as cf
+import json
+import os
+import socket
+import subprocess
+import time
+import urllib.error
+import urllib.request
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+M64 = (1 << 64) - 1
+
+
+def fold(s, tok):
+    z = (s + 0x9E3779B97F4A7C15 + (tok & 0xFFFFFFFF)) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def fake_generate(prompt, n, vocab):
+    s = 0
+    for t in prompt:
+        s = fold(s, t)
+    out = [s % vocab]
+    while len(out) < n:
+        s = fold(s, out[-1])
+        out.append(s % vocab)
+    return out
+
+
+@pytest.fixture(scope="module")
+def serve_fake(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("fake") / "serve_fake")
+    src = [os.path.join(ROOT, p) for p in ("host/serve.cpp", "tests/fake_ssb/fake_ssb.cpp", "substratus_b200/csrc/tokenizer.cpp",
+                                           "substratus_b200/csrc/loader.cpp")]
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wall", "-o", exe] + src, check=True, cwd=os.path.join(ROOT, "host"))
+    return exe
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _req(port, path, body=None, timeout=20):
+    data = None if body is None else (body if isinstance(body, bytes) else json.dumps(body).encode())
+    try:
+        with urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}{path}", data=data), timeout=timeout) as r:
+            raw = r.read()
+            return r.status, (json.loads(raw) if r.headers.get_content_type() == "application/json" else raw.decode())
+    except urllib.error.HTTPError as e:
+        return e.code, json.loads(e.read() or b"{}")
+
+
+def _sse(port, path, body, timeout=30):
+    """-> list of decoded `data:` payloads (the last one is the string "[DONE]")"""
+    with urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}{path}", data=json.dumps(body).encode()), timeout=timeout) as r:
+        assert r.status == 200 and r.headers.get_content_type() == "text/event-stream"
+        raw = r.read()
+    events = []
+    for block in raw.split(b"\n\n"):
+        if block:
+            block = block.decode("utf-8")  # every event on its own must be valid UTF-8 (no character cut between events)
+            assert block.startswith("data: "), block
+            events.append(block[6:] if block[6:] == "[DONE]" else json.loads(block[6:]))
+    return events
+
+
+class Server:
+    def __init__(self, exe, tmp_path, params, tokenizer=None):
+        self.port = _free_port()
+        d = tmp_path / f"model{self.port}"
+        d.mkdir()
+        if tokenizer:
+            tokenizer(str(d / "tokenizer.json"))
+        pf = d / "params.json"
+        pf.write_text(json.dumps(params))
+        env = {k: v for k, v in os.environ.items() if not k.startswith("PARAM_")}
+        env.update(PORT=str(self.port), PARAMS_FILE=str(pf), MODEL_DIR=str(d))
+        self.p = subprocess.Popen([exe], env=env, stderr=subprocess.PIPE, text=True)
+
+    def wait_ready(self, timeout=20):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if _req(self.port, "/")[0] == 200:
+                    return
+            except (urllib.error.URLError, ConnectionError):
+                pass
+            assert self.p.poll() is None, self.p.stderr.read()
+            time.sleep(0.02)
+        raise AssertionError("server did not become ready")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.p.kill()
+        self.p.wait()
+
+
+def test_readiness_503_until_loaded_then_200(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_load_ms": 1500}) as s:
+        t0 = time.time()
+        saw_503 = False
+        while time.time() - t0 < 10:
+            try:
+                code, body = _req(s.port, "/")
+            except (urllib.error.URLError, ConnectionError):
+                time.sleep(0.02)
+                continue
+            if code == 503:
+                saw_503 = True
+                assert body == {"status": "loading"}
+                assert _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 2})[0] == 503  # not ready: refuse work
+                time.sleep(0.1)
+            else:
+                assert code == 200 and body["status"] == "ready"
+                break
+        assert saw_503, "the probe must see 503 (not a refused connection) while the model loads"
+        assert _req(s.port, "/healthz")[0] == 200
+
+
+def test_load_failure_exits_nonzero(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_load_error": 1}) as s:
+        assert s.p.wait(timeout=10) == 1  # Deployment restarts the pod (server_controller.go:280-296)
+        assert "engine create failed" in s.p.stderr.read()
+
+
+def test_generate_and_completions_ids_and_validation(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_vocab": 321, "max_seq_len": 64}) as s:
+        s.wait_ready()
+        prompt = [5, 17, 300, 2]
+        want = fake_generate(prompt, 9, 321)
+        code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 9})
+        assert code == 200 and r["tokens"] == want and r["text"] == ""
+        code, r = _req(s.port, "/v1/completions", {"prompt": prompt, "max_tokens": 9})
+        assert code == 200 and r["choices"][0]["tokens"] == want and r["choices"][0]["finish_reason"] == "length"
+        assert r["usage"] == {"prompt_tokens": 4, "completion_tokens": 9} and r["object"] == "text_completion"
+        assert _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 1})[1]["tokens"] == want[:1]
+        # validation: 400 with an error string, the engine is never called
+        for bad in ({"tokens": [], "max_new_tokens": 2}, {"tokens": [321], "max_new_tokens": 2}, {"tokens": [1.5]}, {"tokens": [-1]},
+                    {"tokens": "x"}, {"tokens": [1] * 60, "max_new_tokens": 10}, {"tokens": [1], "max_new_tokens": 0}, {}):
+            code, r = _req(s.port, "/generate", bad)
+            assert code == 400 and r["error"], bad
+        assert _req(s.port, "/generate", b"{not json")[0] == 400
+        code, r = _req(s.port, "/v1/completions", {"prompt": "text", "max_tokens": 2})
+        assert code == 400 and "tokenizer.json" in r["error"]  # no tokenizer in the model dir: ids only, said clearly
+        assert _req(s.port, "/nope")[0] == 404
+        code, m = _req(s.port, "/metrics")
+        assert code == 200 and "ssb_requests_total" in m and "ssb_generated_tokens_total 19" in m
+
+
+@pytest.mark.parametrize("chunk", [1, 4])
+def test_stream_ids_match_plain_request(serve_fake, tmp_path, chunk):
+    with Server(serve_fake, tmp_path, {"fake_vocab": 500, "stream_chunk": chunk}) as s:
+        s.wait_ready()
+        prompt = [9, 8, 7]
+        want = fake_generate(prompt, 11, 500)
+        ev = _sse(s.port, "/v1/completions", {"prompt": prompt, "max_tokens": 11, "stream": True})
+        assert ev[-1] == "[DONE]"
+        body, last = ev[:-2], ev[-2]
+        assert [len(e["choices"][0]["tokens"]) for e in body] == [1] + [chunk] * (10 // chunk) + ([10 % chunk] if 10 % chunk else [])
+        assert sum((e["choices"][0]["tokens"] for e in body), []) == want
+        assert all(e["choices"][0]["finish_reason"] is None for e in body)
+        assert last["choices"][0]["finish_reason"] == "length" and last["usage"] == {"prompt_tokens": 3, "completion_tokens": 11}
+        ev = _sse(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 11, "stream": 1})
+        assert sum((e["tokens"] for e in ev[:-1]), []) == want and ev[-2]["done"] is True and ev[0]["done"] is False
+
+
+def test_stream_text_is_the_plain_text_cut_at_utf8_boundaries(serve_fake, tmp_path):
+    from test_tokenizer import _llama_like
+
+    vocab = {}
+
+    def make(path):
+        vocab["n"] = _llama_like(path).get_vocab_size()
+
+    # ids are pseudo-random over the whole vocabulary, so byte-fallback pieces (<0xNN>) and multi-byte characters split
+    # across events are common: every event must still be valid UTF-8 and the pieces must add up to the plain answer
+    with Server(serve_fake, tmp_path, {"fake_vocab": 700}, tokenizer=make) as s:
+        s.wait_ready()
+        assert vocab["n"] <= 700
+    with Server(serve_fake, tmp_path, {"fake_vocab": vocab["n"]}, tokenizer=make) as s:
+        s.wait_ready()
+        for text in ["Hello world", "naïve 你好 🙂", "the quick brown fox"]:
+            code, plain = _req(s.port, "/v1/completions", {"prompt": text, "max_tokens": 60})
+            assert code == 200, plain
+            ev = _sse(s.port, "/v1/completions", {"prompt": text, "max_tokens": 60, "stream": True})
+            ids = sum((e["choices"][0]["tokens"] for e in ev[:-1]), [])
+            pieces = [e["choices"][0]["text"] for e in ev[:-1]]
+            assert ids == plain["choices"][0]["tokens"]
+            assert "".join(pieces) == plain["choices"][0]["text"]
+            assert all("�" not in p for p in pieces[:-1]) or "�" in plain["choices"][0]["text"]
+
+
+def test_decode_failure_is_reported(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_fail_after": 2}) as s:
+        s.wait_ready()
+        ev = _sse(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 8, "stream": True})
+        assert ev[-1] == "[DONE]" and "decode failure" in ev[-2]["error"] and len(ev) == 3 + 2  # first token + 2 good chunks
+        code, r = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 8})
+        assert code == 500 and "decode failure" in r["error"]
+        assert "ssb_errors_total 2" in _req(s.port, "/metrics")[1]
+
+
+@pytest.mark.parametrize("stream", [False, True])
+def test_continuous_batching_keeps_every_request_its_own_ids(serve_fake, tmp_path, stream):
+    with Server(serve_fake, tmp_path, {"fake_vocab": 999, "batching": 1, "batch_tick": 4, "max_batch": 4, "fake_step_us": 1500}) as s:
+        s.wait_ready()
+
+        def one(i):
+            prompt = [i + 1, 2 * i + 3, 7]
+            n = 5 + 3 * (i % 5)
+            if stream:
+                ev = _sse(s.port, "/generate", {"tokens": prompt, "max_new_tokens": n, "stream": True})
+                got = sum((e["tokens"] for e in ev[:-1]), [])
+            else:
+                code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": n})
+                assert code == 200, r
+                got = r["tokens"]
+            return got == fake_generate(prompt, n, 999)
+
+        with cf.ThreadPoolExecutor(10) as ex:  # more clients than slots: the rest wait their turn
+            assert all(ex.map(one, range(10)))
+
+
+def test_tensor_parallel_ranks_in_one_container(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"tp_size": 4, "fake_vocab": 100}) as s:
+        s.wait_ready()
+        want = fake_generate([3, 4], 6, 100)
+        assert _req(s.port, "/generate", {"tokens": [3, 4], "max_new_tokens": 6})[1]["tokens"] == want
+        ev = _sse(s.port, "/generate", {"tokens": [3, 4], "max_new_tokens": 6, "stream": True})
+        assert sum((e["tokens"] for e in ev[:-1]), []) == want
+
+
+def test_stream_client_disconnect_frees_the_engine(serve_fake, tmp_path):
+    # 4000 steps x 2 ms = 8 s if the server kept generating for a client that left
+    with Server(serve_fake, tmp_path, {"fake_step_us": 2000, "max_seq_len": 8192}) as s:
+        s.wait_ready()
+        c = socket.create_connection(("127.0.0.1", s.port))
+        body = json.dumps({"tokens": [1], "max_new_tokens": 4000, "stream": True}).encode()
+        c.sendall(b"POST /generate HTTP/1.1\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+        got = b""
+        while b"data: " not in got:
+            got += c.recv(4096)
+        c.close()
+        t0 = time.time()
+        code, r = _req(s.port, "/generate", {"tokens": [2], "max_new_tokens": 3})
+        assert code == 200 and r["tokens"] == fake_generate([2], 3, 1000)
+        assert time.time() - t0 < 4.0, "the abandoned stream kept the engine busy"
