@@ -31,7 +31,7 @@ extern "C" {
 
 #define SSB_OK 0
 #define SSB_EINVAL (-1)  /* bad argument / bad config / bad params.json          */
-#define SSB_EIO (-2)     /* model directory / safetensors / gguf could not be read */
+#define SSB_EIO (-2)     /* model directory / safetensors / .bin / gguf could not be read */
 #define SSB_ENODEV (-3)  /* no CUDA device of compute capability 10.x            */
 #define SSB_ENOMEM (-4)  /* HBM or KV-block pool exhausted                       */
 #define SSB_ECUDA (-5)   /* CUDA runtime error (message in ssb_last_error)       */
@@ -59,7 +59,7 @@ typedef struct ssb_timing {
 
 /* Model load: stands in for the external image's `from_pretrained(/content/model)`
  * at pod start (docs/container-contract.md:25-36).  model_dir is an
- * HF snapshot dir (config.json + *.safetensors [+ index]) or holds a single GGUF
+ * HF snapshot dir (config.json + *.safetensors, else pytorch_model*.bin [+ index]) or holds a single GGUF
  * file; params_json is the text of /content/params.json (internal/controller/
  * params_reconciler.go:36-53), may be NULL or "{}".  Recognised params:
  *   "max_batch" (32), "max_seq_len" (config's), "kv_block_size" (16), "kv_blocks" (auto),
@@ -125,6 +125,15 @@ int ssb_debug_read(ssb_engine* e, const char* name, float* dst, int64_t dst_elem
  * ggml_type = GGML type id (0 F32, 1 F16, 2 Q4_0, 8 Q8_0, 12 Q4_K, 14 Q6_K, 30 BF16); blocks = raw bytes (host);
  * dst = n_elems bf16 bit patterns (host).  Runs the load-time CUDA kernel. */
 int ssb_debug_dequant(int ggml_type, const void* blocks, int64_t nbytes, int64_t n_elems, uint16_t* dst_bf16);
+
+/* Model-artifact inspection without a device: opens model_dir with the engine's own container readers (safetensors,
+ * pytorch_model*.bin torch.save zips, GGUF — SURVEY §8f #2) and returns one tensor's raw stored bytes.  dtype: 0 bf16,
+ * 1 f16, 2 f32, 10 Q4_0, 11 Q4_K, 12 Q6_K, 13 Q8_0, 99 other; shape (outermost first) into shape[0..*ndim), at most 4
+ * dims.  name == NULL: *nbytes_out = number of tensors in the artifact.  dst may be NULL (cap 0) to query sizes.
+ * SSB_EIO if the artifact or tensor is missing, SSB_ENOMEM if cap is too small.  Used by tests/ and by operators
+ * checking an artifact before scheduling a GPU pod; never on the request path. */
+int ssb_model_read_tensor(const char* model_dir, const char* name, void* dst, int64_t cap, int64_t* nbytes_out, int* dtype,
+                          int64_t* shape, int* ndim);
 
 /* Deterministic synthetic-weight generator exposed for the oracle cross-check
  * (tests/: bit-exact against oracle/synth.py).  Fills dst (host, uint16 bf16 bits). */

@@ -59,7 +59,7 @@ static bool ends_with(const std::string& s, const std::string& suf) {
 }
 
 bool ModelFiles::open(const std::string& dir, std::string* err) {
-  std::vector<std::string> st, gg;
+  std::vector<std::string> st, gg, pt;
   DIR* d = opendir(dir.c_str());
   if (!d) {
     *err = "cannot open model dir " + dir + ": " + strerror(errno);
@@ -69,13 +69,20 @@ bool ModelFiles::open(const std::string& dir, std::string* err) {
     std::string n = e->d_name;
     if (ends_with(n, ".safetensors")) st.push_back(n);
     if (ends_with(n, ".gguf") || n == "model.bin") gg.push_back(n);
+    if (n.rfind("pytorch_model", 0) == 0 && ends_with(n, ".bin")) pt.push_back(n);  // pytorch_model.bin / -0000x-of-0000y.bin
   }
   closedir(d);
   std::sort(st.begin(), st.end());
   std::sort(gg.begin(), gg.end());
+  std::sort(pt.begin(), pt.end());
   if (!st.empty()) {
     for (auto& n : st)
       if (!open_safetensors(dir + "/" + n, err)) return false;
+    return true;
+  }
+  if (!pt.empty()) {  // same tensor names as the safetensors of the same snapshot (HF writes both from one state dict)
+    for (auto& n : pt)
+      if (!open_torch_zip(dir + "/" + n, err)) return false;
     return true;
   }
   for (auto& n : gg) {
@@ -85,7 +92,7 @@ bool ModelFiles::open(const std::string& dir, std::string* err) {
     f.reset();
     if (magic) return open_gguf(dir + "/" + n, err);
   }
-  *err = "no *.safetensors or GGUF file in " + dir;
+  *err = "no *.safetensors, pytorch_model*.bin or GGUF file in " + dir;
   return false;
 }
 

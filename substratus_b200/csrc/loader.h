@@ -1,4 +1,4 @@
-// loader.h — model-directory readers: HF snapshot (config.json + safetensors [+index]) and GGUF.
+// loader.h — model-directory readers: HF snapshot (config.json + safetensors or pytorch_model*.bin [+index]) and GGUF.
 // Stands in for the external image's `from_pretrained(/content/model)`; the on-disk layouts are what the
 // reference's model-loader image leaves under the Model artifact (SURVEY.md §8a D0, §8f #2;
 // examples/llama2-7b/base-model.yaml, examples/llama2-13b-chat-gguf/base-model.yaml:8-9 `files: model.bin`).
@@ -40,7 +40,8 @@ class MappedFile {
 
 class ModelFiles {
  public:
-  // Opens every *.safetensors (or the single *.gguf / model.bin GGUF) under dir.  Returns false + err on failure.
+  // Opens every *.safetensors — else every pytorch_model*.bin (torch.save zip, torch_zip.cpp) — else the single
+  // *.gguf / model.bin GGUF under dir.  Returns false + err on failure.
   bool open(const std::string& dir, std::string* err);
   const TensorView* find(const std::string& name) const;
   bool is_gguf() const { return is_gguf_; }
@@ -51,6 +52,7 @@ class ModelFiles {
  private:
   bool open_safetensors(const std::string& path, std::string* err);
   bool open_gguf(const std::string& path, std::string* err);
+  bool open_torch_zip(const std::string& path, std::string* err);
   std::vector<std::unique_ptr<MappedFile>> files_;
   std::map<std::string, TensorView> tensors_;
   bool is_gguf_ = false;

@@ -46,7 +46,7 @@ EXPORTS = [
     "ssb_engine_create", "ssb_engine_destroy", "ssb_engine_info", "ssb_seq_create", "ssb_seq_free", "ssb_seq_len",
     "ssb_prefill", "ssb_decode", "ssb_last_timing", "ssb_timing_reset", "ssb_tp_handle_size", "ssb_tp_export",
     "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_profile", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version", "ssb_tok_load", "ssb_tok_free", "ssb_tok_encode",
-    "ssb_tok_decode",
+    "ssb_tok_decode", "ssb_model_read_tensor",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library(path: str | None = None):
     lib.ssb_tok_free.restype = None
     lib.ssb_tok_encode.argtypes = [vp, C.c_char_p, C.c_int, i32p, C.c_int, ip]
     lib.ssb_tok_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_char_p, C.c_int, ip]
+    lib.ssb_model_read_tensor.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64), ip, C.POINTER(C.c_int64), ip]
     lib.ssb_last_error.restype = C.c_char_p
     lib.ssb_version.restype = C.c_char_p
     if path is None:
@@ -248,6 +249,30 @@ def debug_dequant(ggml_type: int, blocks: np.ndarray, n_elems: int) -> np.ndarra
     _check(lib, lib.ssb_debug_dequant(ggml_type, raw.ctypes.data_as(C.c_void_p), raw.size, n_elems,
                                       out.ctypes.data_as(C.POINTER(C.c_uint16))))
     return out
+
+
+_DTYPE_NAMES = {0: "bf16", 1: "f16", 2: "f32", 10: "q4_0", 11: "q4_k", 12: "q6_k", 13: "q8_0", 99: "other"}
+
+
+def model_tensor_count(model_dir: str) -> int:
+    """Number of tensors the engine's container readers find under model_dir (no device needed)."""
+    lib = load_library()
+    n = C.c_int64()
+    _check(lib, lib.ssb_model_read_tensor(str(model_dir).encode(), None, None, 0, C.byref(n), None, None, None))
+    return n.value
+
+
+def model_read_tensor(model_dir: str, name: str):
+    """One tensor of a Model artifact as the engine's readers see it: (dtype name, shape tuple, raw stored bytes as
+    np.uint8).  Host only — safetensors / pytorch_model*.bin / GGUF (include/ssb.h: ssb_model_read_tensor)."""
+    lib = load_library()
+    nbytes, dt, nd = C.c_int64(), C.c_int(), C.c_int()
+    shape = (C.c_int64 * 4)()
+    d = str(model_dir).encode()
+    _check(lib, lib.ssb_model_read_tensor(d, name.encode(), None, 0, C.byref(nbytes), C.byref(dt), shape, C.byref(nd)))
+    buf = np.empty(nbytes.value, dtype=np.uint8)
+    _check(lib, lib.ssb_model_read_tensor(d, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(nbytes), None, None, None))
+    return _DTYPE_NAMES.get(dt.value, "other"), tuple(shape[i] for i in range(min(nd.value, 4))), buf
 
 
 class NativeTokenizer:

@@ -98,3 +98,194 @@ def test_gguf_container(tmp_path, no_gpu, lib):
     w.close()
     e = _create(tmp_path / "x")
     assert e.code in (EINVAL, EIO)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pytorch_model*.bin (torch.save zip + pickle) — the other HF snapshot layout, read natively by
+# substratus_b200/csrc/torch_zip.cpp; ssb_model_read_tensor exposes what the engine's readers see, byte for byte.
+def _bytes(t):
+    return t.contiguous().view(torch.uint8).numpy().tobytes()
+
+
+def _bin_dir(path, cfg, sd, save=None, **kw):
+    llama_ref.write_hf_dir(str(path), cfg, {})
+    for f in os.listdir(path):
+        if f.endswith(".safetensors") or f.endswith(".index.json"):
+            os.remove(os.path.join(path, f))
+    (save or torch.save)(sd, os.path.join(path, "pytorch_model.bin"), **kw)
+
+
+@pytest.mark.parametrize("variant", ["ordered_bf16", "proto4", "f16", "f32", "module_state_dict", "wrapped"])
+def test_torch_bin_snapshot_reads_the_bytes_torch_saved(tmp_path, no_gpu, lib, variant):
+    from collections import OrderedDict
+
+    from substratus_b200.engine import model_read_tensor, model_tensor_count
+
+    cfg = synth.TINY_GQA
+    sd = OrderedDict(synth.llama_state_dict(cfg, 5))
+    kw = {}
+    if variant == "proto4":
+        kw["pickle_protocol"] = 4
+    if variant in ("f16", "f32"):
+        sd = OrderedDict((k, v.to(torch.float16 if variant == "f16" else torch.float32)) for k, v in sd.items())
+    saved = sd
+    if variant == "module_state_dict":  # nn.Module.state_dict(): OrderedDict subclass state (_metadata) arrives via BUILD
+        m = torch.nn.ModuleDict({"a": torch.nn.Linear(4, 4)})
+        saved = m.state_dict()
+        for k, v in sd.items():
+            saved[k] = v
+    if variant == "wrapped":
+        saved = {"epoch": 3, "lr": 1e-4, "state_dict": sd, "note": "x"}
+    _bin_dir(tmp_path, cfg, saved, **kw)
+    assert model_tensor_count(tmp_path) == len(sd) + (2 if variant == "module_state_dict" else 0)
+    for k, v in sd.items():
+        dt, shape, raw = model_read_tensor(tmp_path, k)
+        assert dt == {"f16": "f16", "f32": "f32"}.get(variant, "bf16") and shape == tuple(v.shape), k
+        assert raw.tobytes() == _bytes(v), k
+    assert _create(tmp_path).code == ENODEV  # the inventory is complete: only the device is missing
+
+
+def test_torch_bin_shards_views_and_shared_storage(tmp_path, no_gpu, lib):
+    from substratus_b200.engine import model_read_tensor
+
+    cfg = synth.TINY_MHA
+    sd = synth.llama_state_dict(cfg, 2)
+    # shard 1 holds slices of ONE big storage (non-zero storage offsets) and a tensor stored twice under two names
+    names = sorted(sd)
+    half = names[: len(names) // 2]
+    flat = torch.cat([sd[k].flatten() for k in half])
+    views, off = {}, 0
+    for k in half:
+        n = sd[k].numel()
+        views[k] = flat[off:off + n].view(sd[k].shape)
+        off += n
+    views["alias.of.norm"] = views["model.norm.weight"] if "model.norm.weight" in views else views[half[0]]
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    for f in os.listdir(tmp_path):
+        if f.endswith(".safetensors"):
+            os.remove(tmp_path / f)
+    torch.save(views, tmp_path / "pytorch_model-00001-of-00002.bin")
+    torch.save({k: sd[k] for k in names[len(names) // 2:]}, tmp_path / "pytorch_model-00002-of-00002.bin")
+    (tmp_path / "pytorch_model.bin.index.json").write_text(json.dumps({"weight_map": {}}))
+    torch.save({"unrelated": torch.zeros(3)}, tmp_path / "training_args.bin")  # not a weight shard: must be ignored
+    for k, v in sd.items():
+        dt, shape, raw = model_read_tensor(tmp_path, k)
+        assert shape == tuple(v.shape) and raw.tobytes() == _bytes(v), k
+    from substratus_b200 import SsbError
+
+    with pytest.raises(SsbError):
+        model_read_tensor(tmp_path, "unrelated")
+    assert _create(tmp_path).code == ENODEV
+
+
+def _stored_zip(path, members, compress=False):
+    import zipfile
+
+    with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED if compress else zipfile.ZIP_STORED) as z:
+        for n, b in members.items():
+            z.writestr(n, b)
+
+
+def test_torch_bin_refuses_what_it_does_not_understand(tmp_path, lib):
+    import io
+    import pickle
+    import zipfile
+
+    from substratus_b200 import SsbError
+    from substratus_b200.engine import model_read_tensor
+
+    cfg = synth.TINY_MHA
+    sd = synth.llama_state_dict(cfg, 2)
+
+    def err(d):
+        with pytest.raises(SsbError) as ei:
+            model_read_tensor(d, "model.norm.weight")
+        return str(ei.value)
+
+    a = tmp_path / "legacy"
+    a.mkdir()
+    torch.save(sd, a / "pytorch_model.bin", _use_new_zipfile_serialization=False)
+    assert "legacy torch.save format" in err(a)
+    b = tmp_path / "transposed"
+    b.mkdir()
+    torch.save({"model.norm.weight": torch.zeros(4, 6).t()}, b / "pytorch_model.bin")
+    assert "not stored contiguously" in err(b)
+    c = tmp_path / "hostile"  # a pickle that would run os.system under pickle.load: here nothing is ever called
+    c.mkdir()
+
+    class Boom:
+        def __reduce__(self):
+            return (os.system, ("touch " + str(tmp_path / "pwned"),))
+
+    _stored_zip(c / "pytorch_model.bin", {"archive/data.pkl": pickle.dumps(Boom(), protocol=2), "archive/version": b"3\n"})
+    assert "does not hold a state dict" in err(c) and not (tmp_path / "pwned").exists()
+    _stored_zip(c / "pytorch_model.bin", {"archive/data.pkl": pickle.dumps({"model.norm.weight": Boom()}, protocol=2)})
+    assert "no tensors" in err(c) and not (tmp_path / "pwned").exists()
+    _stored_zip(c / "pytorch_model.bin", {"archive/data.pkl": b"\x80\x02\x8e\x00."})  # BYTEARRAY8: not in torch checkpoints
+    assert "unsupported pickle opcode 0x8e" in err(c)
+    _stored_zip(c / "pytorch_model.bin", {"archive/data.pkl": b"\x80\x02}X\x04\x00\x00"})
+    assert "truncated" in err(c)
+    _stored_zip(c / "pytorch_model.bin", {"archive/other": b"x"})
+    assert "no data.pkl" in err(c)
+    d = tmp_path / "deflated"
+    d.mkdir()
+    buf = io.BytesIO()
+    torch.save(sd, buf)
+    with zipfile.ZipFile(io.BytesIO(buf.getvalue())) as z:
+        _stored_zip(d / "pytorch_model.bin", {n: z.read(n) for n in z.namelist()}, compress=True)
+    assert "compressed" in err(d)
+    e = tmp_path / "cut"
+    e.mkdir()
+    raw = buf.getvalue()
+    (e / "pytorch_model.bin").write_bytes(raw[: len(raw) // 2])
+    assert "zip" in err(e)
+    # storage shorter than the tensor claims: re-pack with one storage truncated
+    f = tmp_path / "short"
+    f.mkdir()
+    with zipfile.ZipFile(io.BytesIO(raw)) as z:
+        members = {n: z.read(n) for n in z.namelist()}
+    for n in members:
+        if "/data/" in n:
+            members[n] = members[n][:-2]
+    _stored_zip(f / "pytorch_model.bin", members)
+    with pytest.raises(SsbError) as ei:
+        model_read_tensor(f, "model.embed_tokens.weight")
+    assert "runs past its storage" in str(ei.value)
+
+
+def test_torch_bin_zip64_directory(tmp_path, lib):
+    """Checkpoints above 4 GiB use ZIP64 records (sizes/offsets 0xFFFFFFFF + extra field 0x0001, ZIP64 end record and
+    locator).  Re-pack a small checkpoint with every central-directory field forced into its ZIP64 form."""
+    import io
+    import zipfile
+
+    from substratus_b200.engine import model_read_tensor
+
+    sd = {"w": torch.arange(24, dtype=torch.float32).view(4, 6), "v": torch.ones(7, dtype=torch.bfloat16)}
+    buf = io.BytesIO()
+    torch.save(sd, buf)
+    with zipfile.ZipFile(io.BytesIO(buf.getvalue())) as z:
+        members = [(n, z.read(n)) for n in z.namelist()]
+    out, cd = bytearray(), bytearray()
+    for name, data in members:
+        nb = name.encode()
+        lho = len(out)
+        out += struct.pack("<IHHHHHIIIHH", 0x04034B50, 45, 0, 0, 0, 0, 0, 0xFFFFFFFF, 0xFFFFFFFF, len(nb), 20) + nb
+        out += struct.pack("<HHQQ", 1, 16, len(data), len(data)) + data
+        extra = struct.pack("<HHQQQ", 1, 24, len(data), len(data), lho)
+        cd += struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 45, 45, 0, 0, 0, 0, 0, 0xFFFFFFFF, 0xFFFFFFFF, len(nb), len(extra), 0, 0, 0, 0,
+                          0xFFFFFFFF) + nb + extra
+    cd_off = len(out)
+    out += cd
+    z64 = len(out)
+    out += struct.pack("<IQHHIIQQQQ", 0x06064B50, 44, 45, 45, 0, 0, len(members), len(members), len(cd), cd_off)
+    out += struct.pack("<IIQI", 0x07064B50, 0, z64, 1)
+    out += struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, 0xFFFF, 0xFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0)
+    (tmp_path / "pytorch_model.bin").write_bytes(bytes(out))
+    with zipfile.ZipFile(tmp_path / "pytorch_model.bin") as z:  # python agrees this is a valid archive
+        assert sorted(z.namelist()) == sorted(n for n, _ in members)
+    back = torch.load(tmp_path / "pytorch_model.bin")
+    assert torch.equal(back["w"], sd["w"])
+    for k, v in sd.items():
+        dt, shape, raw = model_read_tensor(tmp_path, k)
+        assert shape == tuple(v.shape) and raw.tobytes() == _bytes(v), k

@@ -41,7 +41,7 @@ def fake_generate(prompt, n, vocab):
 def serve_fake(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("fake") / "serve_fake")
     src = [os.path.join(ROOT, p) for p in ("host/serve.cpp", "tests/fake_ssb/fake_ssb.cpp", "substratus_b200/csrc/tokenizer.cpp",
-                                           "substratus_b200/csrc/loader.cpp")]
+                                           "substratus_b200/csrc/loader.cpp", "substratus_b200/csrc/torch_zip.cpp")]
     subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wall", "-o", exe] + src, check=True, cwd=os.path.join(ROOT, "host"))
     return exe
 
