@@ -9,6 +9,7 @@
 
 #include "json.h"
 #include "loader.h"
+#include "unicode_tables.h"
 
 namespace ssb {
 namespace {
@@ -77,48 +78,57 @@ bool utf8_valid(const std::string& s) {
   return true;
 }
 
-// ---- Unicode classes of the GPT-2 pattern.  Exact for ASCII, Latin-1 .. Latin Extended, Greek, Cyrillic, Armenian,
-// Hebrew, Arabic letters, Devanagari .. Thai (treated as letters), Hangul, Kana, CJK; symbol / punctuation / number
-// blocks are listed explicitly.  (A full \p{L}/\p{N} table is 30 KB; prompts outside these ranges may split
-// differently from `tokenizers` — documented limitation, the ids still round-trip through decode.)
-bool is_space(uint32_t c) {
-  return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) || c == 0x2028 ||
-         c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
-}
-bool is_number(uint32_t c) {
-  if (c < 0x80) return c >= '0' && c <= '9';
-  return c == 0xB2 || c == 0xB3 || c == 0xB9 || (c >= 0xBC && c <= 0xBE) || (c >= 0x660 && c <= 0x669) || (c >= 0x6F0 && c <= 0x6F9) ||
-         (c >= 0x966 && c <= 0x96F) || (c >= 0x2070 && c <= 0x2079) || (c >= 0x2080 && c <= 0x2089) || (c >= 0x2150 && c <= 0x218B) ||
-         (c >= 0x2460 && c <= 0x249B) || (c >= 0x24EA && c <= 0x24FF) || (c >= 0x2776 && c <= 0x2793) || (c >= 0x3021 && c <= 0x3029) ||
-         (c >= 0xFF10 && c <= 0xFF19);
-}
-bool is_letter(uint32_t c) {
-  if (c < 0x80) return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
-  if (is_space(c) || is_number(c)) return false;
-  if (c < 0xC0) return c == 0xAA || c == 0xB5 || c == 0xBA;
-  if (c == 0xD7 || c == 0xF7) return false;
-  if (c >= 0x2B9 && c <= 0x36F) return (c >= 0x2B9 && c <= 0x2C1) || (c >= 0x2C6 && c <= 0x2D1) || (c >= 0x2E0 && c <= 0x2E4) || c == 0x2EC || c == 0x2EE;
-  if (c == 0x37E || c == 0x387 || c == 0x3F6 || c == 0x482 || (c >= 0x483 && c <= 0x489)) return false;
-  if (c >= 0x55A && c <= 0x55F) return false;
-  if (c >= 0x589 && c <= 0x5CF) return false;
-  if (c >= 0x5F3 && c <= 0x61F) return false;
-  if (c >= 0x64B && c <= 0x66D) return false;
-  if (c >= 0x2000 && c <= 0x2BFF) {  // punctuation, currency, arrows, math, technical, box drawing, dingbats ...
-    return (c == 0x2071 || c == 0x207F || (c >= 0x2090 && c <= 0x209C) || c == 0x2102 || c == 0x2107 || (c >= 0x210A && c <= 0x2113) ||
-            c == 0x2115 || (c >= 0x2119 && c <= 0x211D) || c == 0x2124 || c == 0x2126 || c == 0x2128 || (c >= 0x212A && c <= 0x212D) ||
-            (c >= 0x212F && c <= 0x2139) || (c >= 0x213C && c <= 0x213F) || (c >= 0x2145 && c <= 0x2149) || c == 0x214E || c == 0x2183 ||
-            c == 0x2184);
+// ---- Unicode classes: \\p{L} / \\p{N} / \\s of the GPT-2 pattern, `Punctuation`'s and `Digits`' predicates.  The tables
+// are generated from the behaviour of the HF `tokenizers` library itself (tools/gen_unicode_tables.py), all planes.
+bool in_table(const uint32_t (*t)[2], int n, uint32_t c) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) / 2;
+    if (c < t[mid][0])
+      hi = mid - 1;
+    else if (c > t[mid][1])
+      lo = mid + 1;
+    else
+      return true;
   }
-  if (c >= 0x2E00 && c <= 0x2E7F) return false;
-  if (c >= 0x3000 && c <= 0x303F) return c == 0x3005 || c == 0x3006 || (c >= 0x3031 && c <= 0x3035) || c == 0x303B || c == 0x303C;
-  if (c >= 0x3099 && c <= 0x30A0) return c == 0x309D || c == 0x309E || c == 0x309F;
-  if (c == 0x30FB) return false;
-  if (c >= 0xD800 && c <= 0xF8FF) return false;
-  if (c >= 0xFE00 && c <= 0xFE6F) return false;
-  if (c >= 0xFF00 && c <= 0xFF0F) return false;
-  if ((c >= 0xFF1A && c <= 0xFF20) || (c >= 0xFF3B && c <= 0xFF40) || (c >= 0xFF5B && c <= 0xFF65)) return false;
-  if (c >= 0xFFE0) return c >= 0x10000 && !(c >= 0x1F000 && c <= 0x1FAFF) && !(c >= 0x1D100 && c <= 0x1D1FF);
-  return true;
+  return false;
+}
+bool is_space(uint32_t c) { return c < 0x80 ? (c == ' ' || (c >= 9 && c <= 13)) : in_table(utab::kSpace, utab::kSpaceN, c); }
+bool is_number(uint32_t c) { return c < 0x80 ? (c >= '0' && c <= '9') : in_table(utab::kNumber, utab::kNumberN, c); }
+bool is_letter(uint32_t c) {
+  return c < 0x80 ? ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z')) : in_table(utab::kLetter, utab::kLetterN, c);
+}
+bool is_punct(uint32_t c) { return in_table(utab::kPunct, utab::kPunctN, c); }
+bool is_numeric(uint32_t c) { return c < 0x80 ? (c >= '0' && c <= '9') : in_table(utab::kNumeric, utab::kNumericN, c); }
+
+// split `s` at the characters `pred` selects: every selected char alone (isolated) or runs of them merged (contiguous);
+// the text between is kept; no empty pieces  (tokenizers: NormalizedString::split with SplitDelimiterBehavior)
+template <class Pred>
+void split_chars(const std::string& s, Pred pred, bool contiguous, std::vector<std::string>* out) {
+  size_t start = 0;   // start of the pending non-matching text
+  size_t run = std::string::npos;  // start of the pending run of matches (contiguous only)
+  for (size_t i = 0; i < s.size();) {
+    size_t n;
+    const uint32_t cp = utf8_decode(s, i, &n);
+    if (pred(cp)) {
+      if (run == std::string::npos) {
+        if (i > start) out->push_back(s.substr(start, i - start));
+        run = i;
+      }
+      if (!contiguous) {
+        out->push_back(s.substr(i, n));
+        run = std::string::npos;
+      }
+      start = i + n;
+    } else if (run != std::string::npos) {
+      if (contiguous) out->push_back(s.substr(run, i - run));
+      run = std::string::npos;
+      start = i;
+    }
+    i += n;
+  }
+  if (run != std::string::npos && contiguous) out->push_back(s.substr(run));
+  else if (start < s.size()) out->push_back(s.substr(start));
 }
 
 struct Sym {
@@ -248,12 +258,49 @@ bool Tokenizer::load(const std::string& path, std::string* err) {
       return false;
     }
   } else if (pre && !pre->is_null()) {
-    if (pre->get_str("type", "") != "ByteLevel" || pre->get_num("use_regex", 1) == 0) {
-      *err = "unsupported pre_tokenizer '" + pre->get_str("type", "") + "' (ByteLevel with the GPT-2 pattern only)";
+    // byte-level family: ByteLevel alone (GPT-2 / OPT) or a Sequence around it (Falcon: Punctuation(Contiguous),
+    // ByteLevel, Digits, Split([0-9][0-9][0-9], Isolated)); each stage re-splits the pieces of the previous one
+    std::vector<const Json*> items;
+    if (pre->get_str("type", "") == "Sequence") {
+      if (const Json* ps = pre->find("pretokenizers"))
+        for (auto& q : ps->arr) items.push_back(&q);
+    } else {
+      items.push_back(pre);
+    }
+    int n_bl = 0;
+    for (const Json* q : items) {
+      const std::string t = q->get_str("type", "");
+      PreStage st;
+      if (t == "ByteLevel") {
+        st.kind = PreStage::kByteLevel;
+        st.a = q->get_num("add_prefix_space", 1) != 0;
+        st.b = q->get_num("use_regex", 1) != 0;
+        ++n_bl;
+      } else if (t == "Punctuation" || t == "Digits") {
+        st.kind = t == "Digits" ? PreStage::kDigits : PreStage::kPunct;
+        const std::string beh = q->get_str("behavior", "Isolated");
+        if (t == "Digits")
+          st.a = q->get_num("individual_digits", 0) == 0;  // a = contiguous
+        else if (beh == "Contiguous" || beh == "Isolated")
+          st.a = beh == "Contiguous";
+        else {
+          *err = "unsupported Punctuation behavior '" + beh + "'";
+          return false;
+        }
+      } else if (t == "Split" && q->find("pattern") && q->find("pattern")->get_str("Regex", "") == "[0-9][0-9][0-9]" &&
+                 q->get_str("behavior", "") == "Isolated" && q->get_num("invert", 0) == 0) {
+        st.kind = PreStage::kSplitDigits3;
+      } else {
+        *err = "unsupported pre_tokenizer '" + t + "' (ByteLevel, Punctuation, Digits, Split([0-9][0-9][0-9], Isolated))";
+        return false;
+      }
+      pre_.push_back(st);
+    }
+    if (n_bl != 1) {
+      *err = "unsupported pre_tokenizer (exactly one ByteLevel stage expected)";
       return false;
     }
     byte_level_ = true;
-    add_prefix_space_ = pre->get_num("add_prefix_space", 0) != 0;
   } else {
     *err = "tokenizer has neither a supported normalizer nor a ByteLevel pre_tokenizer";
     return false;
@@ -353,9 +400,54 @@ void Tokenizer::encode_segment(const std::string& text, bool, std::vector<int32_
     bpe_word(w, out);
     return;
   }
-  // GPT-2 family: split with the GPT-2 pattern, map bytes to the printable alphabet, BPE every piece
-  std::string t = text;
-  if (add_prefix_space_ && t[0] != ' ') t = " " + t;
+  // byte-level family: run the pre-tokenizer stages over the growing list of pieces, BPE every final piece
+  std::vector<std::string> pieces{text}, next;
+  for (const PreStage& st : pre_) {
+    next.clear();
+    for (const std::string& pc : pieces) {
+      switch (st.kind) {
+        case PreStage::kByteLevel: {
+          std::string t = pc;
+          if (st.a && t[0] != ' ') t = " " + t;
+          std::vector<std::string> raw;
+          if (st.b)
+            gpt2_split(t, &raw);
+          else
+            raw.push_back(t);
+          for (const std::string& r : raw) {
+            std::string mapped;
+            for (unsigned char ch : r) mapped += byte_to_unicode_[ch];
+            next.push_back(mapped);
+          }
+          break;
+        }
+        case PreStage::kPunct: split_chars(pc, is_punct, st.a, &next); break;
+        case PreStage::kDigits: split_chars(pc, is_numeric, st.a, &next); break;
+        case PreStage::kSplitDigits3: {
+          auto dig = [&](size_t k) { return k < pc.size() && pc[k] >= '0' && pc[k] <= '9'; };
+          size_t start = 0, i = 0;
+          while (i < pc.size()) {
+            if (dig(i) && dig(i + 1) && dig(i + 2)) {
+              if (i > start) next.push_back(pc.substr(start, i - start));
+              next.push_back(pc.substr(i, 3));
+              i += 3;
+              start = i;
+            } else {
+              ++i;
+            }
+          }
+          if (start < pc.size()) next.push_back(pc.substr(start));
+          break;
+        }
+      }
+    }
+    pieces.swap(next);
+  }
+  for (const std::string& pc : pieces) bpe_word(pc, out);
+}
+
+// The GPT-2 pattern over one piece of text (raw bytes out; lookaheads see the end of the piece as end of input).
+void Tokenizer::gpt2_split(const std::string& t, std::vector<std::string>* pieces) {
   std::vector<uint32_t> cps;
   std::vector<size_t> offs;
   for (size_t i = 0; i < t.size();) {
@@ -366,11 +458,7 @@ void Tokenizer::encode_segment(const std::string& text, bool, std::vector<int32_
   }
   offs.push_back(t.size());
   const size_t N = cps.size();
-  auto emit = [&](size_t a, size_t b) {
-    std::string mapped;
-    for (size_t k = offs[a]; k < offs[b]; ++k) mapped += byte_to_unicode_[(unsigned char)t[k]];
-    bpe_word(mapped, out);
-  };
+  auto emit = [&](size_t a, size_t b) { pieces->push_back(t.substr(offs[a], offs[b] - offs[a])); };
   size_t p = 0;
   while (p < N) {
     // 1. contractions

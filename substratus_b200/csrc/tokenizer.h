@@ -6,7 +6,8 @@
 // tokenizer families of the BASELINE configs:
 //   * SentencePiece-style BPE with byte fallback (Llama-2: normalizer Prepend("▁") + Replace(" ", "▁"), no
 //     pre-tokenizer, decoder Replace/ByteFallback/Fuse/Strip), and
-//   * byte-level BPE with the GPT-2 split pattern (OPT-125m; ByteLevel pre-tokenizer + decoder).
+//   * byte-level BPE with the GPT-2 split pattern (OPT-125m; ByteLevel pre-tokenizer + decoder), also inside the
+//     pre-tokenizer Sequence Falcon ships (Punctuation(Contiguous), ByteLevel, Digits, Split([0-9][0-9][0-9])).
 // Anything else (other normalizers / pre-tokenizers) is REFUSED at load time — the host then only accepts token ids —
 // rather than tokenised approximately.  Parity oracle: the `tokenizers` library (tests/test_tokenizer.py).
 #pragma once
@@ -31,6 +32,13 @@ class Tokenizer {
  private:
   void bpe_word(const std::string& word, std::vector<int32_t>* out) const;
   void encode_segment(const std::string& text, bool first_segment, std::vector<int32_t>* out) const;
+  static void gpt2_split(const std::string& text, std::vector<std::string>* pieces);
+  struct PreStage {  // one pre-tokenizer of the byte-level family; each stage re-splits the previous stage's pieces
+    enum Kind { kByteLevel, kPunct, kDigits, kSplitDigits3 } kind = kByteLevel;
+    bool a = false;  // ByteLevel: add_prefix_space; Punctuation / Digits: contiguous (else isolated)
+    bool b = false;  // ByteLevel: use_regex (the GPT-2 pattern)
+  };
+  std::vector<PreStage> pre_;
 
   std::unordered_map<std::string, int32_t> vocab_;
   std::vector<std::string> id_to_token_;
@@ -39,7 +47,6 @@ class Tokenizer {
   std::vector<bool> is_special_;
   std::vector<int32_t> pre_special_, post_special_;                   // TemplateProcessing "single": ids before / after $A
   bool byte_level_ = false;        // GPT-2 byte-level family
-  bool add_prefix_space_ = false;  // ByteLevel.add_prefix_space
   bool sp_prepend_ = false;        // Llama family: Prepend("▁")
   bool byte_fallback_ = false;
   int32_t unk_id_ = -1;
