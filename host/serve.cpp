@@ -148,19 +148,30 @@ static std::string err_json(const std::string& m) { return "{\"error\":\"" + ssb
 struct GenResult {
   std::vector<int32_t> tokens;
   double ttft_ms = 0, decode_ms = 0;
+  bool hit_eos = false;  // stopped at an end-of-sequence id (which is NOT included in tokens)
   std::string error;
 };
 
 // Called with the ids produced since the previous call (first call: the prefill's token).  Returning false stops the
 // generation early (client went away); only honoured where one engine serves the request (the ranks of a TP group must
-// stay in lock-step, so there the request always runs to max_new).
+// stay in lock-step, so there the request runs on regardless of the client).
 using TokenSink = std::function<bool(const int32_t*, int)>;
+
+// index of the first end-of-sequence id in ids[0..n), or n
+static int find_eos(const std::vector<int32_t>& eos, const int32_t* ids, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int32_t e : eos)
+      if (ids[i] == e) return i;
+  return n;
+}
 
 // one rank's share of a request: identical inputs on every rank, identical greedy ids out.  `chunk` = decode steps per
 // ssb_decode call: max_new-1 for a plain request (ONE call, as the bench measures it), params.json "stream_chunk" (1)
-// for "stream": true.
-static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, int chunk, const TokenSink& sink, bool may_stop,
-                    std::vector<int32_t>* toks, double* ttft_ms, double* decode_ms, std::string* error) {
+// for "stream": true, "eos_check_every" (16) when the request stops at EOS.  `eos` (may be empty) is checked after every
+// call on EVERY rank — the ids are identical across ranks, so all ranks stop at the same call.
+static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, int chunk, const std::vector<int32_t>& eos,
+                    const TokenSink& sink, bool may_stop, std::vector<int32_t>* toks, bool* hit_eos, double* ttft_ms, double* decode_ms,
+                    std::string* error) {
   int sid = -1;
   int rc = ssb_seq_create(e, &sid);
   if (rc != SSB_OK) {
@@ -171,20 +182,27 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
   int n = (int)prompt.size();
   int32_t first = 0;
   toks->assign(max_new, 0);
+  *hit_eos = false;
   rc = ssb_prefill(e, &sid, prompt.data(), &n, 1, &first, nullptr);
   auto t1 = std::chrono::steady_clock::now();
   int done = 0;
   if (rc == SSB_OK) {
     (*toks)[0] = first;
-    done = 1;
-    bool go = !sink || sink(&first, 1) || !may_stop;
+    // deliver the ids of one engine call: cut at the first EOS, feed the sink, decide whether to go on
+    auto deliver = [&](int from, int count) {
+      const int keep = find_eos(eos, toks->data() + from, count);
+      done = from + keep;
+      *hit_eos = keep < count;
+      const bool client_ok = !sink || keep == 0 || sink(toks->data() + from, keep);
+      return !*hit_eos && (client_ok || !may_stop);
+    };
+    bool go = deliver(0, 1);
     while (rc == SSB_OK && go && done < max_new) {
       const int steps = std::min(std::max(1, chunk), max_new - done);
       const int32_t last = (*toks)[done - 1];
       rc = ssb_decode(e, &sid, &last, 1, steps, toks->data() + done, nullptr);
       if (rc != SSB_OK) break;
-      done += steps;
-      go = !sink || sink(toks->data() + done - steps, steps) || !may_stop;
+      go = deliver(done, steps);
     }
   }
   auto t2 = std::chrono::steady_clock::now();
@@ -196,17 +214,23 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
   return rc;
 }
 
-static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, int chunk, const TokenSink& sink) {
+static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, int chunk, const std::vector<int32_t>& eos,
+                             const TokenSink& sink) {
   GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
   const size_t n = g_peers.size() + 1;
   std::vector<std::vector<int32_t>> toks(n);
   std::vector<double> ttft(n, 0), dec(n, 0);
   std::vector<std::string> errs(n);
+  std::vector<char> hit(n, 0);
   std::vector<std::thread> th;
   for (size_t i = 1; i < n; ++i)
-    th.emplace_back([&, i] { run_rank(g_peers[i - 1], prompt, max_new, chunk, nullptr, false, &toks[i], &ttft[i], &dec[i], &errs[i]); });
-  run_rank(g_engine, prompt, max_new, chunk, sink, false, &toks[0], &ttft[0], &dec[0], &errs[0]);
+    th.emplace_back([&, i] {
+      bool h = false;
+      run_rank(g_peers[i - 1], prompt, max_new, chunk, eos, nullptr, false, &toks[i], &h, &ttft[i], &dec[i], &errs[i]);
+      hit[i] = h;
+    });
+  run_rank(g_engine, prompt, max_new, chunk, eos, sink, false, &toks[0], &r.hit_eos, &ttft[0], &dec[0], &errs[0]);
   for (auto& t : th) t.join();
   for (size_t i = 0; i < n; ++i) {
     if (!errs[i].empty()) r.error = "rank " + std::to_string(i) + ": " + errs[i];
@@ -218,23 +242,34 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, in
   return r;
 }
 
-static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int chunk = 1 << 30, const TokenSink& sink = nullptr) {
-  if (!g_peers.empty()) return generate_tp(prompt, max_new, chunk, sink);
+static const std::vector<int32_t> kNoEos;
+static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int chunk = 1 << 30, const TokenSink& sink = nullptr,
+                          const std::vector<int32_t>& eos = kNoEos) {
+  if (!g_peers.empty()) return generate_tp(prompt, max_new, chunk, eos, sink);
   GenResult r;
   if (g_sched) {  // concurrent clients share prefill / decode calls; the sink is fed once per scheduler tick
     ssbhost::Request rq;
     rq.prompt = prompt;
     rq.max_new = max_new;
-    rq.on_tokens = sink;
+    size_t kept = 0;  // ids accepted so far (everything before the first EOS)
+    if (sink || !eos.empty())
+      rq.on_tokens = [&](const int32_t* ids, int n) {
+        const int keep = find_eos(eos, ids, n);
+        kept += (size_t)keep;
+        r.hit_eos = keep < n;
+        const bool client_ok = !sink || keep == 0 || sink(ids, keep);
+        return !r.hit_eos && client_ok;
+      };
     g_sched->submit(&rq);
     r.tokens = rq.tokens;
+    if (r.hit_eos) r.tokens.resize(kept);
     r.error = rq.error;
     r.ttft_ms = rq.ttft_ms;
     r.decode_ms = rq.total_ms - rq.ttft_ms;
     return r;
   }
   std::lock_guard<std::mutex> lk(g_engine_mu);
-  run_rank(g_engine, prompt, max_new, chunk, sink, true, &r.tokens, &r.ttft_ms, &r.decode_ms, &r.error);
+  run_rank(g_engine, prompt, max_new, chunk, eos, sink, true, &r.tokens, &r.hit_eos, &r.ttft_ms, &r.decode_ms, &r.error);
   return r;
 }
 
@@ -283,7 +318,16 @@ static size_t utf8_safe_len(const std::string& s) {
 // Basaran's streaming playground); terminated by `data: [DONE]`.  Text is detokenised incrementally: every event carries
 // the new suffix of decode(all ids so far), cut at a UTF-8 boundary, so the concatenation equals the non-streamed text.
 static int g_stream_chunk = 1;
-static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt, int max_new, bool text_mode) {
+// End-of-sequence handling.  The synthetic benchmark request never stops early ("no EOS stop"), so a
+// request stops at EOS only when it says "stop_at_eos": true (or params.json sets "stop_at_eos": 1 as the default).
+// Ids come from params.json "eos_token_id", else <model_dir>/generation_config.json, else config.json (int or list).
+// The EOS id itself is not returned; finish_reason becomes "stop".  Without streaming the ids are checked every
+// "eos_check_every" (16) decode steps, so at most that many steps are computed past the end.
+static std::vector<int32_t> g_eos;
+static bool g_stop_default = false;
+static int g_eos_every = 16;
+static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt, int max_new, bool text_mode,
+                            const std::vector<int32_t>& eos) {
   send_all(fd, "HTTP/1.1 200 OK\r\nContent-Type: text/event-stream\r\nCache-Control: no-cache\r\nConnection: close\r\n\r\n");
   std::vector<int32_t> all;
   size_t emitted = 0;
@@ -318,7 +362,7 @@ static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt
     all.insert(all.end(), ids, ids + n);
     return event(ids, n, next_piece(false), nullptr, "");
   };
-  GenResult r = generate(prompt, max_new, g_stream_chunk, sink);
+  GenResult r = generate(prompt, max_new, g_stream_chunk, sink, eos);
   if (!r.error.empty()) {
     g_errors++;
     send_all(fd, "data: " + err_json(r.error) + "\n\n");
@@ -331,7 +375,7 @@ static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt
     snprintf(tail, sizeof tail,
              ",\"usage\":{\"prompt_tokens\":%zu,\"completion_tokens\":%zu},\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f",
              prompt.size(), r.tokens.size(), r.ttft_ms, r.decode_ms, tps);
-    event(nullptr, 0, next_piece(true), (int)r.tokens.size() >= max_new ? "length" : "cancelled", tail);
+    event(nullptr, 0, next_piece(true), r.hit_eos ? "stop" : (int)r.tokens.size() >= max_new ? "length" : "cancelled", tail);
   }
   send_all(fd, "data: [DONE]\n\n");
 }
@@ -398,7 +442,7 @@ static void handle(int fd) {
       std::string err;
       std::vector<int32_t> prompt;
       int max_new = 16;
-      bool ok = true, text_mode = false, stream = false;
+      bool ok = true, text_mode = false, stream = false, stop_eos = g_stop_default;
       try {
         Json j = ssb::json_parse(body);
         const bool oai = path == "/v1/completions";
@@ -429,6 +473,11 @@ static void handle(int fd) {
         }
         max_new = (int)j.get_int(oai ? "max_tokens" : "max_new_tokens", 16);
         if (const Json* st = j.find("stream")) stream = (st->kind == Json::Bool && st->b) || (st->kind == Json::Num && st->num != 0);
+        if (const Json* st = j.find("stop_at_eos")) stop_eos = (st->kind == Json::Bool && st->b) || (st->kind == Json::Num && st->num != 0);
+        if (ok && stop_eos && g_eos.empty()) {
+          ok = false;
+          err = "stop_at_eos: no eos_token_id in params.json, generation_config.json or config.json";
+        }
         if (ok && (max_new < 1 || (int)prompt.size() + max_new > g_info.max_seq_len)) {
           ok = false;
           err = "prompt length + max tokens exceeds max_seq_len";
@@ -441,9 +490,9 @@ static void handle(int fd) {
         g_errors++;
         respond(fd, 400, "Bad Request", err_json(err));
       } else if (stream) {
-        stream_response(fd, path == "/v1/completions", prompt, max_new, text_mode);
+        stream_response(fd, path == "/v1/completions", prompt, max_new, text_mode, stop_eos ? g_eos : kNoEos);
       } else {
-        GenResult r = generate(prompt, max_new);
+        GenResult r = stop_eos ? generate(prompt, max_new, g_eos_every, nullptr, g_eos) : generate(prompt, max_new);
         if (!r.error.empty()) {
           g_errors++;
           respond(fd, 500, "Internal Server Error", err_json(r.error));
@@ -452,7 +501,7 @@ static void handle(int fd) {
           g_ttft_ms_sum.store(g_ttft_ms_sum.load() + r.ttft_ms);
           g_decode_ms_sum.store(g_decode_ms_sum.load() + r.decode_ms);
           char tail[256];
-          const double tps = r.decode_ms > 0 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
+          const double tps = r.decode_ms > 0 && r.tokens.size() > 1 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
           snprintf(tail, sizeof tail, "\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f", r.ttft_ms, r.decode_ms, tps);
           std::string text;
           if (text_mode && g_tok) {
@@ -462,12 +511,13 @@ static void handle(int fd) {
               text.assign(buf.data(), (size_t)len);
           }
           if (path == "/generate")
-            respond(fd, 200, "OK", "{\"tokens\":" + ids_json(r.tokens) + ",\"text\":\"" + ssb::json_escape(text) + "\"," + tail + "}");
+            respond(fd, 200, "OK", "{\"tokens\":" + ids_json(r.tokens) + ",\"text\":\"" + ssb::json_escape(text) + "\",\"finish_reason\":\"" +
+                                       (r.hit_eos ? "stop" : "length") + "\"," + tail + "}");
           else
             respond(fd, 200, "OK",
                     "{\"object\":\"text_completion\",\"model\":\"" + std::string(g_info.model_type) +
                         "\",\"choices\":[{\"index\":0,\"text\":\"" + ssb::json_escape(text) + "\",\"tokens\":" + ids_json(r.tokens) +
-                        ",\"finish_reason\":\"length\"}],\"usage\":{\"prompt_tokens\":" + std::to_string(prompt.size()) +
+                        ",\"finish_reason\":\"" + (r.hit_eos ? "stop" : "length") + "\"}],\"usage\":{\"prompt_tokens\":" + std::to_string(prompt.size()) +
                         ",\"completion_tokens\":" + std::to_string(r.tokens.size()) + "}," + tail + "}");
         }
       }
@@ -561,6 +611,24 @@ int main(int argc, char** argv) {
     try {
       const Json pj = ssb::json_parse(params);
       g_stream_chunk = std::max(1, (int)pj.get_int("stream_chunk", 1));
+      g_stop_default = pj.get_int("stop_at_eos", 0) != 0;
+      g_eos_every = std::max(1, (int)pj.get_int("eos_check_every", 16));
+      auto take_eos = [](const Json* v) {
+        if (!v) return;
+        if (v->kind == Json::Num) g_eos.push_back((int32_t)v->num);
+        if (v->kind == Json::Arr)
+          for (auto& x : v->arr)
+            if (x.kind == Json::Num) g_eos.push_back((int32_t)x.num);
+      };
+      take_eos(pj.find("eos_token_id"));
+      for (const char* f : {"/generation_config.json", "/config.json"}) {
+        std::string txt;
+        if (!g_eos.empty() || !read_file(model_dir + f, &txt)) continue;
+        try {
+          take_eos(ssb::json_parse(txt).find("eos_token_id"));
+        } catch (std::exception&) {
+        }
+      }
       if (pj.get_int("batching", 0) != 0 && g_peers.empty()) {
         g_abi.e = g_engine;
         g_sched = new ssbhost::BatchScheduler<AbiEngine>(&g_abi, g_info.max_batch, (int)pj.get_int("batch_tick", 8));

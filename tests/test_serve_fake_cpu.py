@@ -261,3 +261,57 @@ def test_stream_client_disconnect_frees_the_engine(serve_fake, tmp_path):
         code, r = _req(s.port, "/generate", {"tokens": [2], "max_new_tokens": 3})
         assert code == 200 and r["tokens"] == fake_generate([2], 3, 1000)
         assert time.time() - t0 < 4.0, "the abandoned stream kept the engine busy"
+
+
+def _prompt_with_eos_at(vocab, eos, lo, hi, n):
+    """a prompt whose greedy continuation first emits `eos` at an index in [lo, hi)"""
+    for a in range(vocab * vocab):
+        prompt = [a // vocab, a % vocab, 3]
+        want = fake_generate(prompt, n, vocab)
+        if eos in want and lo <= want.index(eos) < hi:
+            return prompt, want
+    raise AssertionError("no such prompt")
+
+
+@pytest.mark.parametrize("mode", ["plain", "batching", "tp"])
+def test_stop_at_eos(serve_fake, tmp_path, mode):
+    extra = {"plain": {}, "batching": {"batching": 1, "batch_tick": 5}, "tp": {"tp_size": 2}}[mode]
+    with Server(serve_fake, tmp_path, dict({"fake_vocab": 40, "eos_token_id": [7, 39], "eos_check_every": 4}, **extra)) as s:
+        s.wait_ready()
+        for lo, hi in ((1, 4), (4, 12), (17, 30), (0, 1)):
+            prompt, want = _prompt_with_eos_at(40, 7, lo, hi, 32)
+            k = min(want.index(7), want.index(39) if 39 in want else 99)
+            code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 32})
+            assert code == 200 and r["tokens"] == want and r["finish_reason"] == "length"  # default: the benchmark request never stops
+            code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 32, "stop_at_eos": True})
+            assert code == 200 and r["tokens"] == want[:k] and r["finish_reason"] == "stop", (lo, r, want)
+            code, r = _req(s.port, "/v1/completions", {"prompt": prompt, "max_tokens": 32, "stop_at_eos": True})
+            assert r["choices"][0]["tokens"] == want[:k] and r["choices"][0]["finish_reason"] == "stop"
+            assert r["usage"]["completion_tokens"] == k
+            ev = _sse(s.port, "/v1/completions", {"prompt": prompt, "max_tokens": 32, "stop_at_eos": True, "stream": True})
+            assert sum((e["choices"][0]["tokens"] for e in ev[:-1]), []) == want[:k]
+            assert ev[-2]["choices"][0]["finish_reason"] == "stop" and ev[-1] == "[DONE]"
+        # a request that never meets EOS inside max_tokens ends with "length"
+        prompt, want = _prompt_with_eos_at(40, 7, 20, 32, 32)
+        k = min(want.index(7), want.index(39) if 39 in want else 99)
+        code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": k, "stop_at_eos": True})
+        assert r["tokens"] == want[:k] and r["finish_reason"] == "length"
+
+
+def test_eos_id_comes_from_the_model_dir_and_can_be_the_default(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_vocab": 40}) as s:  # no eos anywhere: asking for it is a client error
+        s.wait_ready()
+        code, r = _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 4, "stop_at_eos": True})
+        assert code == 400 and "eos_token_id" in r["error"]
+
+    def with_config(path):
+        with open(os.path.join(os.path.dirname(path), "config.json"), "w") as f:
+            json.dump({"eos_token_id": 7}, f)
+
+    with Server(serve_fake, tmp_path, {"fake_vocab": 40, "stop_at_eos": 1}, tokenizer=lambda p: with_config(p)) as s:
+        s.wait_ready()
+        prompt, want = _prompt_with_eos_at(40, 7, 3, 20, 32)
+        code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 32})
+        assert r["tokens"] == want[:want.index(7)] and r["finish_reason"] == "stop"
+        code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 32, "stop_at_eos": False})
+        assert r["tokens"] == want
