@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--ref-new-tokens", type=int, default=5)
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--engine-params", default="", help="JSON object merged into the engine's params.json (experiments, e.g. "
+                    "'{\"tp_mega\": 1}'); echoed in config.engine_params so an overridden run is never mistaken for the default")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +254,8 @@ def main():
         json.dump(cfg, f)
     params = {"weights": "synthetic", "seed": 0, "max_batch": max(args.batch, 32), "max_seq_len": PROMPT_LEN + NEW_TOKENS + 16,
               "use_pdl": args.pdl, "use_graph": args.graph, "device": local_rank, "tp_size": world, "tp_rank": rank}
+    extra_params = json.loads(args.engine_params) if args.engine_params else {}
+    params.update(extra_params)
     t_load = time.time()
     eng = Engine(tmp, params)
     if world > 1:
@@ -358,6 +362,8 @@ def main():
         "gpu_launches": launches, "clocks": m["clocks"], "roofline": roofline, "load_s": t_load,
         "hbm_gb": info.hbm_bytes_allocated / 1e9,
     }
+    if extra_params:
+        line["config"]["engine_params"] = extra_params
     if B == 1 and not args.no_batch32:  # the metric is quoted at batch 1 AND 32: same engine, second measurement
         m32 = measure(32, max(2, args.steps // 2), 2)
         line["batch32"] = {"value": m32["value"], "unit": "tokens/s", "e2e": m32["e2e"], "ttft_ms_p50": m32["ttft_ms_p50"],

@@ -511,7 +511,10 @@ int Engine::alloc_runtime(const Json& params) {
     }
   }
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
-  use_mega_ = params.get_int("use_mega", 1) != 0 && tp_size_ == 1 && !cfg_.falcon && !prof_fwd_;
+  // under tensor parallelism the persistent kernel is opt-in ("tp_mega": 1): its in-kernel allreduce (mega.h) was
+  // written after the last multi-GPU session and has not run on hardware yet
+  const bool tp_mega = tp_size_ > 1 && params.get_int("tp_mega", 0) != 0 && D == 128;
+  use_mega_ = params.get_int("use_mega", 1) != 0 && (tp_size_ == 1 || tp_mega) && !cfg_.falcon && !prof_fwd_;
   if (use_mega_) {
     const int group = cfg_.heads / cfg_.kv_heads, ag = mega_attn_group(group);
     const int ch = mega_attn_chunk(D, ag);
@@ -1260,6 +1263,13 @@ int Engine::forward_mega(int B) {
   a.prof = mega_prof_;
   a.n_stages = mega_pick_stages(B == 1 ? 1 : (B == 2 ? 2 : 4), mega_k_max_);
   if (a.n_stages == 0) RET(SSB_EINVAL, "decode step does not fit the persistent kernel's shared memory");
+  if (tp_size_ > 1) {  // "tp_mega": allreduce inside the kernel, same exchange pool / epochs as launch_tp_allreduce_resid
+    a.tp_size = tp_size_;
+    a.tp_rank = tp_rank_;
+    a.peer_partials = d_peer_partials_;
+    a.peer_flags = d_peer_flags_;
+    a.parity_stride = (long long)m_max_ * cfg_.hidden;
+  }
   CK(launch_decode_mega(a, LaunchCfg{stream_, false, n_sm_}));
   launches_per_forward_ = 1;
   timing_.kernel_launches += 1;

@@ -357,7 +357,58 @@ SSB_DEVINL void attention_phase(const MegaArgs& a, const bf16* kcache, const bf1
   }
 }
 
-template <int BT, int D, int G>
+// system-scope accessors for the cross-GPU exchange (same PTX as the allreduce kernel in kernels.cu)
+constexpr int TP_MAX = 8;
+SSB_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+SSB_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SSB_DEVINL float4 ld_relaxed_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------- consumers: allreduce(sum) + residual under tensor
+// parallelism, between two grid barriers (see mega.h).  `seq` = index of this allreduce inside the forward.
+SSB_DEVINL void tp_reduce_phase(const MegaArgs& a, int seq, int tid) {
+  const uint32_t epoch = (uint32_t)ld_acquire_gpu(reinterpret_cast<const unsigned*>(a.fwd_counter)) * (uint32_t)(2 * a.n_layers) +
+                         (uint32_t)seq + 1u;
+  const size_t poff = (size_t)(seq & 1) * (size_t)a.parity_stride;
+  if (blockIdx.x == 0 && tid < a.tp_size && tid != a.tp_rank) {
+    __threadfence_system();  // the partials of ALL local CTAs (observed through the grid barrier) before the flag
+    st_release_sys(a.peer_flags[tid] + a.tp_rank, epoch);
+  }
+  if (tid < a.tp_size && tid != a.tp_rank) {
+    const uint32_t* f = a.peer_flags[a.tp_rank] + tid;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+  named_bar_sync(1, MG_CW * 32);
+  const int total4 = a.M * a.hidden / 4;
+  for (int i = blockIdx.x * (MG_CW * 32) + tid; i < total4; i += gridDim.x * MG_CW * 32) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {  // rank order: every rank computes bit-identical sums
+      if (r < a.tp_size) {
+        const float4 v = ld_relaxed_sys_f4(a.peer_partials[r] + poff + (size_t)i * 4);
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
+      }
+    }
+    const uint2 rv = __ldcg(reinterpret_cast<const uint2*>(a.h) + i);
+    uint2 o;
+    o.x = pack_bf16(bf16r(s.x) + bf_lo(rv.x), bf16r(s.y) + bf_hi(rv.x));
+    o.y = pack_bf16(bf16r(s.z) + bf_lo(rv.y), bf16r(s.w) + bf_hi(rv.y));
+    reinterpret_cast<uint2*>(a.h)[i] = o;
+  }
+}
+
+template <int BT, int D, int G, bool TP = false>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   bf16* tiles = reinterpret_cast<bf16*>(smem_raw);
@@ -455,7 +506,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.resid = a.h;
     g.ld_out = h;
     MG_STAMP();  // 6: x staged
-    consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    if constexpr (TP) {
+      g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l) & 1) * (size_t)a.parity_stride;
+      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      grid_sync(a.grid_bar, n_sync, n_ctas);
+      tp_reduce_phase(a, 2 * l, tid);
+    } else {
+      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    }
     MG_STAMP();  // 7: o consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 8
@@ -478,7 +536,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.resid = a.h;
     g.ld_out = h;
     MG_STAMP();  // 12: x staged
-    consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    if constexpr (TP) {
+      g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l + 1) & 1) * (size_t)a.parity_stride;
+      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      grid_sync(a.grid_bar, n_sync, n_ctas);
+      tp_reduce_phase(a, 2 * l + 1, tid);
+    } else {
+      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    }
     MG_STAMP();  // 13: down consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 14 (= 0 of the next layer)
@@ -552,12 +617,12 @@ int mega_pick_stages(int bt, int k_max) {
   return mega_smem_bytes(bt, k_max, s) <= 225 * 1024 ? s : 0;
 }
 
-template <int BT, int D, int G>
+template <int BT, int D, int G, bool TP = false>
 static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
   const size_t smem = mega_smem_bytes(BT, a.k_max, a.n_stages);
   static unsigned long long attr_mask = 0;  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = {};
@@ -577,12 +642,22 @@ static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, decode_mega_kernel<BT, D, G>, a);
+  return cudaLaunchKernelEx(&cfg, decode_mega_kernel<BT, D, G, TP>, a);
 }
 
 template <int BT>
 static cudaError_t launch_mega_b(const MegaArgs& a, const LaunchCfg& lc) {
   const int g = a.attn_g;
+  if (a.tp_size > 1) {  // tensor-parallel variant: Llama head size only
+    if (a.head_dim != 128 || a.tp_size > TP_MAX || (a.hidden & 3) || !a.peer_partials || !a.peer_flags) return cudaErrorInvalidValue;
+    switch (g) {
+      case 1: return launch_mega_t<BT, 128, 1, true>(a, lc);
+      case 2: return launch_mega_t<BT, 128, 2, true>(a, lc);
+      case 4: return launch_mega_t<BT, 128, 4, true>(a, lc);
+      case 8: return launch_mega_t<BT, 128, 8, true>(a, lc);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (a.head_dim == 128) {
     switch (g) {
       case 1: return launch_mega_t<BT, 128, 1>(a, lc);

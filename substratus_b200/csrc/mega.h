@@ -30,6 +30,17 @@ struct MegaArgs {
   unsigned* grid_bar;  // [2], zero on entry and on exit
   int n_stages, k_max;
   unsigned long long* prof;  // optional [1024] globaltimer stamps of CTA 0 (debug_taps engines only)
+  // ---- tensor parallel (params.json "tp_mega": 1; new fields stay at the END so the single-GPU instantiations keep
+  // their parameter layout).  tp_size > 1 selects decode_mega_kernel<.., TP=true>: the row-parallel projections (o,
+  // down) leave fp32 partials in this rank's exchange buffer and every allreduce is
+  //   grid barrier -> flag to the peers -> wait for the peers' flags -> each CTA pulls ITS slice of [M, hidden] from all
+  //   ranks over NVLink, adds the residual, writes h -> grid barrier
+  // i.e. one extra grid barrier and one NVLink round trip per allreduce, no kernel boundary (same epochs, flags and
+  // parity double-buffering as tp_allreduce_resid_kernel, so prefill through the multi-kernel path interleaves freely).
+  int tp_size, tp_rank;
+  float* const* peer_partials;  // [tp_size] peer-mapped partial buffers [2][rows_max][hidden]
+  uint32_t* const* peer_flags;  // [tp_size] flag arrays [tp_size], living at the receiver
+  long long parity_stride;      // elements between the two parity buffers
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);

@@ -42,9 +42,14 @@ def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
         dist.destroy_process_group()
 
 
+# {"tp_mega": 1}: the persistent decode kernel with its in-kernel allreduce (csrc/mega.h).  Written after the round-1
+# multi-GPU budget was spent, never run on hardware: a cross-GPU spin-wait bug would hang the box, so it only runs when
+# SSB_EXPERIMENTAL=1 is set (tools/r2_tp_mega.sh runs it under a short timeout).
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}])
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1}])
 def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
+    if mode.get("tp_mega") and os.environ.get("SSB_EXPERIMENTAL") != "1":
+        pytest.skip("experimental (set SSB_EXPERIMENTAL=1)")
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     from substratus_b200 import Engine
@@ -55,7 +60,7 @@ def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     gen = torch.Generator().manual_seed(5)
     prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (19, 40)]
     ngen = 6
-    with Engine(str(tmp_path), dict(mode, max_batch=4, max_seq_len=160)) as e:
+    with Engine(str(tmp_path), dict({k: v for k, v in mode.items() if k != "tp_mega"}, max_batch=4, max_seq_len=160)) as e:
         t1, l1 = e.generate(prompts, ngen, want_logits=True)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
