@@ -315,3 +315,23 @@ def test_eos_id_comes_from_the_model_dir_and_can_be_the_default(serve_fake, tmp_
         assert r["tokens"] == want[:want.index(7)] and r["finish_reason"] == "stop"
         code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": 32, "stop_at_eos": False})
         assert r["tokens"] == want
+
+
+def test_sub_infer_client_and_load_generator(serve_fake, tmp_path, capsys):
+    """tools/sub_infer.py (the `sub infer` the reference only stubs, internal/cli/infer.go) against the host: single
+    request, and the SURVEY §8d synthetic load through HTTP with concurrent clients sharing decode calls."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("sub_infer", os.path.join(ROOT, "tools", "sub_infer.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    with Server(serve_fake, tmp_path, {"fake_vocab": 777, "batching": 1, "max_batch": 8, "fake_step_us": 300, "fake_load_ms": 400}) as s:
+        url = f"http://127.0.0.1:{s.port}"
+        assert cli.main(["--url", url, "--wait", "20", "--ids", "5,6,7", "--max-tokens", "6"]) == 0
+        assert capsys.readouterr().out.split() == [str(t) for t in fake_generate([5, 6, 7], 6, 777)]
+        line = cli.bench(url, 12, 6, 777, 64, 20, 60)
+        capsys.readouterr()
+        assert line["failed"] == 0 and line["generated_tokens"] == 12 * 20 and line["ttft_ms_p50"] > 0 and line["tokens_per_sec"] > 0
+        r = cli.stream_completion(url, cli.synthetic_prompt(777, 3, 64), 20)
+        assert r["tokens"] == fake_generate(cli.synthetic_prompt(777, 3, 64), 20, 777) and r["finish_reason"] == "length"
+        assert cli.main(["--url", url, "text prompt without a tokenizer"]) == 1  # the server's 400 is reported, not swallowed
