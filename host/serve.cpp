@@ -32,9 +32,11 @@
 
 #include "../include/ssb.h"
 #include "../substratus_b200/csrc/json.h"
+#include "sampler.h"
 #include "scheduler.h"
 
 using ssb::Json;
+using ssbhost::Sampling;
 
 static std::atomic<int> g_ready{0};  // 0 loading, 1 ready, -1 failed
 static ssb_engine* g_engine = nullptr;
@@ -169,9 +171,12 @@ static int find_eos(const std::vector<int32_t>& eos, const int32_t* ids, int n) 
 // ssb_decode call: max_new-1 for a plain request (ONE call, as the bench measures it), params.json "stream_chunk" (1)
 // for "stream": true, "eos_check_every" (16) when the request stops at EOS.  `eos` (may be empty) is checked after every
 // call on EVERY rank — the ids are identical across ranks, so all ranks stop at the same call.
+// With samp.on() the engine is driven one step per call and the token is drawn on the host from the step's logits
+// (sampler.h); every rank of a TP group draws from bit-identical logits with the same seed.
+static const Sampling kGreedy;
 static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_new, int chunk, const std::vector<int32_t>& eos,
                     const TokenSink& sink, bool may_stop, std::vector<int32_t>* toks, bool* hit_eos, double* ttft_ms, double* decode_ms,
-                    std::string* error) {
+                    std::string* error, const Sampling& samp = kGreedy) {
   int sid = -1;
   int rc = ssb_seq_create(e, &sid);
   if (rc != SSB_OK) {
@@ -183,10 +188,14 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
   int32_t first = 0;
   toks->assign(max_new, 0);
   *hit_eos = false;
-  rc = ssb_prefill(e, &sid, prompt.data(), &n, 1, &first, nullptr);
+  std::vector<float> logits(samp.on() ? (size_t)g_info.vocab_size : 0);
+  std::vector<std::pair<float, int>> cand;
+  ssbhost::Rng rng{samp.seed};
+  rc = ssb_prefill(e, &sid, prompt.data(), &n, 1, &first, samp.on() ? logits.data() : nullptr);
   auto t1 = std::chrono::steady_clock::now();
   int done = 0;
   if (rc == SSB_OK) {
+    if (samp.on()) first = ssbhost::sample_token(logits.data(), g_info.vocab_size, samp, rng, cand);
     (*toks)[0] = first;
     // deliver the ids of one engine call: cut at the first EOS, feed the sink, decide whether to go on
     auto deliver = [&](int from, int count) {
@@ -198,10 +207,11 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
     };
     bool go = deliver(0, 1);
     while (rc == SSB_OK && go && done < max_new) {
-      const int steps = std::min(std::max(1, chunk), max_new - done);
+      const int steps = samp.on() ? 1 : std::min(std::max(1, chunk), max_new - done);
       const int32_t last = (*toks)[done - 1];
-      rc = ssb_decode(e, &sid, &last, 1, steps, toks->data() + done, nullptr);
+      rc = ssb_decode(e, &sid, &last, 1, steps, toks->data() + done, samp.on() ? logits.data() : nullptr);
       if (rc != SSB_OK) break;
+      if (samp.on()) (*toks)[done] = ssbhost::sample_token(logits.data(), g_info.vocab_size, samp, rng, cand);
       go = deliver(done, steps);
     }
   }
@@ -215,7 +225,7 @@ static int run_rank(ssb_engine* e, const std::vector<int32_t>& prompt, int max_n
 }
 
 static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, int chunk, const std::vector<int32_t>& eos,
-                             const TokenSink& sink) {
+                             const TokenSink& sink, const Sampling& samp) {
   GenResult r;
   std::lock_guard<std::mutex> lk(g_engine_mu);
   const size_t n = g_peers.size() + 1;
@@ -227,10 +237,10 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, in
   for (size_t i = 1; i < n; ++i)
     th.emplace_back([&, i] {
       bool h = false;
-      run_rank(g_peers[i - 1], prompt, max_new, chunk, eos, nullptr, false, &toks[i], &h, &ttft[i], &dec[i], &errs[i]);
+      run_rank(g_peers[i - 1], prompt, max_new, chunk, eos, nullptr, false, &toks[i], &h, &ttft[i], &dec[i], &errs[i], samp);
       hit[i] = h;
     });
-  run_rank(g_engine, prompt, max_new, chunk, eos, sink, false, &toks[0], &r.hit_eos, &ttft[0], &dec[0], &errs[0]);
+  run_rank(g_engine, prompt, max_new, chunk, eos, sink, false, &toks[0], &r.hit_eos, &ttft[0], &dec[0], &errs[0], samp);
   for (auto& t : th) t.join();
   for (size_t i = 0; i < n; ++i) {
     if (!errs[i].empty()) r.error = "rank " + std::to_string(i) + ": " + errs[i];
@@ -244,9 +254,13 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, in
 
 static const std::vector<int32_t> kNoEos;
 static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int chunk = 1 << 30, const TokenSink& sink = nullptr,
-                          const std::vector<int32_t>& eos = kNoEos) {
-  if (!g_peers.empty()) return generate_tp(prompt, max_new, chunk, eos, sink);
+                          const std::vector<int32_t>& eos = kNoEos, const Sampling& samp = kGreedy) {
+  if (!g_peers.empty()) return generate_tp(prompt, max_new, chunk, eos, sink, samp);
   GenResult r;
+  if (g_sched && samp.on()) {
+    r.error = "sampling (temperature > 0) is not available while continuous batching is on: the shared decode loop is greedy";
+    return r;
+  }
   if (g_sched) {  // concurrent clients share prefill / decode calls; the sink is fed once per scheduler tick
     ssbhost::Request rq;
     rq.prompt = prompt;
@@ -269,7 +283,7 @@ static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int c
     return r;
   }
   std::lock_guard<std::mutex> lk(g_engine_mu);
-  run_rank(g_engine, prompt, max_new, chunk, eos, sink, true, &r.tokens, &r.hit_eos, &r.ttft_ms, &r.decode_ms, &r.error);
+  run_rank(g_engine, prompt, max_new, chunk, eos, sink, true, &r.tokens, &r.hit_eos, &r.ttft_ms, &r.decode_ms, &r.error, samp);
   return r;
 }
 
@@ -327,7 +341,7 @@ static std::vector<int32_t> g_eos;
 static bool g_stop_default = false;
 static int g_eos_every = 16;
 static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt, int max_new, bool text_mode,
-                            const std::vector<int32_t>& eos) {
+                            const std::vector<int32_t>& eos, const Sampling& samp) {
   send_all(fd, "HTTP/1.1 200 OK\r\nContent-Type: text/event-stream\r\nCache-Control: no-cache\r\nConnection: close\r\n\r\n");
   std::vector<int32_t> all;
   size_t emitted = 0;
@@ -362,7 +376,7 @@ static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt
     all.insert(all.end(), ids, ids + n);
     return event(ids, n, next_piece(false), nullptr, "");
   };
-  GenResult r = generate(prompt, max_new, g_stream_chunk, sink, eos);
+  GenResult r = generate(prompt, max_new, g_stream_chunk, sink, eos, samp);
   if (!r.error.empty()) {
     g_errors++;
     send_all(fd, "data: " + err_json(r.error) + "\n\n");
@@ -443,6 +457,7 @@ static void handle(int fd) {
       std::vector<int32_t> prompt;
       int max_new = 16;
       bool ok = true, text_mode = false, stream = false, stop_eos = g_stop_default;
+      Sampling samp;
       try {
         Json j = ssb::json_parse(body);
         const bool oai = path == "/v1/completions";
@@ -474,6 +489,21 @@ static void handle(int fd) {
         max_new = (int)j.get_int(oai ? "max_tokens" : "max_new_tokens", 16);
         if (const Json* st = j.find("stream")) stream = (st->kind == Json::Bool && st->b) || (st->kind == Json::Num && st->num != 0);
         if (const Json* st = j.find("stop_at_eos")) stop_eos = (st->kind == Json::Bool && st->b) || (st->kind == Json::Num && st->num != 0);
+        samp.temperature = (float)j.get_num("temperature", 0.0);  // 0 (default) = greedy, the engine's device-resident loop
+        samp.top_p = (float)j.get_num("top_p", 1.0);
+        samp.top_k = (int)j.get_int("top_k", 0);
+        if (const Json* sd = j.find("seed"); sd && sd->kind == Json::Num)
+          samp.seed = (uint64_t)sd->num;
+        else
+          samp.seed = (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() ^ ((uint64_t)g_requests.load() << 32);
+        if (ok && (samp.temperature < 0 || !(samp.top_p > 0 && samp.top_p <= 1) || samp.top_k < 0)) {
+          ok = false;
+          err = "temperature must be >= 0, top_p in (0, 1], top_k >= 0";
+        }
+        if (ok && samp.on() && g_sched) {
+          ok = false;
+          err = "sampling (temperature > 0) is not available while continuous batching is on: the shared decode loop is greedy";
+        }
         if (ok && stop_eos && g_eos.empty()) {
           ok = false;
           err = "stop_at_eos: no eos_token_id in params.json, generation_config.json or config.json";
@@ -490,9 +520,10 @@ static void handle(int fd) {
         g_errors++;
         respond(fd, 400, "Bad Request", err_json(err));
       } else if (stream) {
-        stream_response(fd, path == "/v1/completions", prompt, max_new, text_mode, stop_eos ? g_eos : kNoEos);
+        stream_response(fd, path == "/v1/completions", prompt, max_new, text_mode, stop_eos ? g_eos : kNoEos, samp);
       } else {
-        GenResult r = stop_eos ? generate(prompt, max_new, g_eos_every, nullptr, g_eos) : generate(prompt, max_new);
+        GenResult r = (stop_eos || samp.on()) ? generate(prompt, max_new, stop_eos ? g_eos_every : 1 << 30, nullptr, stop_eos ? g_eos : kNoEos, samp)
+                                              : generate(prompt, max_new);
         if (!r.error.empty()) {
           g_errors++;
           respond(fd, 500, "Internal Server Error", err_json(r.error));

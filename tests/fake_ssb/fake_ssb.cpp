@@ -30,6 +30,12 @@ inline uint64_t fold(uint64_t s, int32_t tok) {
 }
 }  // namespace
 
+// fp32 "logits" of the fake model in state s: the greedy id (s % vocab) gets 9, every other id a hash value in [0, 8)
+static void fake_logits(uint64_t s, int vocab, float* out) {
+  for (int v = 0; v < vocab; ++v) out[v] = 8.0f * (float)((fold(s, v) >> 40) & 0xFFFF) / 65536.0f;
+  out[s % (uint64_t)vocab] = 9.0f;
+}
+
 struct ssb_engine {
   int vocab = 1000, max_batch = 32, max_seq_len = 4096, tp_size = 1, tp_rank = 0;
   int step_us = 0, fail_after = -1;  // "fake_step_us": sleep per decode step; "fake_fail_after": decode calls before an error
@@ -103,7 +109,7 @@ int ssb_seq_free(ssb_engine* e, int seq_id) {
   std::lock_guard<std::mutex> lk(e->mu);
   return e->seqs.erase(seq_id) ? SSB_OK : SSB_EINVAL;
 }
-int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float*) {
+int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits) {
   if (!e || !seq_ids || !tokens || !lens || !next_tok || nseq < 1) return SSB_EINVAL;
   if (e->tp_size > 1 && !e->connected) {
     g_err = "tensor-parallel engine used before ssb_tp_connect";
@@ -121,10 +127,11 @@ int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const 
     it->second.second += lens[i];
     off += (size_t)lens[i];
     next_tok[i] = (int32_t)(it->second.first % (uint64_t)e->vocab);
+    if (logits) fake_logits(it->second.first, e->vocab, logits + (size_t)i * e->vocab);
   }
   return SSB_OK;
 }
-int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float*) {
+int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float* logits) {
   if (!e || !seq_ids || !last_tok || !out_tok || nseq < 1 || nsteps < 1) return SSB_EINVAL;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->fail_after >= 0 && e->decode_calls >= e->fail_after) {
@@ -144,6 +151,7 @@ int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int n
       ++it->second.second;
       tok = (int32_t)(it->second.first % (uint64_t)e->vocab);
       out_tok[(size_t)i * nsteps + s] = tok;
+      if (logits) fake_logits(it->second.first, e->vocab, logits + ((size_t)s * nseq + i) * e->vocab);  // [nsteps][nseq][V]
     }
   }
   if (e->step_us > 0) std::this_thread::sleep_for(std::chrono::microseconds((long long)e->step_us * nsteps));

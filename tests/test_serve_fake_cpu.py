@@ -335,3 +335,44 @@ def test_sub_infer_client_and_load_generator(serve_fake, tmp_path, capsys):
         r = cli.stream_completion(url, cli.synthetic_prompt(777, 3, 64), 20)
         assert r["tokens"] == fake_generate(cli.synthetic_prompt(777, 3, 64), 20, 777) and r["finish_reason"] == "length"
         assert cli.main(["--url", url, "text prompt without a tokenizer"]) == 1  # the server's 400 is reported, not swallowed
+
+
+@pytest.mark.parametrize("mode", ["plain", "tp"])
+def test_sampling_is_opt_in_seeded_and_filters_like_hf(serve_fake, tmp_path, mode):
+    """temperature > 0: the host draws each token from the step's logits (host/sampler.h: temperature -> top_k -> top_p,
+    HF order).  The fake model puts ~0.3 of the mass on its greedy id at T = 1 and spreads the rest."""
+    V = 50
+    with Server(serve_fake, tmp_path, dict({"fake_vocab": V}, **({"tp_size": 2} if mode == "tp" else {}))) as s:
+        s.wait_ready()
+        prompt, n = [4, 5, 6], 40
+        greedy = fake_generate(prompt, n, V)
+
+        def gen(**kw):
+            code, r = _req(s.port, "/generate", dict({"tokens": prompt, "max_new_tokens": n}, **kw))
+            assert code == 200, r
+            return r["tokens"]
+
+        assert gen() == greedy and gen(temperature=0) == greedy
+        assert gen(temperature=1.0, top_k=1, seed=1) == greedy           # top_k = 1 leaves only the argmax
+        assert gen(temperature=1.0, top_p=0.05, seed=2) == greedy        # a nucleus smaller than the top token's mass
+        assert gen(temperature=0.05, seed=3) == greedy                   # cold: e^(1/0.05) ratio to the runner-up
+        a, b, c = gen(temperature=1.0, seed=7), gen(temperature=1.0, seed=7), gen(temperature=1.0, seed=8)
+        assert a == b and a != c and a != greedy and len(a) == n          # seeded, and really sampling
+        assert all(0 <= t < V for t in a)
+        # the sampled ids feed back into the model: after the first non-greedy draw the fake's continuation follows it
+        k = next(i for i, (x, y) in enumerate(zip(a, greedy)) if x != y)
+        assert a[:k] == greedy[:k]
+        ev = _sse(s.port, "/v1/completions", {"prompt": prompt, "max_tokens": n, "stream": True, "temperature": 1.0, "seed": 7})
+        assert sum((e["choices"][0]["tokens"] for e in ev[:-1]), []) == a  # same seed, streamed
+        hot = gen(temperature=50.0, seed=5)                               # near-uniform: the greedy id is rarely drawn
+        assert sum(x == y for x, y in zip(hot, fake_generate(prompt, n, V))) < n // 2
+        for bad in ({"temperature": -1}, {"temperature": 1, "top_p": 0}, {"temperature": 1, "top_p": 1.5}, {"temperature": 1, "top_k": -2}):
+            assert _req(s.port, "/generate", dict({"tokens": prompt, "max_new_tokens": 4}, **bad))[0] == 400
+
+
+def test_sampling_is_refused_under_batching(serve_fake, tmp_path):
+    with Server(serve_fake, tmp_path, {"fake_vocab": 50, "batching": 1}) as s:
+        s.wait_ready()
+        code, r = _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 4, "temperature": 0.7})
+        assert code == 400 and "batching" in r["error"]
+        assert _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 4})[0] == 200
