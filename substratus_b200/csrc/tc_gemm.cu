@@ -220,6 +220,9 @@ struct SkWs {
   unsigned* flags;  // [slots], zero on entry and on exit
 };
 
+#ifndef TC_SK_PREFETCH_RING
+#define TC_SK_PREFETCH_RING 0
+#endif
 template <int TN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemvArgs a, const SkWs ws) {
@@ -271,7 +274,30 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool waited = false;
-      for (long long u = u0; u < u1; ++u) {
+      long long ustart = u0;
+#if TC_SK_PREFETCH_RING
+      // compile-time experiment for round 2 (never run on hardware): put the weight tiles of the first ring-full of
+      // units in flight before the dependency wait instead of only the first one, so the HBM stream of this projection
+      // ramps up while the previous kernel drains; the activation tiles follow after the wait on the same barriers.
+      {
+        const long long upre = min(u1, u0 + (long long)Cfg::STAGES);
+        int st = 0;
+        for (long long u = u0; u < upre; ++u, ++st) {  // the ring starts empty: no empty-wait in the first pass
+          mbar_expect_tx(&full[st], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(smem + (size_t)st * Cfg::STAGE_BYTES, &tmA, (int)(u % nkb) * TC_BK, (int)(u / nkb) * TC_BM, &full[st]);
+        }
+        pdl_wait();
+        waited = true;
+        st = 0;
+        for (long long u = u0; u < upre; ++u, ++st)
+          tma_load_2d(smem + (size_t)st * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (int)(u % nkb) * TC_BK, 0, &full[st]);
+        const int n = (int)(upre - u0);
+        stage = n % Cfg::STAGES;
+        phase = n == Cfg::STAGES ? 1u : 0u;
+        ustart = upre;
+      }
+#endif
+      for (long long u = ustart; u < u1; ++u) {
         const int nt = (int)(u / nkb), kb = (int)(u % nkb);
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
