@@ -452,6 +452,15 @@ int Engine::alloc_runtime(const Json& params) {
     tp_off_flags_ = b_part + b_recv;
     tp_off_pflags_ = tp_off_flags_ + 64;
     tp_pool_bytes_ = tp_off_pflags_ + 64;
+    tp_two_shot_ = params.get_int("tp_two_shot", 0) != 0 && !cfg_.falcon;
+    tp_two_shot_min_rows_ = std::max(1, (int)params.get_int("tp_two_shot_min_rows", 64));
+    if (tp_two_shot_) {  // opt-in: the default pool layout (and its size check in tp_connect) is unchanged
+      tp_off_gather_ = tp_pool_bytes_;
+      tp_pool_bytes_ += (size_t)m_max_ * h * sizeof(bf16);
+      TRY(dmalloc(&d_peer_gather_, 8));
+      TRY(dmalloc(&tp2_done_, 1));
+      CK(cudaMemset(tp2_done_, 0, sizeof(unsigned)));
+    }
     TRY(dmalloc(&tp_pool_, tp_pool_bytes_));
     CK(cudaMemset(tp_pool_ + tp_off_flags_, 0, 128));
     tp_partials_ = (float*)tp_pool_;
@@ -720,6 +729,24 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     ta.out = h_;
     ta.variant = 1;  // st.release.sys alone orders the partials before the flag (measured 1.4 us faster than fence + store)
   }
+  // experimental: prefill-sized forwards reduce-scatter + gather bf16 slices instead of pulling every peer's full partial
+  const bool tp_two = tp && tp_two_shot_ && M >= tp_two_shot_min_rows_;
+  TpArgs2 t2 = {};
+  if (tp_two) {
+    t2.rank = tp_rank_;
+    t2.size = tp_size_;
+    t2.peer_partials = d_peer_partials_;
+    t2.peer_flags = d_peer_flags_;
+    t2.peer_gather = d_peer_gather_;
+    t2.tp_step = tp_step_;
+    t2.n_per_step = 2 * cfg_.layers;
+    t2.parity_stride = (long long)m_max_ * h;
+    t2.M = M;
+    t2.hidden = h;
+    t2.resid = h_;
+    t2.out = h_;
+    t2.done = tp2_done_;
+  }
   TpPushArgs tpa = {};
   if (tp_push) {
     tpa.size = tp_size_;
@@ -842,6 +869,10 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     if (tp_push) {
       CK(launch_tp_reduce_push(tpa, lc(true)));
       ++launches;
+    } else if (tp_two) {
+      t2.seq_in_step = 2 * l;
+      CK(launch_tp_allreduce2(t2, lc(true)));
+      ++launches;
     } else if (tp) {
       ta.seq_in_step = 2 * l;
       CK(launch_tp_allreduce_resid(ta, lc(true)));
@@ -889,6 +920,10 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     prof_mark("down");
     if (tp_push) {
       CK(launch_tp_reduce_push(tpa, lc(true)));
+      ++launches;
+    } else if (tp_two) {
+      t2.seq_in_step = 2 * l + 1;
+      CK(launch_tp_allreduce2(t2, lc(true)));
       ++launches;
     } else if (tp) {
       ta.seq_in_step = 2 * l + 1;
@@ -1629,6 +1664,11 @@ int Engine::tp_connect(const void* all, int n) {
   CK(cudaMemcpy(d_peer_flags_, pf.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_peer_recv_, pr.data(), 8 * sizeof(float*), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_peer_pflags_, pq.data(), 8 * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+  if (tp_two_shot_) {
+    std::vector<bf16*> pg(8, nullptr);
+    for (int r = 0; r < n; ++r) pg[r] = (bf16*)(pool[r] + tp_off_gather_);
+    CK(cudaMemcpy(d_peer_gather_, pg.data(), 8 * sizeof(bf16*), cudaMemcpyHostToDevice));
+  }
   tp_connected_ = true;
   return SSB_OK;
 }

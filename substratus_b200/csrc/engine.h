@@ -131,6 +131,12 @@ class Engine {
   unsigned long long** d_peer_pflags_ = nullptr;
   std::vector<void*> ipc_opened_;
   bool tp_connected_ = false, tp_push_ = false;
+  // experimental two-shot prefill allreduce (tp_twoshot.cu): gather region appended to the exchange pool when enabled
+  bool tp_two_shot_ = false;
+  int tp_two_shot_min_rows_ = 64;
+  size_t tp_off_gather_ = 0;
+  bf16** d_peer_gather_ = nullptr;
+  unsigned* tp2_done_ = nullptr;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;

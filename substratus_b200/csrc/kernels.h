@@ -139,6 +139,24 @@ struct TpArgs {
 };
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);
 
+// two-shot allreduce for prefill-sized activations (tp_twoshot.cu; params "tp_two_shot", experimental): each rank
+// reduces its 1/size slice and the bf16 slices are gathered through `peer_gather` (one [rows_max][hidden] bf16 buffer per
+// rank in the exchange pool).  "slice ready" flags are entries [8 + src] of the receiver's flag array.
+struct TpArgs2 {
+  int rank, size;
+  float* const* peer_partials;
+  uint32_t* const* peer_flags;
+  bf16* const* peer_gather;
+  const int* tp_step;
+  int seq_in_step, n_per_step;
+  long long parity_stride;
+  int M, hidden;
+  const bf16* resid;
+  bf16* out;
+  unsigned* done;  // CTA-completion counter (this rank's memory), zero on entry and on exit
+};
+cudaError_t launch_tp_allreduce2(const TpArgs2& a, const LaunchCfg& lc);
+
 // push-model reduce (decode): partials were pushed into recv[parity][src][M][hidden] by the GEMV epilogues of all
 // ranks; wait until every source's arrival counter reached `target`, sum the slots in rank order, add the residual.
 struct TpPushArgs {

@@ -46,9 +46,12 @@ def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
 # multi-GPU budget was spent, never run on hardware: a cross-GPU spin-wait bug would hang the box, so it only runs when
 # SSB_EXPERIMENTAL=1 is set (tools/r2_tp_mega.sh runs it under a short timeout).
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1}])
+# {"tp_two_shot": 1}: reduce-scatter + bf16 gather allreduce for prefill-sized forwards (csrc/tp_twoshot.cu), same status.
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
+                                  {"gemm_path": "tc", "tp_two_shot": 1, "tp_two_shot_min_rows": 16}],
+                         ids=["gemv", "tc", "exp_tp_mega", "exp_two_shot"])
 def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
-    if mode.get("tp_mega") and os.environ.get("SSB_EXPERIMENTAL") != "1":
+    if (mode.get("tp_mega") or mode.get("tp_two_shot")) and os.environ.get("SSB_EXPERIMENTAL") != "1":
         pytest.skip("experimental (set SSB_EXPERIMENTAL=1)")
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -60,7 +63,7 @@ def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     gen = torch.Generator().manual_seed(5)
     prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (19, 40)]
     ngen = 6
-    with Engine(str(tmp_path), dict({k: v for k, v in mode.items() if k != "tp_mega"}, max_batch=4, max_seq_len=160)) as e:
+    with Engine(str(tmp_path), dict({k: v for k, v in mode.items() if not k.startswith("tp_")}, max_batch=4, max_seq_len=160)) as e:
         t1, l1 = e.generate(prompts, ngen, want_logits=True)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
