@@ -41,6 +41,15 @@ WORKLOADS = {
     "llama2-13b": dict(model_type="llama", hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
                        num_attention_heads=40, num_key_value_heads=40, vocab_size=32000, max_position_embeddings=4096,
                        rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
+    # BASELINE config 4 (examples/falcon-40b): new_decoder_architecture, 128 query / 8 KV heads of 64, GELU MLP 4h, parallel block
+    "falcon-40b": dict(model_type="falcon", hidden_size=8192, num_hidden_layers=60, num_attention_heads=128, num_kv_heads=8,
+                       vocab_size=65024, layer_norm_epsilon=1e-5, new_decoder_architecture=True, parallel_attn=True, bias=False,
+                       alibi=False, multi_query=True, rope_theta=10000.0, max_position_embeddings=2048,
+                       tie_word_embeddings=False, torch_dtype="bfloat16"),
+    "tiny-falcon": dict(model_type="falcon", hidden_size=256, num_hidden_layers=6, num_attention_heads=4, num_kv_heads=2,
+                        vocab_size=512, layer_norm_epsilon=1e-5, new_decoder_architecture=True, parallel_attn=True, bias=False,
+                        alibi=False, multi_query=True, rope_theta=10000.0, max_position_embeddings=512,
+                        tie_word_embeddings=False, torch_dtype="bfloat16"),
     "llama2-70b": dict(model_type="llama", hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
                        num_attention_heads=64, num_key_value_heads=8, vocab_size=32000, max_position_embeddings=4096,
                        rms_norm_eps=1e-5, rope_theta=10000.0, tie_word_embeddings=False, torch_dtype="bfloat16"),
@@ -116,15 +125,21 @@ class ClockSampler:
 def _hf_cpu_timed(cfg, layers, prompt_len, new_tokens, batch, dtype):
     """Build a `layers`-deep model at cfg's shapes (random init) and time prefill + greedy decode on the CPU."""
     import torch
-    from transformers import LlamaConfig, LlamaForCausalLM
-    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+    falcon = cfg.get("model_type") == "falcon"
+    if falcon:
+        from transformers import FalconConfig as Config, FalconForCausalLM as Model
+        from transformers.models.falcon.modeling_falcon import FalconRotaryEmbedding as Rotary
+    else:
+        from transformers import LlamaConfig as Config, LlamaForCausalLM as Model
+        from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding as Rotary
 
     keys = {k: v for k, v in cfg.items() if k not in ("model_type", "torch_dtype", "rope_theta")}
     keys["num_hidden_layers"] = layers
-    hcfg = LlamaConfig(**keys, rope_parameters={"rope_type": "default", "rope_theta": cfg.get("rope_theta", 10000.0)},
-                       attn_implementation="eager")
+    hcfg = Config(**keys, rope_parameters={"rope_type": "default", "rope_theta": cfg.get("rope_theta", 10000.0)},
+                  attn_implementation="eager")
     with torch.device("meta"):
-        m = LlamaForCausalLM(hcfg)
+        m = Model(hcfg)
     m = m.to_empty(device="cpu").to(dtype)
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():
@@ -133,7 +148,7 @@ def _hf_cpu_timed(cfg, layers, prompt_len, new_tokens, batch, dtype):
                 p.uniform_(-0.0346, 0.0346, generator=g)
             else:
                 p.fill_(1.0)
-    m.model.rotary_emb = LlamaRotaryEmbedding(hcfg)
+    (m.transformer if falcon else m.model).rotary_emb = Rotary(hcfg)  # to_empty() dropped the inv_freq buffer
     m.eval()
     ids = torch.tensor(synthetic_prompts(cfg["vocab_size"], batch, prompt_len))
     with torch.no_grad():
@@ -333,7 +348,9 @@ def main():
     for k in ("gate_up", "qkv", "down", "o", "lm_head", "attn"):
         ms, by = eng.bench_kernel(k, rows=B, ctx=int(ctx_mean), iters=64)
         kern[k] = {"ms": ms, "bytes": by, "gbs": by / (ms * 1e-3) / 1e9}
-    mega = world == 1 and B <= 4
+    # the persistent kernel serves Llama-family decode at batch <= 4 on one GPU (and under TP only with the experimental
+    # "tp_mega" engine param); Falcon always runs the multi-kernel path
+    mega = B <= 4 and cfg.get("model_type") != "falcon" and (world == 1 or bool(extra_params.get("tp_mega")))
     if mega:
         roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent single-kernel decode step: all projections, attention, pick)",
                     "achieved": m["step_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": m["step_gbs"] / peak_gbs,

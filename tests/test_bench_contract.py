@@ -27,6 +27,14 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_falcon_family():
+    """BASELINE config 4 is a Falcon model: the CPU arm must build that family too (FalconForCausalLM, eager)."""
+    r = _run(["--impl", "reference", "--workload", "tiny-falcon", "--steps", "1", "--warmup", "0", "--ref-prompt-len", "8", "--ref-new-tokens", "3"])
+    assert r.returncode == 0, r.stderr[-800:]
+    d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["value"] > 0 and "tiny-falcon" in d["config"]["workload"]
+
+
 def test_reference_arm_other_ranks_are_silent():
     r = _run(["--impl", "reference", "--workload", "tiny", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
