@@ -381,6 +381,9 @@ def main():
     }
     if extra_params:
         line["config"]["engine_params"] = extra_params
+    from substratus_b200.engine import load_library
+
+    line["engine"] = load_library().ssb_version().decode()  # names the SSB_LIB_VARIANT build, if one was selected
     if B == 1 and not args.no_batch32:  # the metric is quoted at batch 1 AND 32: same engine, second measurement
         m32 = measure(32, max(2, args.steps // 2), 2)
         line["batch32"] = {"value": m32["value"], "unit": "tokens/s", "e2e": m32["e2e"], "ttft_ms_p50": m32["ttft_ms_p50"],

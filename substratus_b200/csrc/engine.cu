@@ -1936,6 +1936,10 @@ int ssb_tok_decode(ssb_tokenizer* t, const int32_t* ids, int n, int skip_special
   return SSB_OK;
 }
 const char* ssb_last_error(void) { return ssb::get_error(); }
+#ifdef SSB_VARIANT
+const char* ssb_version(void) { return "substratus_b200 0.1 (sm_100a) variant=" SSB_VARIANT; }
+#else
 const char* ssb_version(void) { return "substratus_b200 0.1 (sm_100a)"; }
+#endif
 
 }  // extern "C"
