@@ -16,7 +16,10 @@
 #include "kernels.h"
 #include "mega.h"
 
-constexpr int MG_CW = 8;                      // consumer warps
+#ifndef MG_CW_N
+#define MG_CW_N 8  // compile-time experiment (make variants: "cw16"): 16 consumer warps, 64 KiB ring stages
+#endif
+constexpr int MG_CW = MG_CW_N;                // consumer warps
 constexpr int MG_PW = 4;                      // producer warps (one warp issues ~1 bulk copy / 70 cycles: see kernels.cu)
 constexpr int MG_THREADS = (MG_CW + MG_PW) * 32;
 constexpr int MG_ROWS = 2 * MG_CW;
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 }
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages) {
-  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128;
+  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128 + (MG_CW > 8 ? 128 : 0);
 }
 
 int mega_pick_stages(int bt, int k_max) {
