@@ -6,6 +6,28 @@
 #pragma once
 #include "common.cuh"
 
+// GEMV_MIXED_FMA=1 (compile-time experiment, variant library "fhfma"; never run on hardware): sm_100's mixed-precision
+// FMA `fma.rn.f32.bf16` (SASS FHFMA.BF16 with .H0/.H1 operand halves) takes the packed bf16 weights and activations as
+// they sit in the registers, so the 24 shift/mask unpack instructions per 8 weights x 2 rows disappear and the loop is
+// FMAs and shared loads only.  bf16 x bf16 is exact in fp32 and the accumulation order below is the same, so the
+// results are bit-identical to the fmaf path.
+#ifndef GEMV_MIXED_FMA
+#define GEMV_MIXED_FMA 0
+#endif
+// acc += lo(w)*lo(x); acc += hi(w)*hi(x)   (in this order)
+SSB_DEVINL float fma2_bf16(uint32_t w, uint32_t x, float acc) {
+#if GEMV_MIXED_FMA
+  asm("{\n\t.reg .b16 wl, wh, xl, xh;\n\tmov.b32 {wl, wh}, %1;\n\tmov.b32 {xl, xh}, %2;\n\t"
+      "fma.rn.f32.bf16 %0, wl, xl, %0;\n\tfma.rn.f32.bf16 %0, wh, xh, %0;\n\t}"
+      : "+f"(acc)
+      : "r"(w), "r"(x));
+  return acc;
+#else
+  acc = fmaf(bf_lo(w), bf_lo(x), acc);
+  return fmaf(bf_hi(w), bf_hi(x), acc);
+#endif
+}
+
 template <int BT>
 SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__ w1, const bf16* __restrict__ xs, int K, int k0, int len,
                            int lane, float (&acc0)[BT], float (&acc1)[BT]) {
@@ -30,11 +52,16 @@ SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+#if GEMV_MIXED_FMA
+          s0 = fma2_bf16(u0[i], xu[i], s0);
+          s1 = fma2_bf16(u1[i], xu[i], s1);
+#else
           const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
           s0 = fmaf(bf_lo(u0[i]), xl, s0);
           s0 = fmaf(bf_hi(u0[i]), xh, s0);
           s1 = fmaf(bf_lo(u1[i]), xl, s1);
           s1 = fmaf(bf_hi(u1[i]), xh, s1);
+#endif
         }
         p0[it] = s0;
         p1[it] = s1;
@@ -55,11 +82,16 @@ SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+#if GEMV_MIXED_FMA
+          s0 = fma2_bf16(u0[i], xu[i], s0);
+          s1 = fma2_bf16(u1[i], xu[i], s1);
+#else
           const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
           s0 = fmaf(bf_lo(u0[i]), xl, s0);
           s0 = fmaf(bf_hi(u0[i]), xh, s0);
           s1 = fmaf(bf_lo(u1[i]), xl, s1);
           s1 = fmaf(bf_hi(u1[i]), xh, s1);
+#endif
         }
         acc0[b] += s0;
         acc1[b] += s1;
