@@ -14,8 +14,10 @@ llama_ref.write_hf_dir(d, cfg, synth.llama_state_dict(cfg, 21))
 g = torch.Generator().manual_seed(3)
 res = {}
 for name, prompts in (("b1", [torch.randint(0, cfg["vocab_size"], (37,), generator=g).tolist()]),
-                      ("b3", [torch.randint(0, cfg["vocab_size"], (n,), generator=g).tolist() for n in (5, 18, 64)])):
-    with Engine(d, {"max_batch": 4, "max_seq_len": 160}) as e:
+                      ("b3", [torch.randint(0, cfg["vocab_size"], (n,), generator=g).tolist() for n in (5, 18, 64)]),
+                      # 12 rows: tensor-core stream-K decode projections (tc_min_rows = 8) and the split-context attention kernels
+                      ("b12", [torch.randint(0, cfg["vocab_size"], (n,), generator=g).tolist() for n in range(3, 39, 3)])):
+    with Engine(d, {"max_batch": 16, "max_seq_len": 160}) as e:
         toks, lg = e.generate(prompts, 12, want_logits=True)
     res[name + "_toks"], res[name + "_logits"] = toks, lg
 np.savez(out, **res)

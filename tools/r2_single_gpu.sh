@@ -1,23 +1,28 @@
 #!/bin/bash
 # Round-2 runbook, ONE GPU: first hardware run of everything DESIGN.md section 9 lists for a single device.
-#   (here, free)   make -C substratus_b200/csrc variants        # builds lib/libsubstratus_b200.{fhfma,fhfma12,synclight,cw12,skprefetch}.so
+#   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,cw12,skprefetch}.so
 #   gpurun --timeout 1500 -- 'bash tools/r2_single_gpu.sh'
-# Every step has its own timeout; results land in gpurun_out/r2_single_*.{log,jsonl}.
+# Every step has its own timeout; results land in gpurun_out/r2_single_*.{log,jsonl,npz}.
+# None of the variants changes arithmetic or summation order, so each must reproduce the default library's logits
+# BIT FOR BIT (tools/dump_logits.py at batch 1 / 3 / 12 -> tools/ab_bitexact.py); only then is it benchmarked.
 set -u
 mkdir -p gpurun_out
+rm -f gpurun_out/r2_single_bench.jsonl
 echo "== 1. full GPU suite on the default library (includes the tests written after the round-1 GPU budget ran out)"
 timeout -k 20 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/r2_single_suite.log
+echo "== 2. default library: reference logits, bench lines at batch 1 (+32)"
 timeout -k 20 200 python tools/dump_logits.py gpurun_out/r2_logits_default.npz 2>&1 | tail -1
-echo "== 2. default bench line"
-timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/r2_single_bench.jsonl
-for V in fhfma fhfma12 synclight cw12 skprefetch; do
+timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
+# variant : extra bench flags (mega-kernel variants only matter at batch <= 4; skprefetch only at batch >= 8)
+for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "synclight:--no-batch32" "skprefetch:--batch 32"; do
+  V=${SPEC%%:*}; FLAGS=${SPEC#*:}
   [ -f substratus_b200/lib/libsubstratus_b200.$V.so ] || { echo "variant $V not built (make -C substratus_b200/csrc variants)"; continue; }
-  echo "== 3. variant $V: parity subset, then the same bench line"
-  SSB_LIB_VARIANT=$V timeout -k 20 400 python -m pytest tests/test_parity_gpu.py -x -q 2>&1 | tail -3 | tee gpurun_out/r2_single_parity_$V.log
+  echo "== 3. variant $V"
   SSB_LIB_VARIANT=$V timeout -k 20 200 python tools/dump_logits.py gpurun_out/r2_logits_$V.npz 2>&1 | tail -1
-  python tools/ab_bitexact.py gpurun_out/r2_logits_default.npz gpurun_out/r2_logits_$V.npz 2>&1 | tee gpurun_out/r2_single_bitexact_$V.log
-  if grep -q "passed" gpurun_out/r2_single_parity_$V.log && ! grep -q "failed" gpurun_out/r2_single_parity_$V.log; then
-    SSB_LIB_VARIANT=$V timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
+  if python tools/ab_bitexact.py gpurun_out/r2_logits_default.npz gpurun_out/r2_logits_$V.npz 2>&1 | tee gpurun_out/r2_single_bitexact_$V.log | tail -6; then
+    SSB_LIB_VARIANT=$V timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline $FLAGS 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
+  else
+    echo "variant $V is NOT bit-identical to the default library: not benchmarked"
   fi
 done
 python - <<'PY'
@@ -28,5 +33,6 @@ for ln in open("gpurun_out/r2_single_bench.jsonl"):
     except ValueError:
         continue
     b32 = d.get("batch32", {})
-    print(f'{d.get("engine", "?"):55s} B=1 {d["value"]:8.1f} tok/s (frac {d["roofline"]["frac"]:.3f})  B=32 {b32.get("value", 0):8.1f}  TTFT {d["ttft_ms_p50"]:.1f} ms')
+    print(f'{d.get("engine", "?"):58s} B={d["config"]["batch"]:<3d} {d["value"]:9.1f} tok/s  frac {d["roofline"]["decode_step"]["frac"]:.3f}  '
+          f'batch32 {b32.get("value", 0):8.1f}  TTFT {d["ttft_ms_p50"]:.1f} ms')
 PY
