@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round-2 runbook, ONE GPU: first hardware run of everything DESIGN.md section 9 lists for a single device.
+#   (here, free)   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/ubench_fma tools/ubench_fma.cu
 #   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,cw12,skprefetch}.so
 #   gpurun --timeout 1500 -- 'bash tools/r2_single_gpu.sh'
 # Every step has its own timeout; results land in gpurun_out/r2_single_*.{log,jsonl,npz}.
@@ -11,6 +12,8 @@ mkdir -p gpurun_out
 rm -f gpurun_out/r2_single_bench.jsonl
 echo "== 1. full GPU suite on the default library (includes the tests written after the round-1 GPU budget ran out)"
 timeout -k 20 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/r2_single_suite.log
+echo "== 1b. FFMA vs FHFMA.BF16 issue rate (reads the fhfma experiment)"
+[ -x tools/bin/ubench_fma ] && timeout -k 5 60 tools/bin/ubench_fma 2>&1 | tee gpurun_out/r2_ubench_fma.log
 echo "== 2. default library: reference logits, bench lines at batch 1 (+32)"
 timeout -k 20 200 python tools/dump_logits.py gpurun_out/r2_logits_default.npz 2>&1 | tail -1
 timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
