@@ -62,12 +62,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// TC_SK_SMEM_BUDGET (compile-time experiment, variant library "sk2cta": 104 KiB + TC_SK_PREFETCH_RING): shared-memory
+// budget of the ring for the decode-sized tiles (TN <= 64).  At ~100 KiB two CTAs fit on an SM, so under PDL the CTAs of
+// the NEXT projection become resident while this one is still in its mainloop / epilogue, set up their barriers and TMEM
+// and put their first weight tiles in flight; 5 x 20 KiB per CTA still covers the per-SM HBM latency-bandwidth product.
+#ifndef TC_SK_SMEM_BUDGET
+#define TC_SK_SMEM_BUDGET (200 * 1024)
+#endif
 template <int TN>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;                       // 16 KiB
   static constexpr int B_BYTES = TN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BUDGET = TN <= 64 ? TC_SK_SMEM_BUDGET : 200 * 1024;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * TN <= 32) ? 32 : (2 * TN <= 64) ? 64 : (2 * TN <= 128) ? 128 : (2 * TN <= 256) ? 256 : 512;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 runbook, ONE GPU: first hardware run of everything DESIGN.md section 9 lists for a single device.
 #   (here, free)   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/ubench_fma tools/ubench_fma.cu
-#   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,cw12,skprefetch}.so
+#   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,cw12,skprefetch,sk2cta}.so
 #   gpurun --timeout 1500 -- 'bash tools/r2_single_gpu.sh'
 # Every step has its own timeout; results land in gpurun_out/r2_single_*.{log,jsonl,npz}.
 # fhfma / synclight / skprefetch change neither arithmetic nor summation order, so they must reproduce the default
@@ -18,7 +18,7 @@ echo "== 2. default library: reference logits, bench lines at batch 1 (+32)"
 timeout -k 20 200 python tools/dump_logits.py gpurun_out/r2_logits_default.npz 2>&1 | tail -1
 timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
 # variant : extra bench flags (mega-kernel variants only matter at batch <= 4; skprefetch only at batch >= 8)
-for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "synclight:--no-batch32" "skprefetch:--batch 32"; do
+for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "synclight:--no-batch32" "skprefetch:--batch 32" "sk2cta:--batch 32"; do
   V=${SPEC%%:*}; FLAGS=${SPEC#*:}
   [ -f substratus_b200/lib/libsubstratus_b200.$V.so ] || { echo "variant $V not built (make -C substratus_b200/csrc variants)"; continue; }
   echo "== 3. variant $V"
