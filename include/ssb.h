@@ -65,7 +65,13 @@ typedef struct ssb_timing {
  *   "max_batch" (32), "max_seq_len" (config's), "kv_block_size" (16), "kv_blocks" (auto),
  *   "weights": "file" | "synthetic" (seeded hash weights at config.json's shapes; "seed"),
  *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank), "allreduce": "p2p" | "nccl",
- *   "use_pdl" (1), "use_graph" (1).
+ *   "use_pdl" (1), "use_graph" (1), "use_mega" (1: persistent single-kernel decode step at batch <= 4),
+ *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (8), "tc_streamk" (1), "prefill_chunk" (1024),
+ *   experimental, off by default, never run on hardware yet: "tp_mega" (persistent kernel under
+ *   tensor parallelism with an in-kernel allreduce), "tp_two_shot" / "tp_two_shot_min_rows" (reduce-scatter + gather
+ *   allreduce for prefill-sized forwards), "tp_push" (push-model allreduce, measured slower).
+ * Keys the engine does not know are ignored (the serve host keeps its own keys in the same file: "batching",
+ * "batch_tick", "stream_chunk", "stop_at_eos", "eos_token_id", "eos_check_every").
  * With tp_size > 1 the engine is usable only after ssb_tp_connect(). */
 int ssb_engine_create(const char* model_dir, const char* params_json, ssb_engine** out);
 void ssb_engine_destroy(ssb_engine* e);
