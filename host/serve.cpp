@@ -39,6 +39,16 @@ using ssb::Json;
 using ssbhost::Sampling;
 
 static std::atomic<int> g_ready{0};  // 0 loading, 1 ready, -1 failed
+// SIGTERM (pod deletion / rollout): stop accepting, answer the readiness probe with 503 so the Service drops the pod,
+// let the requests in flight finish, exit 0 — inside the default 30 s terminationGracePeriodSeconds of the Deployment
+// the reconciler creates (server_controller.go:122-178 sets none, so the Kubernetes default applies).
+static std::atomic<bool> g_draining{false};
+static std::atomic<int> g_inflight{0};
+static int g_listen_fd = -1;
+static void on_sigterm(int) {
+  g_draining = true;
+  if (g_listen_fd >= 0) shutdown(g_listen_fd, SHUT_RD);  // wakes accept(); async-signal-safe
+}
 static ssb_engine* g_engine = nullptr;
 static ssb_info g_info;
 static std::mutex g_engine_mu;  // ssb_* calls on one engine are not re-entrant
@@ -394,7 +404,13 @@ static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt
   send_all(fd, "data: [DONE]\n\n");
 }
 
+struct InflightGuard {
+  InflightGuard() { ++g_inflight; }
+  ~InflightGuard() { --g_inflight; }
+};
+
 static void handle(int fd) {
+  InflightGuard guard;
   std::string req;
   char buf[8192];
   size_t hdr_end = std::string::npos;
@@ -434,8 +450,10 @@ static void handle(int fd) {
 
   if (method == "GET" && (path == "/" || path == "/healthz" || path == "/readyz")) {
     // readiness: 200 only when weights are on the device and the engine answered ssb_engine_info
-    const int st = g_ready.load();
-    if (st == 1)
+    const int st = g_draining.load() ? 2 : g_ready.load();
+    if (st == 2)
+      respond(fd, 503, "Service Unavailable", "{\"status\":\"draining\"}");
+    else if (st == 1)
       respond(fd, 200, "OK", "{\"status\":\"ready\",\"engine\":\"" + std::string(ssb_version()) + "\",\"model_type\":\"" +
                                  std::string(g_info.model_type) + "\"}");
     else
@@ -562,6 +580,7 @@ static void handle(int fd) {
 
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
+  signal(SIGTERM, on_sigterm);
   const std::string model_dir = (argc > 1 && argv[1][0] != '-') ? argv[1] : getenv_or("MODEL_DIR", "/content/model");
   const std::string params_file = getenv_or("PARAMS_FILE", "/content/params.json");
   const int port = atoi(getenv_or("PORT", "8080").c_str());
@@ -677,12 +696,22 @@ int main(int argc, char** argv) {
   });
   loader.detach();
 
+  g_listen_fd = ls;
   for (;;) {
     int fd = accept(ls, nullptr, nullptr);
+    if (g_draining.load()) {
+      if (fd >= 0) close(fd);
+      break;
+    }
     if (fd < 0) continue;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
     timeval snd{10, 0};  // a stalled streaming client must not hold the engine (or the batch scheduler) for ever
     setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &snd, sizeof snd);
     std::thread(handle, fd).detach();
   }
+  close(ls);
+  fprintf(stderr, "serve: SIGTERM, draining %d request(s)\n", g_inflight.load());
+  for (int i = 0; i < 250 && g_inflight.load() > 0; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  fprintf(stderr, "serve: exit\n");
+  _exit(0);  // engine teardown is the process exit: the device context goes with it
 }

@@ -376,3 +376,27 @@ def test_sampling_is_refused_under_batching(serve_fake, tmp_path):
         code, r = _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 4, "temperature": 0.7})
         assert code == 400 and "batching" in r["error"]
         assert _req(s.port, "/generate", {"tokens": [1], "max_new_tokens": 4})[0] == 200
+
+
+def test_sigterm_drains_in_flight_requests_then_exits_zero(serve_fake, tmp_path):
+    """Pod deletion: SIGTERM -> no new connections, the request in flight completes, exit code 0 (no restart-loop noise)."""
+    import signal
+    import threading
+
+    with Server(serve_fake, tmp_path, {"fake_step_us": 3000}) as s:
+        s.wait_ready()
+        out = {}
+
+        def long_request():
+            out["r"] = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 400}, timeout=60)  # ~1.2 s of decode
+
+        t = threading.Thread(target=long_request)
+        t.start()
+        time.sleep(0.3)
+        s.p.send_signal(signal.SIGTERM)
+        t.join(timeout=30)
+        assert out["r"][0] == 200 and out["r"][1]["tokens"] == fake_generate([1, 2], 400, 1000)
+        assert s.p.wait(timeout=30) == 0
+        assert "draining" in s.p.stderr.read()
+        with pytest.raises((urllib.error.URLError, ConnectionError)):
+            _req(s.port, "/")
