@@ -388,14 +388,16 @@ def test_sigterm_drains_in_flight_requests_then_exits_zero(serve_fake, tmp_path)
         out = {}
 
         def long_request():
-            out["r"] = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 400}, timeout=60)  # ~1.2 s of decode
+            out["r"] = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 600}, timeout=60)  # ~1.8 s of decode
 
         t = threading.Thread(target=long_request)
         t.start()
-        time.sleep(0.3)
+        deadline = time.time() + 10
+        while "ssb_requests_total 1" not in _req(s.port, "/metrics")[1] and time.time() < deadline:  # the request is in the engine
+            time.sleep(0.02)
         s.p.send_signal(signal.SIGTERM)
         t.join(timeout=30)
-        assert out["r"][0] == 200 and out["r"][1]["tokens"] == fake_generate([1, 2], 400, 1000)
+        assert out["r"][0] == 200 and out["r"][1]["tokens"] == fake_generate([1, 2], 600, 1000)
         assert s.p.wait(timeout=30) == 0
         assert "draining" in s.p.stderr.read()
         with pytest.raises((urllib.error.URLError, ConnectionError)):
