@@ -67,6 +67,7 @@ typedef struct ssb_timing {
  *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank), "allreduce": "p2p" | "nccl",
  *   "use_pdl" (1), "use_graph" (1), "use_mega" (1: persistent single-kernel decode step at batch <= 4),
  *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (8), "tc_streamk" (1), "prefill_chunk" (1024),
+ *   "attn_splits" (0 = heuristic; context splits of the decode attention kernels, a sweep knob),
  *   experimental, off by default, never run on hardware yet: "tp_mega" (persistent kernel under
  *   tensor parallelism with an in-kernel allreduce), "tp_two_shot" / "tp_two_shot_min_rows" (reduce-scatter + gather
  *   allreduce for prefill-sized forwards), "tp_push" (push-model allreduce, measured slower).

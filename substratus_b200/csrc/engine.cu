@@ -399,6 +399,7 @@ std::string Engine::prof_report() {
 int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
+  if (attn_splits_ > 0) return std::min(attn_splits_, gc >= 4 ? 16 : 32);  // params "attn_splits": sweep knob, 0 = heuristic
   const int ctas = M * (Hl_ / gc);
   int s = ((gc >= 4 ? 2 : 4) * n_sm_ + ctas - 1) / ctas;
   return std::max(1, std::min(s, gc >= 4 ? 16 : 32));
@@ -412,6 +413,7 @@ int Engine::alloc_runtime(const Json& params) {
   if (max_batch_ < 1 || max_seq_ < 1 || (block_size_ != 8 && block_size_ != 16 && block_size_ != 32 && block_size_ != 64))
     RET(SSB_EINVAL, "bad max_batch / max_seq_len / kv_block_size (8|16|32|64)");
   max_blocks_per_seq_ = (max_seq_ + block_size_ - 1) / block_size_;
+  attn_splits_ = (int)params.get_int("attn_splits", 0);
   m_max_ = std::max(max_batch_, (int)params.get_int("prefill_chunk", 1024));
   max_steps_ = max_seq_;
   // rope table

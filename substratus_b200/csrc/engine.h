@@ -162,6 +162,7 @@ class Engine {
   // stats
   mutable ssb_timing timing_ = {};
   int decode_splits_(int M) const;
+  int attn_splits_ = 0;
 };
 
 void set_error(const std::string& s);
