@@ -13,3 +13,12 @@ def test_batch_scheduler_with_fake_engine(tmp_path):
                    check=True, cwd=os.path.join(ROOT, "host"))
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "SCHEDULER TEST OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_host_sampler_draws_from_the_filtered_softmax(tmp_path):
+    """host/sampler.h (opt-in sampling of the serve host): chi-square against the exact temperature/top_k/top_p distribution."""
+    exe = str(tmp_path / "test_sampler")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "host", "test_sampler.cpp")], check=True,
+                   cwd=os.path.join(ROOT, "host"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "SAMPLER TEST OK" in r.stdout, r.stdout + r.stderr
