@@ -549,8 +549,8 @@ int Engine::alloc_runtime(const Json& params) {
         TRY(dmalloc(&mega_prof_, 1024));
         CK(cudaMemset(mega_prof_, 0, 1024 * sizeof(unsigned long long)));
       }
-      TRY(dmalloc(&mega_bar_, 2));
-      CK(cudaMemset(mega_bar_, 0, 2 * sizeof(unsigned)));
+      TRY(dmalloc(&mega_bar_, 1024));  // [0] barrier counter, [1] exit counter, [32 + 32 g] group counters of the tree-barrier experiment
+      CK(cudaMemset(mega_bar_, 0, 1024 * sizeof(unsigned)));
     }
   }
   return SSB_OK;
