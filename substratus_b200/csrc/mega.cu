@@ -108,9 +108,72 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
   named_bar_sync(1, MG_CW * 32);
 }
 
+// MG_L2_AHEAD=N (compile-time experiment, variant library "l2ahead"; never run on hardware): the shared-memory ring holds
+// 192 KiB = 4.3 us of this SM's HBM share, but the gap QKV -> barrier -> attention -> barrier -> x staging is ~16 us, so
+// HBM idles for most of it.  With N > 0 every producer warp walks the SAME weight stream a second time, N ring fills
+// ahead of its copies, issuing `cp.async.bulk.prefetch.L2` for the rows it will copy later: while the ring is full the
+// next N x 32 KiB per SM (N = 10: 47 MB chip-wide, L2 is 126 MB) keep streaming HBM -> L2, and the later bulk copies
+// hit L2, which an SM can drain at twice its HBM share.  Prefetches change no result (bit-identity gate applies).
+#ifndef MG_L2_AHEAD
+#define MG_L2_AHEAD 0
+#endif
+SSB_DEVINL void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+// the weight stream of one CTA in producer order: per layer wqkv, wo, wgu, wdown; then lm_head.  step() = one ring fill.
+struct Ahead {
+  int idx = -1;  // matrix index in stream order: 4 * layer + {0 wqkv, 1 wo, 2 wgu, 3 wdown}; 4 * n_layers = lm_head
+  const bf16* W = nullptr;
+  int K = 0, ps = 0, p1 = 0, kc = 0, nk = 0;
+  bool live = true;
+  SSB_DEVINL void open_next(const MegaArgs& a) {  // advance to the next matrix in which this CTA owns rows
+    for (;;) {
+      ++idx;
+      if (idx > 4 * a.n_layers) {
+        live = false;
+        return;
+      }
+      int N;
+      if (idx == 4 * a.n_layers) {
+        W = a.lm_head;
+        N = a.vocab;
+        K = a.hidden;
+      } else {
+        const MegaLayer& w = a.layers[idx >> 2];
+        const int m = idx & 3;
+        W = m == 0 ? w.wqkv : m == 1 ? w.wo : m == 2 ? w.wgu : w.wdown;
+        N = m == 0 ? a.q_rows + 2 * a.kv_rows : m == 2 ? 2 * a.inter : a.hidden;
+        K = m == 1 ? a.q_rows : m == 3 ? a.inter : a.hidden;
+      }
+      const int P = N >> 1;
+      ps = (int)(((long long)blockIdx.x * P) / gridDim.x);
+      p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+      nk = (K + MG_KC - 1) / MG_KC;
+      kc = 0;
+      if (ps < p1) return;
+    }
+  }
+  SSB_DEVINL void step(const MegaArgs& a, int lane, int pw) {  // prefetch one ring fill, move on
+    if (live && idx < 0) open_next(a);
+    if (!live) return;
+    constexpr int RPP = MG_ROWS / MG_PW;
+    const int nr = 2 * min(MG_CW, p1 - ps);
+    const int r0 = pw * RPP;
+    const int mine = max(0, min(RPP, nr - r0));
+    const int k0 = kc * MG_KC;
+    const int len = min(MG_KC, K - k0);
+    if (lane < mine) prefetch_l2_bulk(W + (size_t)(2 * ps + r0 + lane) * K + k0, (uint32_t)(len * 2));
+    if (++kc == nk) {
+      kc = 0;
+      ps += MG_CW;
+      if (ps >= p1) open_next(a);
+    }
+  }
+};
+
 // ---------------------------------------------------------------- producer: stream this CTA's rows of one matrix
 SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        uint64_t pol, int lane, int pw) {
+                        uint64_t pol, int lane, int pw, [[maybe_unused]] const MegaArgs& ma, [[maybe_unused]] Ahead& ah) {
   const int P = N >> 1;
   const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
   const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
@@ -120,6 +183,9 @@ SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full
     for (int kc = 0; kc < nk; ++kc) {
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
+#if MG_L2_AHEAD > 0
+      ah.step(ma, lane, pw);  // keep the L2 prefetch cursor MG_L2_AHEAD fills ahead of this copy
+#endif
       mbar_wait(&empty[r.stage], r.phase ^ 1);
       constexpr int RPP = MG_ROWS / MG_PW;
       const int r0 = pw * RPP;
@@ -482,14 +548,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     // ================================================================ producers: every weight byte of the step, in order
     const uint64_t pol = policy_evict_first();
     const int pw = warp - MG_CW;
+    Ahead ah;
+#if MG_L2_AHEAD > 0
+    for (int i = 0; i < MG_L2_AHEAD; ++i) ah.step(a, lane, pw);
+#endif
     for (int l = 0; l < a.n_layers; ++l) {
       const MegaLayer& w = a.layers[l];
-      produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
-      produce(w.wo, h, a.q_rows, tiles, full, empty, a.n_stages, r, pol, lane, pw);
-      produce(w.wgu, 2 * a.inter, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
-      produce(w.wdown, h, a.inter, tiles, full, empty, a.n_stages, r, pol, lane, pw);
+      produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
+      produce(w.wo, h, a.q_rows, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
+      produce(w.wgu, 2 * a.inter, h, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
+      produce(w.wdown, h, a.inter, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
     }
-    produce(a.lm_head, a.vocab, h, tiles, full, empty, a.n_stages, r, pol, lane, pw);
+    produce(a.lm_head, a.vocab, h, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
     return;
   }
 
