@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 runbook, ONE GPU: first hardware run of everything DESIGN.md section 9 lists for a single device.
 #   (here, free)   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/ubench_fma tools/ubench_fma.cu
-#   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,synctree,l2ahead,combo,combo2,cw12,skprefetch,sk2cta}.so
+#   (here, free)   make -C substratus_b200/csrc variants   # lib/libsubstratus_b200.{fhfma,fhfma12,synclight,synctree,l2ahead,combo,combo2,cw12,skprefetch,sk2cta,attnlite}.so
 #   gpurun --timeout 1500 -- 'bash tools/r2_single_gpu.sh'
 # Every step has its own timeout; results land in gpurun_out/r2_single_*.{log,jsonl,npz}.
 # fhfma / synclight / skprefetch change neither arithmetic nor summation order, so they must reproduce the default
@@ -23,7 +23,7 @@ echo "       so if the consumers were the limit the @l2 numbers of the fhfma bui
 timeout -k 20 200 python tools/kbench.py '{"use_mega": 0}' 1 2>&1 | tee gpurun_out/r2_kbench_default.log
 [ -f substratus_b200/lib/libsubstratus_b200.fhfma.so ] && SSB_LIB_VARIANT=fhfma timeout -k 20 200 python tools/kbench.py '{"use_mega": 0}' 1 2>&1 | tee gpurun_out/r2_kbench_fhfma.log
 # variant : extra bench flags (mega-kernel variants only matter at batch <= 4; skprefetch only at batch >= 8)
-for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "synclight:--no-batch32" "synctree:--no-batch32" "l2ahead:--no-batch32" "combo:--no-batch32" "combo2:--no-batch32" "skprefetch:--batch 32" "sk2cta:--batch 32"; do
+for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "synclight:--no-batch32" "synctree:--no-batch32" "l2ahead:--no-batch32" "combo:--no-batch32" "combo2:--no-batch32" "skprefetch:--batch 32" "sk2cta:--batch 32" "attnlite:--batch 32"; do
   V=${SPEC%%:*}; FLAGS=${SPEC#*:}
   [ -f substratus_b200/lib/libsubstratus_b200.$V.so ] || { echo "variant $V not built (make -C substratus_b200/csrc variants)"; continue; }
   echo "== 3. variant $V"
