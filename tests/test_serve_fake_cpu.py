@@ -39,6 +39,8 @@ def fake_generate(prompt, n, vocab):
 
 @pytest.fixture(scope="module")
 def serve_fake(tmp_path_factory):
+    if os.environ.get("SERVE_FAKE_EXE"):  # e.g. an -fsanitize=address,undefined build of the same sources
+        return os.environ["SERVE_FAKE_EXE"]
     exe = str(tmp_path_factory.mktemp("fake") / "serve_fake")
     src = [os.path.join(ROOT, p) for p in ("host/serve.cpp", "tests/fake_ssb/fake_ssb.cpp", "substratus_b200/csrc/tokenizer.cpp",
                                            "substratus_b200/csrc/loader.cpp", "substratus_b200/csrc/torch_zip.cpp")]
