@@ -250,7 +250,11 @@ bool ModelFiles::open_gguf(const std::string& path, std::string* err) {
     Info in;
     in.name = c.str();
     uint32_t nd = c.rd<uint32_t>();
-    for (uint32_t d = 0; d < nd; ++d) in.dims.push_back((int64_t)c.rd<uint64_t>());
+    if (nd > 8) {  // GGML_MAX_DIMS is 4: a larger count is a corrupt header, not a reason to loop 2^32 times
+      c.ok = false;
+      break;
+    }
+    for (uint32_t d = 0; d < nd && c.ok; ++d) in.dims.push_back((int64_t)c.rd<uint64_t>());
     in.type = c.rd<uint32_t>();
     in.off = c.rd<uint64_t>();
     infos.push_back(std::move(in));
@@ -259,16 +263,34 @@ bool ModelFiles::open_gguf(const std::string& path, std::string* err) {
     *err = path + ": truncated GGUF header";
     return false;
   }
-  const uint64_t align = (uint64_t)gguf_meta_.get_num("general.alignment", 32);
+  const double align_d = gguf_meta_.get_num("general.alignment", 32);
+  if (!(align_d >= 1 && align_d <= 65536)) {
+    *err = path + ": bad general.alignment";
+    return false;
+  }
+  const uint64_t align = (uint64_t)align_d;
   uint64_t pos = (uint64_t)(c.p - f->data());
   pos = (pos + align - 1) / align * align;
+  if (pos > f->size()) {
+    *err = path + ": truncated GGUF header";
+    return false;
+  }
   const uint8_t* base = f->data() + pos;
+  const uint64_t avail = f->size() - pos;
   for (auto& in : infos) {
     TensorView v;
     v.name = in.name;
     v.shape.assign(in.dims.rbegin(), in.dims.rend());  // GGUF stores the fastest dim first
     int64_t n = 1;
-    for (auto d : in.dims) n *= d;
+    bool sane = true;
+    for (auto d : in.dims) {  // corrupt dims must not overflow the byte count below
+      if (d < 0 || d > (int64_t)1 << 40 || (d > 0 && n > ((int64_t)1 << 48) / d)) sane = false;
+      if (sane) n *= d;
+    }
+    if (!sane) {
+      *err = path + ": tensor " + in.name + " has impossible dimensions";
+      return false;
+    }
     switch (in.type) {
       case 0: v.dtype = DT_F32; v.nbytes = (size_t)n * 4; break;
       case 1: v.dtype = DT_F16; v.nbytes = (size_t)n * 2; break;
@@ -279,7 +301,7 @@ bool ModelFiles::open_gguf(const std::string& path, std::string* err) {
       case 14: v.dtype = DT_Q6_K; v.nbytes = (size_t)(n / 256) * 210; break;
       default: v.dtype = DT_OTHER; v.nbytes = 0;
     }
-    if (pos + in.off + v.nbytes > f->size()) {
+    if (in.off > avail || v.nbytes > avail - in.off) {
       *err = path + ": tensor " + in.name + " out of range";
       return false;
     }

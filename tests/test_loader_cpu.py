@@ -4,6 +4,7 @@ with a precise error on any box; a complete artifact then fails with SSB_ENODEV 
 import json
 import os
 import struct
+import time
 
 import pytest
 import torch
@@ -289,3 +290,78 @@ def test_torch_bin_zip64_directory(tmp_path, lib):
     for k, v in sd.items():
         dt, shape, raw = model_read_tensor(tmp_path, k)
         assert shape == tuple(v.shape) and raw.tobytes() == _bytes(v), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Corrupt artifacts must end in a clean error, never in a crash, a hang or an out-of-bounds read: seeded mutation
+# fuzz of the three container readers through ssb_model_read_tensor (a GGUF header with a dimension count of 2^32-1
+# used to spin for minutes — found by this fuzz).
+def _mutations(raw, rng, n):
+    for _ in range(n):
+        m = bytearray(raw)
+        for _ in range(rng.randint(1, 6)):
+            if len(m) < 2:
+                break
+            k, pos = rng.random(), rng.randrange(len(m))
+            if k < 0.5:
+                m[pos] = rng.randrange(256)
+            elif k < 0.7:
+                del m[pos:pos + rng.randint(1, 16)]
+            elif k < 0.9:
+                m[pos:pos] = bytes(rng.randrange(256) for _ in range(rng.randint(1, 16)))
+            else:
+                del m[rng.randrange(1, len(m)):]
+        yield bytes(m)
+
+
+@pytest.mark.parametrize("kind", ["safetensors", "torch_bin", "gguf"])
+def test_corrupt_containers_fail_cleanly(tmp_path, lib, kind):
+    import ctypes as C
+    import random
+
+    import numpy as np
+    from safetensors.torch import save_file
+
+    from substratus_b200 import load_library
+
+    sd = {"a.weight": torch.arange(64, dtype=torch.bfloat16).view(8, 8), "b": torch.ones(5, dtype=torch.float32)}
+    if kind == "safetensors":
+        path = tmp_path / "model.safetensors"
+        save_file(sd, str(path))
+        names = [b"a.weight", b"b", None]
+    elif kind == "torch_bin":
+        path = tmp_path / "pytorch_model.bin"
+        torch.save(sd, path)
+        names = [b"a.weight", b"b", None]
+    else:
+        gguf = pytest.importorskip("gguf")
+        path = tmp_path / "model.gguf"
+        w = gguf.GGUFWriter(str(path), "llama")
+        w.add_block_count(1)
+        w.add_embedding_length(32)
+        w.add_token_list(["a", "b", "c"])
+        w.add_tensor("token_embd.weight", np.arange(96, dtype=np.float32).reshape(3, 32))
+        w.add_tensor("blk.0.attn_q.weight", np.ones((32, 32), dtype=np.float16))
+        w.write_header_to_file()
+        w.write_kv_data_to_file()
+        w.write_tensors_to_file()
+        w.close()
+        names = [b"token_embd.weight", b"blk.0.attn_q.weight", None]
+    raw = path.read_bytes()
+    L = load_library()
+    n, dt, nd = C.c_int64(), C.c_int(), C.c_int()
+    shape = (C.c_int64 * 4)()
+    out = (C.c_uint8 * 8192)()
+    d = str(tmp_path).encode()
+    assert all(L.ssb_model_read_tensor(d, nm, out, 8192, C.byref(n), C.byref(dt), shape, C.byref(nd)) == 0 for nm in names)
+    cases = list(_mutations(raw, random.Random(11), 500))
+    if kind == "gguf":  # the regression: tensor-info dimension count 0xFFFFFFFF
+        i = raw.index(b"token_embd.weight") + len(b"token_embd.weight")
+        cases.append(raw[:i] + b"\xff\xff\xff\xff" + raw[i + 4:])
+    t0 = time.time()
+    for m in cases:
+        path.write_bytes(m)
+        for nm in names:
+            rc = L.ssb_model_read_tensor(d, nm, out, 8192, C.byref(n), C.byref(dt), shape, C.byref(nd))
+            assert rc in (0, -1, -2, -4), rc  # OK or EINVAL / EIO / ENOMEM, and we are still alive
+    assert time.time() - t0 < 60
