@@ -77,7 +77,17 @@ class JsonParser {
     while (s[n]) ++n;
     return n;
   }
+  // nesting guard: params.json comes from the user's CRD (.spec.params) and request bodies from the network; a few
+  // hundred thousand '[' must end in an error, not in a stack overflow of this recursive descent
+  int depth_ = 0;
+  struct Depth {
+    int& d;
+    explicit Depth(int& x) : d(x) { ++d; }
+    ~Depth() { --d; }
+  };
   Json value() {
+    Depth guard(depth_);
+    if (depth_ > 128) fail("nesting too deep");
     ws();
     if (p_ >= e_) fail("unexpected end");
     Json j;

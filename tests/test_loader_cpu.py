@@ -365,3 +365,16 @@ def test_corrupt_containers_fail_cleanly(tmp_path, lib, kind):
             rc = L.ssb_model_read_tensor(d, nm, out, 8192, C.byref(n), C.byref(dt), shape, C.byref(nd))
             assert rc in (0, -1, -2, -4), rc  # OK or EINVAL / EIO / ENOMEM, and we are still alive
     assert time.time() - t0 < 60
+
+
+def test_pathological_json_is_an_error_not_a_crash(tmp_path, lib):
+    """params.json is user input (.spec.params): 200 000 nested brackets used to overflow the parser's stack."""
+    import ctypes as C
+
+    from substratus_b200 import load_library
+
+    L = load_library()
+    for payload in (b"[" * 200000, b'{"a":' * 100000, b'"' + b"\\" * 100001, b"1e999999", b'{"a":1,}', b"\xff\xfe"):
+        h = C.c_void_p()
+        assert L.ssb_engine_create(str(tmp_path).encode(), payload, C.byref(h)) == EINVAL
+        assert b"json" in L.ssb_last_error() or b"params" in L.ssb_last_error()

@@ -404,3 +404,43 @@ def test_sigterm_drains_in_flight_requests_then_exits_zero(serve_fake, tmp_path)
         assert "draining" in s.p.stderr.read()
         with pytest.raises((urllib.error.URLError, ConnectionError)):
             _req(s.port, "/")
+
+
+def test_malformed_requests_do_not_take_the_server_down(serve_fake, tmp_path):
+    """Garbage on the wire (the Service is reachable by anything in the cluster) gets an error or a closed connection;
+    the server keeps serving.  Includes a body nested 200 000 levels deep (the JSON parser has a nesting guard)."""
+    import random
+
+    with Server(serve_fake, tmp_path, {"fake_vocab": 100}) as s:
+        s.wait_ready()
+        rng = random.Random(9)
+        good = json.dumps({"tokens": [1, 2], "max_new_tokens": 3}).encode()
+        payloads = [
+            b"", b"\r\n\r\n", b"GET", b"GET / HTTP/1.1", b"POST /generate HTTP/1.1\r\nContent-Length: -5\r\n\r\n{}",
+            b"POST /generate HTTP/1.1\r\nContent-Length: 99999999999999999999\r\n\r\n{}",
+            b"POST /generate HTTP/1.1\r\nContent-Length: 10\r\n\r\n{}",  # shorter body than announced, then close
+            b"POST /generate HTTP/1.1\r\nContent-Length: 200000\r\n\r\n" + b"[" * 200000,
+            b"POST /generate HTTP/1.1\r\nContent-Length: 9\r\n\r\n{\"a\":\xff\xfe}",
+            b"POST /v1/completions HTTP/1.1\r\nContent-Length: 2\r\n\r\n[]",
+            b"\x00" * 5000, b"A" * 70000 + b"\r\n\r\n", b"POST  HTTP/1.1\r\n\r\n", b"POST /generate\r\n\r\n",
+        ]
+        for _ in range(60):
+            m = bytearray(b"POST /generate HTTP/1.1\r\nContent-Length: %d\r\n\r\n" % len(good) + good)
+            for _ in range(rng.randint(1, 5)):
+                m[rng.randrange(len(m))] = rng.randrange(256)
+            payloads.append(bytes(m))
+        for pl in payloads:
+            c = socket.create_connection(("127.0.0.1", s.port), timeout=10)
+            try:
+                c.sendall(pl)
+                c.shutdown(socket.SHUT_WR)
+                c.settimeout(10)
+                while c.recv(65536):
+                    pass
+            except OSError:
+                pass
+            finally:
+                c.close()
+            assert s.p.poll() is None, (pl[:60], s.p.stderr.read()[-400:])
+        code, r = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 3})
+        assert code == 200 and r["tokens"] == fake_generate([1, 2], 3, 100)
