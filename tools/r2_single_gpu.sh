@@ -44,6 +44,10 @@ for SPEC in "fhfma:--no-batch32" "fhfma12:--no-batch32" "cw12:--no-batch32" "syn
     echo "variant $V failed its gate: not benchmarked"
   fi
 done
+echo "== 4. batch-32 decode attention: context-split sweep on the default library (heuristic gives 1 split at 32 x 32 heads)"
+for S in 2 4; do
+  timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --batch 32 --engine-params "{\"attn_splits\": $S}" 2>&1 | tail -1 | tee -a gpurun_out/r2_single_bench.jsonl
+done
 python - <<'PY'
 import json
 for ln in open("gpurun_out/r2_single_bench.jsonl"):
@@ -52,6 +56,6 @@ for ln in open("gpurun_out/r2_single_bench.jsonl"):
     except ValueError:
         continue
     b32 = d.get("batch32", {})
-    print(f'{d.get("engine", "?"):58s} B={d["config"]["batch"]:<3d} {d["value"]:9.1f} tok/s  frac {d["roofline"]["decode_step"]["frac"]:.3f}  '
+    print(f'{d.get("engine", "?") + " " + json.dumps(d["config"].get("engine_params", {})):70s} B={d["config"]["batch"]:<3d} {d["value"]:9.1f} tok/s  frac {d["roofline"]["decode_step"]["frac"]:.3f}  '
           f'batch32 {b32.get("value", 0):8.1f}  TTFT {d["ttft_ms_p50"]:.1f} ms')
 PY
