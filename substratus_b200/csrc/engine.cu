@@ -463,7 +463,14 @@ int Engine::alloc_runtime(const Json& params) {
       TRY(dmalloc(&tp2_done_, 1));
       CK(cudaMemset(tp2_done_, 0, sizeof(unsigned)));
     }
+    tp_mega_mode_ = D == 128 && !cfg_.falcon ? (int)params.get_int("tp_mega", 0) : 0;
+    if (tp_mega_mode_ == 2) {
+      tp_off_ctaflags_ = tp_pool_bytes_;
+      tp_pool_bytes_ += 8 * 256 * sizeof(uint32_t);
+      TRY(dmalloc(&d_peer_cta_flags_, 8));
+    }
     TRY(dmalloc(&tp_pool_, tp_pool_bytes_));
+    if (tp_mega_mode_ == 2) CK(cudaMemset(tp_pool_ + tp_off_ctaflags_, 0, 8 * 256 * sizeof(uint32_t)));
     CK(cudaMemset(tp_pool_ + tp_off_flags_, 0, 128));
     tp_partials_ = (float*)tp_pool_;
     tp_recv_ = (float*)(tp_pool_ + tp_off_recv_);
@@ -1306,6 +1313,8 @@ int Engine::forward_mega(int B) {
     a.peer_partials = d_peer_partials_;
     a.peer_flags = d_peer_flags_;
     a.parity_stride = (long long)m_max_ * cfg_.hidden;
+    a.tp_mode = tp_mega_mode_ == 2 ? 2 : 1;
+    a.peer_cta_flags = d_peer_cta_flags_;
   }
   CK(launch_decode_mega(a, LaunchCfg{stream_, false, n_sm_}));
   launches_per_forward_ = 1;
@@ -1666,6 +1675,11 @@ int Engine::tp_connect(const void* all, int n) {
   CK(cudaMemcpy(d_peer_flags_, pf.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_peer_recv_, pr.data(), 8 * sizeof(float*), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_peer_pflags_, pq.data(), 8 * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+  if (tp_mega_mode_ == 2) {
+    std::vector<uint32_t*> pc(8, nullptr);
+    for (int r = 0; r < n; ++r) pc[r] = (uint32_t*)(pool[r] + tp_off_ctaflags_);
+    CK(cudaMemcpy(d_peer_cta_flags_, pc.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  }
   if (tp_two_shot_) {
     std::vector<bf16*> pg(8, nullptr);
     for (int r = 0; r < n; ++r) pg[r] = (bf16*)(pool[r] + tp_off_gather_);

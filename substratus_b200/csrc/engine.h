@@ -137,6 +137,10 @@ class Engine {
   size_t tp_off_gather_ = 0;
   bf16** d_peer_gather_ = nullptr;
   unsigned* tp2_done_ = nullptr;
+  // "tp_mega": 2 — per-CTA exchange flags [8][256] u32, appended to the exchange pool when enabled
+  int tp_mega_mode_ = 0;
+  size_t tp_off_ctaflags_ = 0;
+  uint32_t** d_peer_cta_flags_ = nullptr;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;

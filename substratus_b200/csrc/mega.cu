@@ -522,6 +522,51 @@ SSB_DEVINL void tp_reduce_phase(const MegaArgs& a, int seq, int tid) {
   }
 }
 
+SSB_DEVINL float2 ld_relaxed_sys_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// "tp_mega": 2 (mega.h): exchange between the CTAs with the same index on every rank, called right after the row-parallel
+// projection WITHOUT a grid barrier in between.  Buffer reuse: this CTA rewrites its range of the parity buffer two
+// allreduces later, after it received the peers' CTA-c flag of the allreduce in between, which they store only after
+// their loads of this one have returned (program order + release).
+constexpr int MG_CTA_FLAG_STRIDE = 256;
+SSB_DEVINL void tp_reduce_cta(const MegaArgs& a, int seq, int tid) {
+  const uint32_t epoch = (uint32_t)ld_acquire_gpu(reinterpret_cast<const unsigned*>(a.fwd_counter)) * (uint32_t)(2 * a.n_layers) +
+                         (uint32_t)seq + 1u;
+  const size_t poff = (size_t)(seq & 1) * (size_t)a.parity_stride;
+  named_bar_sync(1, MG_CW * 32);  // every consumer warp of this CTA has stored its partial pairs
+  if (tid < a.tp_size && tid != a.tp_rank) {
+    __threadfence_system();
+    st_release_sys(a.peer_cta_flags[tid] + (size_t)a.tp_rank * MG_CTA_FLAG_STRIDE + blockIdx.x, epoch);
+    const uint32_t* f = a.peer_cta_flags[a.tp_rank] + (size_t)tid * MG_CTA_FLAG_STRIDE + blockIdx.x;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+  named_bar_sync(1, MG_CW * 32);
+  const int P = a.hidden >> 1;
+  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  const int np = p1 - p0;
+  for (int i = tid; i < a.M * np; i += MG_CW * 32) {
+    const int m = i / np, p = p0 + (i - m * np);
+    const size_t o = (size_t)m * a.hidden + 2 * (size_t)p;
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {  // rank order, own partial included: bit-identical sums on every rank
+      if (r < a.tp_size) {
+        const float2 v = ld_relaxed_sys_f2(a.peer_partials[r] + poff + o);
+        s.x += v.x;
+        s.y += v.y;
+      }
+    }
+    const uint32_t rv = __ldcg(reinterpret_cast<const uint32_t*>(a.h + o));
+    *reinterpret_cast<uint32_t*>(a.h + o) = pack_bf16(bf16r(s.x) + bf_lo(rv), bf16r(s.y) + bf_hi(rv));
+  }
+}
+
 template <int BT, int D, int G, bool TP = false>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -627,8 +672,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l) & 1) * (size_t)a.parity_stride;
       consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
-      grid_sync(a.grid_bar, n_sync, n_ctas);
-      tp_reduce_phase(a, 2 * l, tid);
+      if (a.tp_mode == 2) {
+        tp_reduce_cta(a, 2 * l, tid);
+      } else {
+        grid_sync(a.grid_bar, n_sync, n_ctas);
+        tp_reduce_phase(a, 2 * l, tid);
+      }
     } else {
       consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
     }
@@ -657,8 +706,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l + 1) & 1) * (size_t)a.parity_stride;
       consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
-      grid_sync(a.grid_bar, n_sync, n_ctas);
-      tp_reduce_phase(a, 2 * l + 1, tid);
+      if (a.tp_mode == 2) {
+        tp_reduce_cta(a, 2 * l + 1, tid);
+      } else {
+        grid_sync(a.grid_bar, n_sync, n_ctas);
+        tp_reduce_phase(a, 2 * l + 1, tid);
+      }
     } else {
       consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
     }
@@ -771,6 +824,7 @@ static cudaError_t launch_mega_b(const MegaArgs& a, const LaunchCfg& lc) {
   const int g = a.attn_g;
   if (a.tp_size > 1) {  // tensor-parallel variant: Llama head size only
     if (a.head_dim != 128 || a.tp_size > TP_MAX || (a.hidden & 3) || !a.peer_partials || !a.peer_flags) return cudaErrorInvalidValue;
+    if (a.tp_mode == 2 && (!a.peer_cta_flags || lc.n_sm > MG_CTA_FLAG_STRIDE)) return cudaErrorInvalidValue;
     switch (g) {
       case 1: return launch_mega_t<BT, 128, 1, true>(a, lc);
       case 2: return launch_mega_t<BT, 128, 2, true>(a, lc);

@@ -41,6 +41,13 @@ struct MegaArgs {
   float* const* peer_partials;  // [tp_size] peer-mapped partial buffers [2][rows_max][hidden]
   uint32_t* const* peer_flags;  // [tp_size] flag arrays [tp_size], living at the receiver
   long long parity_stride;      // elements between the two parity buffers
+  // "tp_mega": 2 — per-CTA exchange instead of a grid-wide one: CTA c of every rank produces the SAME output range of the
+  // row-parallel projection (same grid, same dims), so it only needs the partials of the peers' CTA c.  It flags them
+  // (flag [src rank][cta] at the receiver), waits for theirs, pulls their range, adds its own partial and the residual and
+  // writes its range of h; the phase then ends with the ordinary grid barrier.  One grid barrier less per allreduce than
+  // mode 1 and no GPU-wide skew wait.
+  int tp_mode;                       // 1 | 2
+  uint32_t* const* peer_cta_flags;   // [tp_size] -> u32 [8][256] at each receiver
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);
