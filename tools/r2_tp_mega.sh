@@ -12,8 +12,11 @@ N=${1:-2}
 WL=${2:-llama2-7b}
 mkdir -p gpurun_out
 echo "== 1. parity: tp_mega and the two-shot prefill allreduce vs TP1 and the oracle (tiny model, $N GPUs)"
-SSB_EXPERIMENTAL=1 timeout -k 20 300 python -m pytest tests/test_tp_gpu.py -x -q -k "exp_" 2>&1 | tail -15 | tee gpurun_out/r2_tp_mega_parity.log
-if ! grep -q "passed" gpurun_out/r2_tp_mega_parity.log; then echo "parity not green: stop here"; exit 1; fi
+SSB_EXPERIMENTAL=1 timeout -k 20 420 python -m pytest tests/test_tp_gpu.py -q -k "exp_" 2>&1 | tail -15 | tee gpurun_out/r2_tp_mega_parity.log
+# no -x: every experimental mode reports on its own; a mode that failed is then left out of the A/B runs below by hand
+if ! grep -q "passed" gpurun_out/r2_tp_mega_parity.log || grep -q "failed\|error" gpurun_out/r2_tp_mega_parity.log; then
+  echo "parity not (all) green: fix or drop the failing mode before benchmarking"; exit 1
+fi
 echo "== 2. decode tokens/s, default TP path vs tp_mega ($WL, TP$N)"
 for P in '{}' '{"tp_mega": 1}' '{"tp_mega": 2}' '{"tp_two_shot": 1}' '{"tp_mega": 2, "tp_two_shot": 1}'; do
   timeout -k 20 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
