@@ -47,3 +47,85 @@ def test_gpu_arm_refuses_without_a_gpu():
         pytest.skip("GPU present")
     r = _run(["--workload", "tiny", "--steps", "1", "--warmup", "0"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_gpu_arm_control_flow_against_a_mock_engine(monkeypatch, capsys):
+    """bench.py's GPU arm end to end on CPU with a mock Engine (control flow and JSON contract, not numbers): the keys the
+    driver reads, the TTFT top-up to >= 20 samples, a failing batch-32 sub-measurement that must not lose
+    the headline line, --engine-params echoed in config."""
+    import importlib
+    import time
+
+    import numpy as np
+
+    import substratus_b200
+
+    class Timing:
+        prefill_ms, decode_ms, kernel_launches, h2d_bytes, d2h_bytes = 1.0, 2.0, 129, 4096, 512
+
+    class Info:
+        weight_bytes_per_step, kv_bytes_per_token, hbm_bytes_allocated, hidden_size = 13.2e9, 524288, 14e9, 4096
+
+    class MockEngine:
+        def __init__(self, model_dir, params):
+            self.info, self.params, self.n = Info(), params, 0
+
+        def seq_create(self):
+            self.n += 1
+            return self.n
+
+        def seq_free(self, sid):
+            pass
+
+        def prefill(self, sids, prompts):
+            if self.params.get("fail32") and len(sids) == 32:
+                raise RuntimeError("boom")
+            time.sleep(0.001)
+            return np.zeros(len(sids), dtype=np.int32), None
+
+        def decode(self, sids, first, n):
+            time.sleep(0.002)
+            return np.zeros((len(sids), n), dtype=np.int32), None
+
+        def timing(self):
+            return Timing()
+
+        def timing_reset(self):
+            pass
+
+        def bench_kernel(self, kind, rows, ctx, iters):
+            return 0.03, 1.8e8
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(substratus_b200, "Engine", MockEngine)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+
+    def run(argv):
+        monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+        capsys.readouterr()
+        bench.main()
+        lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+        assert len(lines) == 1  # ONE JSON line
+        return json.loads(lines[0])
+
+    d = run(["--steps", "3", "--warmup", "1", "--no-cpu-baseline"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "ttft_ms_p50"):
+        assert key in d, key
+    assert d["steps"] == 3 and d["n_gpus"] == 1 and d["ttft_samples"] == 20 and d["batch32"]["value"] > 0
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["kernel"].startswith("decode_mega_kernel")
+    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--engine-params", '{"fail32": 1}'])
+    assert d["value"] > 0 and "boom" in d["batch32"]["error"] and d["config"]["engine_params"] == {"fail32": 1}
+    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--batch", "32"])
+    assert d["config"]["batch"] == 32 and "batch32" not in d and d["roofline"]["kernel"].startswith("gate/up")
+    d = run(["--steps", "25", "--warmup", "1", "--no-cpu-baseline", "--no-batch32"])
+    assert d["ttft_samples"] == 25
