@@ -52,3 +52,16 @@ def test_shard_ranges():
     assert tp.shard_ranges(64, 8) == [(i * 8, i * 8 + 8) for i in range(8)]
     with pytest.raises(ValueError):
         tp.shard_ranges(10, 4)
+
+
+def test_exchange_protocols_survive_random_interleavings():
+    """Model (not the CUDA code) of the experimental TP exchange protocols — flags, epochs, parity double-buffering —
+    under randomised CTA scheduling: no deadlock, no stale or overwritten read (tools/tp_protocol_check.py)."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tp_protocol_check", os.path.join(root, "tools", "tp_protocol_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main(20)
