@@ -18,26 +18,31 @@ from . import synth
 from .llama_ref import apply_rope, rope_tables
 
 
-def falcon_state_dict(cfg: dict, seed: int) -> dict:
+def falcon_tensor_specs(cfg: dict) -> dict:
+    """HF tensor name -> (tensor id, shape, amp, base)."""
     h, nh, nkv = cfg["hidden_size"], cfg["num_attention_heads"], cfg["num_kv_heads"]
     d = h // nh
     ffn = cfg.get("ffn_hidden_size") or 4 * h
     v = cfg["vocab_size"]
-    sd = {"transformer.word_embeddings.weight": synth.synth_bf16(seed, synth.GLOBAL + synth.G_EMBED, (v, h), synth.W_AMP)}
+    sp = {"transformer.word_embeddings.weight": (synth.GLOBAL + synth.G_EMBED, (v, h), synth.W_AMP, 0.0)}
     for l in range(cfg["num_hidden_layers"]):
         p, t = f"transformer.h.{l}.", l * 16
-        sd[p + "self_attention.query_key_value.weight"] = synth.synth_bf16(seed, t + synth.K_QKV, ((nh + 2 * nkv) * d, h), synth.W_AMP)
-        sd[p + "self_attention.dense.weight"] = synth.synth_bf16(seed, t + synth.K_O, (h, h), synth.W_AMP)
-        sd[p + "mlp.dense_h_to_4h.weight"] = synth.synth_bf16(seed, t + synth.K_FC1, (ffn, h), synth.W_AMP)
-        sd[p + "mlp.dense_4h_to_h.weight"] = synth.synth_bf16(seed, t + synth.K_FC2, (h, ffn), synth.W_AMP)
-        sd[p + "ln_attn.weight"] = synth.synth_bf16(seed, t + synth.K_LN1, (h,), synth.NORM_AMP, 1.0)
-        sd[p + "ln_attn.bias"] = synth.synth_bf16(seed, t + synth.K_LN1_B, (h,), synth.NORM_AMP, 0.0)
-        sd[p + "ln_mlp.weight"] = synth.synth_bf16(seed, t + synth.K_LN2, (h,), synth.NORM_AMP, 1.0)
-        sd[p + "ln_mlp.bias"] = synth.synth_bf16(seed, t + synth.K_LN2_B, (h,), synth.NORM_AMP, 0.0)
-    sd["transformer.ln_f.weight"] = synth.synth_bf16(seed, synth.GLOBAL + synth.G_NORM, (h,), synth.NORM_AMP, 1.0)
-    sd["transformer.ln_f.bias"] = synth.synth_bf16(seed, synth.GLOBAL + synth.G_NORM_B, (h,), synth.NORM_AMP, 0.0)
-    sd["lm_head.weight"] = synth.synth_bf16(seed, synth.GLOBAL + synth.G_LMHEAD, (v, h), synth.W_AMP * synth.LMHEAD_GAIN)
-    return sd
+        sp[p + "self_attention.query_key_value.weight"] = (t + synth.K_QKV, ((nh + 2 * nkv) * d, h), synth.W_AMP, 0.0)
+        sp[p + "self_attention.dense.weight"] = (t + synth.K_O, (h, h), synth.W_AMP, 0.0)
+        sp[p + "mlp.dense_h_to_4h.weight"] = (t + synth.K_FC1, (ffn, h), synth.W_AMP, 0.0)
+        sp[p + "mlp.dense_4h_to_h.weight"] = (t + synth.K_FC2, (h, ffn), synth.W_AMP, 0.0)
+        sp[p + "ln_attn.weight"] = (t + synth.K_LN1, (h,), synth.NORM_AMP, 1.0)
+        sp[p + "ln_attn.bias"] = (t + synth.K_LN1_B, (h,), synth.NORM_AMP, 0.0)
+        sp[p + "ln_mlp.weight"] = (t + synth.K_LN2, (h,), synth.NORM_AMP, 1.0)
+        sp[p + "ln_mlp.bias"] = (t + synth.K_LN2_B, (h,), synth.NORM_AMP, 0.0)
+    sp["transformer.ln_f.weight"] = (synth.GLOBAL + synth.G_NORM, (h,), synth.NORM_AMP, 1.0)
+    sp["transformer.ln_f.bias"] = (synth.GLOBAL + synth.G_NORM_B, (h,), synth.NORM_AMP, 0.0)
+    sp["lm_head.weight"] = (synth.GLOBAL + synth.G_LMHEAD, (v, h), synth.W_AMP * synth.LMHEAD_GAIN, 0.0)
+    return sp
+
+
+def falcon_state_dict(cfg: dict, seed: int) -> dict:
+    return {k: synth.synth_bf16(seed, tid, shape, amp, base) for k, (tid, shape, amp, base) in falcon_tensor_specs(cfg).items()}
 
 
 FALCON_40B = dict(model_type="falcon", hidden_size=8192, num_hidden_layers=60, num_attention_heads=128, num_kv_heads=8,
@@ -51,7 +56,7 @@ TINY_FALCON = dict(FALCON_40B, hidden_size=512, num_hidden_layers=2, num_attenti
 class FalconRef:
     def __init__(self, cfg: dict, sd: dict, dtype=torch.bfloat16):
         self.cfg, self.dtype = cfg, dtype
-        self.sd = {k: v.to(dtype) for k, v in sd.items()}
+        self.sd = sd if getattr(sd, "lazy", False) else {k: v.to(dtype) for k, v in sd.items()}
         self.h, self.nh, self.nkv = cfg["hidden_size"], cfg["num_attention_heads"], cfg["num_kv_heads"]
         self.d = self.h // self.nh
         self.L = cfg["num_hidden_layers"]

@@ -74,7 +74,7 @@ class LlamaRef:
     def __init__(self, cfg: dict, sd: dict, dtype=torch.bfloat16):
         self.cfg = cfg
         self.dtype = dtype
-        self.sd = {k: v.to(dtype) for k, v in sd.items()}
+        self.sd = sd if getattr(sd, "lazy", False) else {k: v.to(dtype) for k, v in sd.items()}
         self.h = cfg["hidden_size"]
         self.nh = cfg["num_attention_heads"]
         self.nkv = cfg.get("num_key_value_heads", self.nh)

@@ -57,12 +57,37 @@ def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << np.uint32(16)).view(np.float32)
 
 
+_fast_fill = None  # optional (seed, tid, start, n, amp, base) -> uint16 bits; tests plug in the engine's C host twin
+
+
+def set_fast_fill(fn) -> None:
+    """Full-width parity tests generate billions of synthetic weights; the numpy hash above manages ~8 M/s.  They may
+    plug in ``substratus_b200.engine.synth_fill_host`` (the C twin of the same generator, checked bit-for-bit against
+    this module in tests/test_oracle.py) to fill large tensors.  Values are identical; only the speed differs."""
+    global _fast_fill
+    _fast_fill = fn
+
+
+def synth_bits(seed: int, tid: int, n: int, amp: float, base: float = 0.0) -> np.ndarray:
+    if _fast_fill is not None and n >= (1 << 16):
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+
+        nthr = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+        step = -(-n // nthr)
+        parts = [(s0, min(step, n - s0)) for s0 in range(0, n, step)]
+        with ThreadPoolExecutor(nthr) as ex:  # ctypes releases the GIL inside the C call
+            outs = list(ex.map(lambda p: _fast_fill(seed, tid, p[0], p[1], amp, base), parts))
+        return np.concatenate(outs) if len(outs) > 1 else outs[0]
+    return f32_to_bf16_bits(synth_f32(seed, tid, n, amp, base))
+
+
 def synth_bf16(seed: int, tid: int, shape, amp: float, base: float = 0.0):
     """torch.bfloat16 tensor of ``shape`` with the engine's synthetic values."""
     import torch
 
     n = int(np.prod(shape))
-    bits = f32_to_bf16_bits(synth_f32(seed, tid, n, amp, base))
+    bits = synth_bits(seed, tid, n, amp, base)
     return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16).reshape(*shape)
 
 
@@ -75,31 +100,52 @@ LMHEAD_GAIN = 4.0
 NORM_AMP = 0.1
 
 
-def llama_state_dict(cfg: dict, seed: int) -> dict:
-    """HF-named state dict (bf16) for a Llama-family config dict (HF ``config.json`` keys)."""
+def llama_tensor_specs(cfg: dict) -> dict:
+    """HF tensor name -> (tensor id, shape, amp, base) for a Llama-family config dict (HF ``config.json`` keys)."""
     h = cfg["hidden_size"]
     nh = cfg["num_attention_heads"]
     nkv = cfg.get("num_key_value_heads", nh)
     d = cfg.get("head_dim") or h // nh
     inter = cfg["intermediate_size"]
     v = cfg["vocab_size"]
-    sd = {}
-    sd["model.embed_tokens.weight"] = synth_bf16(seed, GLOBAL + G_EMBED, (v, h), W_AMP)
+    sp = {"model.embed_tokens.weight": (GLOBAL + G_EMBED, (v, h), W_AMP, 0.0)}
     for l in range(cfg["num_hidden_layers"]):
         p = f"model.layers.{l}."
         t = l * 16
-        sd[p + "self_attn.q_proj.weight"] = synth_bf16(seed, t + K_Q, (nh * d, h), W_AMP)
-        sd[p + "self_attn.k_proj.weight"] = synth_bf16(seed, t + K_K, (nkv * d, h), W_AMP)
-        sd[p + "self_attn.v_proj.weight"] = synth_bf16(seed, t + K_V, (nkv * d, h), W_AMP)
-        sd[p + "self_attn.o_proj.weight"] = synth_bf16(seed, t + K_O, (h, nh * d), W_AMP)
-        sd[p + "mlp.gate_proj.weight"] = synth_bf16(seed, t + K_GATE, (inter, h), W_AMP)
-        sd[p + "mlp.up_proj.weight"] = synth_bf16(seed, t + K_UP, (inter, h), W_AMP)
-        sd[p + "mlp.down_proj.weight"] = synth_bf16(seed, t + K_DOWN, (h, inter), W_AMP)
-        sd[p + "input_layernorm.weight"] = synth_bf16(seed, t + K_LN1, (h,), NORM_AMP, 1.0)
-        sd[p + "post_attention_layernorm.weight"] = synth_bf16(seed, t + K_LN2, (h,), NORM_AMP, 1.0)
-    sd["model.norm.weight"] = synth_bf16(seed, GLOBAL + G_NORM, (h,), NORM_AMP, 1.0)
-    sd["lm_head.weight"] = synth_bf16(seed, GLOBAL + G_LMHEAD, (v, h), W_AMP * LMHEAD_GAIN)
-    return sd
+        sp[p + "self_attn.q_proj.weight"] = (t + K_Q, (nh * d, h), W_AMP, 0.0)
+        sp[p + "self_attn.k_proj.weight"] = (t + K_K, (nkv * d, h), W_AMP, 0.0)
+        sp[p + "self_attn.v_proj.weight"] = (t + K_V, (nkv * d, h), W_AMP, 0.0)
+        sp[p + "self_attn.o_proj.weight"] = (t + K_O, (h, nh * d), W_AMP, 0.0)
+        sp[p + "mlp.gate_proj.weight"] = (t + K_GATE, (inter, h), W_AMP, 0.0)
+        sp[p + "mlp.up_proj.weight"] = (t + K_UP, (inter, h), W_AMP, 0.0)
+        sp[p + "mlp.down_proj.weight"] = (t + K_DOWN, (h, inter), W_AMP, 0.0)
+        sp[p + "input_layernorm.weight"] = (t + K_LN1, (h,), NORM_AMP, 1.0)
+        sp[p + "post_attention_layernorm.weight"] = (t + K_LN2, (h,), NORM_AMP, 1.0)
+    sp["model.norm.weight"] = (GLOBAL + G_NORM, (h,), NORM_AMP, 1.0)
+    sp["lm_head.weight"] = (GLOBAL + G_LMHEAD, (v, h), W_AMP * LMHEAD_GAIN, 0.0)
+    return sp
+
+
+def llama_state_dict(cfg: dict, seed: int) -> dict:
+    """HF-named state dict (bf16) for a Llama-family config dict."""
+    return {k: synth_bf16(seed, tid, shape, amp, base) for k, (tid, shape, amp, base) in llama_tensor_specs(cfg).items()}
+
+
+class LazyStateDict:
+    """Mapping that generates each synthetic tensor on access (in ``dtype``) and keeps nothing: a full-depth 7B oracle in
+    fp32 would otherwise hold 27 GB.  ``oracle.llama_ref.LlamaRef`` / ``falcon_ref.FalconRef`` take it in place of a dict."""
+
+    lazy = True
+
+    def __init__(self, specs: dict, seed: int, dtype):
+        self.specs, self.seed, self.dtype = specs, seed, dtype
+
+    def __getitem__(self, k):
+        tid, shape, amp, base = self.specs[k]
+        return synth_bf16(self.seed, tid, shape, amp, base).to(self.dtype)
+
+    def keys(self):
+        return self.specs.keys()
 
 
 LLAMA2_7B = dict(model_type="llama", hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
