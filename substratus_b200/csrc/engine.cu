@@ -469,8 +469,14 @@ int Engine::alloc_runtime(const Json& params) {
       tp_pool_bytes_ += 8 * 256 * sizeof(uint32_t);
       TRY(dmalloc(&d_peer_cta_flags_, 8));
     }
+    if (tp_mega_mode_ == 3) {
+      tp_off_ll_ = (tp_pool_bytes_ + 255) & ~(size_t)255;
+      tp_pool_bytes_ = tp_off_ll_ + 2 * 8 * 4 * (size_t)(h / 2) * sizeof(uint4);
+      TRY(dmalloc(&d_peer_ll_, 8));
+    }
     TRY(dmalloc(&tp_pool_, tp_pool_bytes_));
     if (tp_mega_mode_ == 2) CK(cudaMemset(tp_pool_ + tp_off_ctaflags_, 0, 8 * 256 * sizeof(uint32_t)));
+    if (tp_mega_mode_ == 3) CK(cudaMemset(tp_pool_ + tp_off_ll_, 0, tp_pool_bytes_ - tp_off_ll_));  // epoch 0 = never written
     CK(cudaMemset(tp_pool_ + tp_off_flags_, 0, 128));
     tp_partials_ = (float*)tp_pool_;
     tp_recv_ = (float*)(tp_pool_ + tp_off_recv_);
@@ -1313,8 +1319,11 @@ int Engine::forward_mega(int B) {
     a.peer_partials = d_peer_partials_;
     a.peer_flags = d_peer_flags_;
     a.parity_stride = (long long)m_max_ * cfg_.hidden;
-    a.tp_mode = tp_mega_mode_ == 2 ? 2 : 1;
+    a.tp_mode = tp_mega_mode_ >= 2 ? tp_mega_mode_ : 1;
     a.peer_cta_flags = d_peer_cta_flags_;
+    a.peer_ll = d_peer_ll_;
+    a.ll_src_stride = 4LL * (cfg_.hidden / 2);
+    a.ll_parity_stride = 8 * a.ll_src_stride;
   }
   CK(launch_decode_mega(a, LaunchCfg{stream_, false, n_sm_}));
   launches_per_forward_ = 1;
@@ -1679,6 +1688,11 @@ int Engine::tp_connect(const void* all, int n) {
     std::vector<uint32_t*> pc(8, nullptr);
     for (int r = 0; r < n; ++r) pc[r] = (uint32_t*)(pool[r] + tp_off_ctaflags_);
     CK(cudaMemcpy(d_peer_cta_flags_, pc.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  }
+  if (tp_mega_mode_ == 3) {
+    std::vector<uint4*> pl(8, nullptr);
+    for (int r = 0; r < n; ++r) pl[r] = (uint4*)(pool[r] + tp_off_ll_);
+    CK(cudaMemcpy(d_peer_ll_, pl.data(), 8 * sizeof(uint4*), cudaMemcpyHostToDevice));
   }
   if (tp_two_shot_) {
     std::vector<bf16*> pg(8, nullptr);

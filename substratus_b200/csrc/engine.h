@@ -141,6 +141,9 @@ class Engine {
   int tp_mega_mode_ = 0;
   size_t tp_off_ctaflags_ = 0;
   uint32_t** d_peer_cta_flags_ = nullptr;
+  // "tp_mega": 3 — LL push receive buffers [2 parity][8 src][4 rows][hidden/2] uint4, appended to the exchange pool
+  size_t tp_off_ll_ = 0;
+  uint4** d_peer_ll_ = nullptr;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;
   int tap_rows_ = 0;

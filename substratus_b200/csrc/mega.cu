@@ -254,9 +254,24 @@ SSB_DEVINL void stage_x(const bf16* x, int ldx, int M, int K, const bf16* norm_w
 }
 
 // ---------------------------------------------------------------- consumers: one projection (same loop as gemv_kernel)
+constexpr int EPI_LL = 100;  // mega-only epilogue: "tp_mega": 3 push exchange (see mega.h)
+struct LlCtx {
+  const MegaArgs* ma;
+  uint32_t epoch;
+  size_t off;  // parity + source-rank offset (uint4 units) into every receive buffer
+};
+SSB_DEVINL void st_relaxed_sys_v4(uint4* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SSB_DEVINL uint4 ld_relaxed_sys_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 template <int BT, int EPI>
 SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        int warp, int lane) {
+                        int warp, int lane, [[maybe_unused]] const LlCtx* ll = nullptr) {
   const int K = a.K;
   const int P = a.N >> 1;
   const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
@@ -295,7 +310,18 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
           v1 = s1;
         }
       }
-      if (lane < BT && lane < a.M) gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
+      if constexpr (EPI == EPI_LL) {
+        if (lane < BT && lane < a.M) {
+          const MegaArgs& ma = *ll->ma;
+          const uint4 w = make_uint4(__float_as_uint(v0), ll->epoch, __float_as_uint(v1), ll->epoch);
+          const size_t o = ll->off + (size_t)lane * (size_t)(ma.hidden >> 1) + (size_t)pair;
+#pragma unroll
+          for (int rk = 0; rk < 8; ++rk)
+            if (rk < ma.tp_size) st_relaxed_sys_v4(ma.peer_ll[rk] + o, w);  // own slot included: the reduce reads all ranks alike
+        }
+      } else {
+        if (lane < BT && lane < a.M) gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
+      }
     }
   }
 }
@@ -567,6 +593,36 @@ SSB_DEVINL void tp_reduce_cta(const MegaArgs& a, int seq, int tid) {
   }
 }
 
+// "tp_mega": 3 — wait for the pushed partials of this CTA's pair range (all ranks, own included), sum in rank order, add the
+// residual, write h.  Slot reuse: a source rewrites slot (parity, pair) two allreduces later, after it received this CTA's
+// push of the allreduce in between, which this CTA issues only after the grid barrier that follows these reads.
+SSB_DEVINL void tp_reduce_ll(const MegaArgs& a, int seq, uint32_t epoch, int tid) {
+  const int P = a.hidden >> 1;
+  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  const int np = p1 - p0;
+  const uint4* base = a.peer_ll[a.tp_rank] + (size_t)(seq & 1) * (size_t)a.ll_parity_stride;
+  for (int i = tid; i < a.M * np; i += MG_CW * 32) {
+    const int m = i / np, p = p0 + (i - m * np);
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {
+      if (r < a.tp_size) {
+        const uint4* slot = base + (size_t)r * (size_t)a.ll_src_stride + (size_t)m * P + p;
+        uint4 v;
+        do {
+          v = ld_relaxed_sys_v4(slot);
+        } while (v.y != epoch || v.w != epoch);
+        s.x += __uint_as_float(v.x);
+        s.y += __uint_as_float(v.z);
+      }
+    }
+    const size_t o = (size_t)m * a.hidden + 2 * (size_t)p;
+    const uint32_t rv = __ldcg(reinterpret_cast<const uint32_t*>(a.h + o));
+    *reinterpret_cast<uint32_t*>(a.h + o) = pack_bf16(bf16r(s.x) + bf_lo(rv), bf16r(s.y) + bf_hi(rv));
+  }
+}
+
 template <int BT, int D, int G, bool TP = false>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -627,6 +683,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     }
   }
   grid_sync(a.grid_bar, n_sync, n_ctas);
+  // epoch of allreduce `seq` of this forward = ll_epoch0 + seq (never 0; the forward counter was bumped above and is
+  // visible through the grid barrier)
+  [[maybe_unused]] uint32_t ll_epoch0 = 0;
+  if constexpr (TP) ll_epoch0 = (uint32_t)ld_acquire_gpu(reinterpret_cast<const unsigned*>(a.fwd_counter)) * (uint32_t)(2 * a.n_layers) + 1u;
 
   GemvArgs g = {};
   g.M = a.M;
@@ -671,8 +731,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     MG_STAMP();  // 6: x staged
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l) & 1) * (size_t)a.parity_stride;
+      if (a.tp_mode == 3) {
+        const LlCtx lx = {&a, ll_epoch0 + (uint32_t)(2 * l), (size_t)((2 * l) & 1) * (size_t)a.ll_parity_stride + (size_t)a.tp_rank * (size_t)a.ll_src_stride};
+        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, &lx);
+        tp_reduce_ll(a, 2 * l, lx.epoch, tid);
+      } else {
       consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
-      if (a.tp_mode == 2) {
+      }
+      if (a.tp_mode == 3) {
+      } else if (a.tp_mode == 2) {
         tp_reduce_cta(a, 2 * l, tid);
       } else {
         grid_sync(a.grid_bar, n_sync, n_ctas);
@@ -705,8 +772,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     MG_STAMP();  // 12: x staged
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l + 1) & 1) * (size_t)a.parity_stride;
+      if (a.tp_mode == 3) {
+        const LlCtx lx = {&a, ll_epoch0 + (uint32_t)(2 * l + 1), (size_t)((2 * l + 1) & 1) * (size_t)a.ll_parity_stride + (size_t)a.tp_rank * (size_t)a.ll_src_stride};
+        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, &lx);
+        tp_reduce_ll(a, 2 * l + 1, lx.epoch, tid);
+      } else {
       consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
-      if (a.tp_mode == 2) {
+      }
+      if (a.tp_mode == 3) {
+      } else if (a.tp_mode == 2) {
         tp_reduce_cta(a, 2 * l + 1, tid);
       } else {
         grid_sync(a.grid_bar, n_sync, n_ctas);
@@ -825,6 +899,7 @@ static cudaError_t launch_mega_b(const MegaArgs& a, const LaunchCfg& lc) {
   if (a.tp_size > 1) {  // tensor-parallel variant: Llama head size only
     if (a.head_dim != 128 || a.tp_size > TP_MAX || (a.hidden & 3) || !a.peer_partials || !a.peer_flags) return cudaErrorInvalidValue;
     if (a.tp_mode == 2 && (!a.peer_cta_flags || lc.n_sm > MG_CTA_FLAG_STRIDE)) return cudaErrorInvalidValue;
+    if (a.tp_mode == 3 && !a.peer_ll) return cudaErrorInvalidValue;
     switch (g) {
       case 1: return launch_mega_t<BT, 128, 1, true>(a, lc);
       case 2: return launch_mega_t<BT, 128, 2, true>(a, lc);

@@ -46,8 +46,15 @@ struct MegaArgs {
   // (flag [src rank][cta] at the receiver), waits for theirs, pulls their range, adds its own partial and the residual and
   // writes its range of h; the phase then ends with the ordinary grid barrier.  One grid barrier less per allreduce than
   // mode 1 and no GPU-wide skew wait.
-  int tp_mode;                       // 1 | 2
+  int tp_mode;                       // 1 | 2 | 3
   uint32_t* const* peer_cta_flags;   // [tp_size] -> u32 [8][256] at each receiver
+  // "tp_mega": 3 — low-latency PUSH exchange (the wire format of NCCL's LL protocol): the row-parallel epilogue stores
+  // every fp32 partial pair straight into all ranks' receive slots as ONE 16-byte word {v0, epoch, v1, epoch}; the
+  // receiver polls the slot itself until both epoch halves match, so there is no separate flag, no fence and no remote
+  // read on the critical path (one NVLink one-way latency per allreduce instead of flag + pull round trip).  Slots:
+  // ll[parity][src rank][row][pair] (uint4), CTA c of every rank owns the same pair range, so only same-index CTAs talk.
+  uint4* const* peer_ll;             // [tp_size] peer-mapped receive buffers
+  long long ll_parity_stride, ll_src_stride;  // in uint4 units
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);

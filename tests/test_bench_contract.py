@@ -116,16 +116,46 @@ def test_gpu_arm_control_flow_against_a_mock_engine(monkeypatch, capsys):
         assert len(lines) == 1  # ONE JSON line
         return json.loads(lines[0])
 
-    d = run(["--steps", "3", "--warmup", "1", "--no-cpu-baseline"])
+    d = run(["--steps", "3", "--warmup", "1", "--no-cpu-baseline", "--no-extras"])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "ttft_ms_p50"):
         assert key in d, key
     assert d["steps"] == 3 and d["n_gpus"] == 1 and d["ttft_samples"] == 20 and d["batch32"]["value"] > 0
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["kernel"].startswith("decode_mega_kernel")
-    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--engine-params", '{"fail32": 1}'])
+    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-extras", "--engine-params", '{"fail32": 1}'])
     assert d["value"] > 0 and "boom" in d["batch32"]["error"] and d["config"]["engine_params"] == {"fail32": 1}
     d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--batch", "32"])
     assert d["config"]["batch"] == 32 and "batch32" not in d and d["roofline"]["kernel"].startswith("gate/up")
     d = run(["--steps", "25", "--warmup", "1", "--no-cpu-baseline", "--no-batch32"])
     assert d["ttft_samples"] == 25
+
+
+def test_reference_arm_is_a_full_depth_measurement():
+    """no layer extrapolation — the line describes exactly what was timed."""
+    r = _run(["--impl", "reference", "--workload", "tiny", "--steps", "3", "--warmup", "1", "--ref-prompt-len", "16", "--ref-new-tokens", "4"])
+    assert r.returncode == 0, r.stderr[-500:]
+    d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert d["steps"] == 3 and d["tokens_per_step"] >= 1 and "full-depth (8 layers" in d["config"]["sample"] and "extrapolat" not in d["config"]["sample"]
+    assert abs(d["value"] - d["tokens_per_step"] * 1e3 / d["ms_per_step"]) / d["value"] < 1e-6  # value == tokens per step / mean step time
+
+
+def test_synthetic_q4_0_gguf_writer(tmp_path):
+    """bench.py's config-3 file generator: a well-formed Q4_0 GGUF the engine's own reader accepts (host side only)."""
+    import importlib
+
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    from substratus_b200.engine import model_read_tensor, model_tensor_count
+
+    cfg = dict(bench.WORKLOADS["tiny"], num_hidden_layers=2, intermediate_size=704)
+    size = bench.write_q4_0_gguf(str(tmp_path / "model.bin"), cfg)
+    assert size > 0 and model_tensor_count(str(tmp_path)) == 3 + 9 * 2
+    dt, shape, raw = model_read_tensor(str(tmp_path), "blk.1.ffn_down.weight")
+    assert dt == "q4_0" and shape == (256, 704) and raw.size == 256 * 704 // 32 * 18
+    import numpy as np
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants
+
+    w = quants.dequantize(raw.reshape(256, -1), T.Q4_0)
+    assert np.isfinite(w).all() and 0.005 < float(w.std()) < 0.05

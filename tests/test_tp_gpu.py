@@ -48,8 +48,9 @@ def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
 @pytest.mark.parametrize("world", [2, 4])
 # {"tp_two_shot": 1}: reduce-scatter + bf16 gather allreduce for prefill-sized forwards (csrc/tp_twoshot.cu), same status.
 @pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
-                                  {"gemm_path": "tc", "tp_two_shot": 1, "tp_two_shot_min_rows": 16}, {"gemm_path": "gemv", "tp_mega": 2}],
-                         ids=["gemv", "tc", "exp_tp_mega", "exp_two_shot", "exp_tp_mega2"])
+                                  {"gemm_path": "tc", "tp_two_shot": 1, "tp_two_shot_min_rows": 16}, {"gemm_path": "gemv", "tp_mega": 2},
+                                  {"gemm_path": "gemv", "tp_mega": 3}],
+                         ids=["gemv", "tc", "exp_tp_mega", "exp_two_shot", "exp_tp_mega2", "exp_tp_mega3"])
 def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     if (mode.get("tp_mega") or mode.get("tp_two_shot")) and os.environ.get("SSB_EXPERIMENTAL") != "1":
         pytest.skip("experimental (set SSB_EXPERIMENTAL=1)")

@@ -17,7 +17,7 @@ timeout -k 20 1200 python -m pytest tests/test_fullwidth_gpu.py -m gpu -q --dura
 echo "== 4. default library: logits dump, phase timeline, bench (batch 1 + 32)"
 timeout -k 20 200 python tools/dump_logits.py $O/r2_logits_default.npz 2>&1 | tail -1
 timeout -k 20 200 python tools/mega_prof.py 1 2>&1 | tee $O/r2_mega_prof_default.log
-timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee -a $O/r2_single_bench.jsonl
+timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras 2>&1 | tail -1 | tee -a $O/r2_single_bench.jsonl
 for SPEC in "combo2:--no-batch32" "combo:--no-batch32" "fhfma:--no-batch32" "l2ahead:--no-batch32" "synclight:--no-batch32" "synctree:--no-batch32" "cw12:--no-batch32" "fhfma12:--no-batch32" "skprefetch:--batch 32" "sk2cta:--batch 32" "attnlite:--batch 32"; do
   V=${SPEC%%:*}; FLAGS=${SPEC#*:}
   [ -f substratus_b200/lib/libsubstratus_b200.$V.so ] || { echo "variant $V not built"; continue; }
@@ -32,12 +32,15 @@ for SPEC in "combo2:--no-batch32" "combo:--no-batch32" "fhfma:--no-batch32" "l2a
     grep -q "passed" $O/r2_parity_$V.log && ! grep -q "failed\|error" $O/r2_parity_$V.log && GATE=0
   fi
   if [ $GATE -eq 0 ]; then
-    SSB_LIB_VARIANT=$V timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline $FLAGS 2>&1 | tail -1 | tee -a $O/r2_single_bench.jsonl
+    SSB_LIB_VARIANT=$V timeout -k 20 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras $FLAGS 2>&1 | tail -1 | tee -a $O/r2_single_bench.jsonl
     case $V in combo2|combo|l2ahead) SSB_LIB_VARIANT=$V timeout -k 20 200 python tools/mega_prof.py 1 2>&1 | tee $O/r2_mega_prof_$V.log;; esac
   else
     echo "variant $V failed its gate: not benchmarked"
   fi
 done
+echo "== 6. the full default line (all BASELINE configs as sub-objects, CPU baseline) and the reference arm"
+( time timeout -k 20 900 python bench.py --steps 5 --warmup 3 ) > $O/r2_bench_full.log 2>&1; tail -4 $O/r2_bench_full.log | cut -c1-3000
+( time timeout -k 20 600 python bench.py --impl reference --steps 4 --warmup 1 ) > $O/r2_bench_ref.log 2>&1; tail -4 $O/r2_bench_ref.log | cut -c1-1500
 python - <<'PY'
 import json
 for ln in open("gpurun_out/r2_single_bench.jsonl"):

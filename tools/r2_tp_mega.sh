@@ -18,7 +18,7 @@ if ! grep -q "passed" gpurun_out/r2_tp_mega_parity.log || grep -q "failed\|error
   echo "parity not (all) green: fix or drop the failing mode before benchmarking"; exit 1
 fi
 echo "== 2. decode tokens/s, default TP path vs tp_mega ($WL, TP$N)"
-for P in '{}' '{"tp_mega": 1}' '{"tp_mega": 2}' '{"tp_two_shot": 1}' '{"tp_mega": 2, "tp_two_shot": 1}'; do
+for P in '{}' '{"tp_mega": 1}' '{"tp_mega": 2}' '{"tp_mega": 3}' '{"tp_two_shot": 1}' '{"tp_mega": 3, "tp_two_shot": 1}'; do
   timeout -k 20 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
     bench.py --gpus $N --steps 3 --warmup 3 --workload $WL --no-batch32 --no-cpu-baseline --engine-params "$P" 2>&1 | tail -1 \
     | tee -a gpurun_out/r2_tp_mega_bench.jsonl

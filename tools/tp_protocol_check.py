@@ -1,5 +1,5 @@
 """Randomised interleaving check of the cross-GPU exchange PROTOCOLS of the experimental tensor-parallel paths — a
-model of csrc/mega.cu (tp_reduce_phase = "mode1", tp_reduce_cta = "mode2") and csrc/tp_twoshot.cu ("twoshot"), not the
+model of csrc/mega.cu (tp_reduce_phase = "mode1", tp_reduce_cta = "mode2", the LL push exchange tp_reduce_ll = "ll") and csrc/tp_twoshot.cu ("twoshot"), not the
 CUDA code itself: flags, epochs, parity double-buffering of the partials, the single-buffered gather of the two-shot.
 Each CTA is a generator; `yield` = a point where any other CTA may run.  Reads assert they see exactly the value of the
 allreduce they belong to (not a stale one, not one overwritten by a later allreduce)."""
@@ -14,6 +14,7 @@ def run(protocol, R, C, K, seed):
     gather = [[None] * C for _ in range(R)]                                # two-shot: single-buffered gather per rank (slice = rank's)
     flag2 = [[0] * R for _ in range(R)]
     done = [0] * R
+    ll = [[[[(None, 0)] * C for _ in range(R)] for _ in range(2)] for _ in range(R)]   # "ll": [recv][parity][src][cta] = (value, epoch)
     def grid_barrier(r, n):            # n-th barrier of this rank (monotonic counter like the kernel's)
         bar[r][0] += 1
         while bar[r][0] < n * C: yield
@@ -24,7 +25,19 @@ def run(protocol, R, C, K, seed):
             yield
             partial[r][par][c] = (r, k)                                    # projection epilogue
             yield
-            if protocol == "mode2":
+            if protocol == "ll":
+                # mode 3 of mega.cu: push {value, epoch} into every rank's slot (own included), no flag; the receiver polls
+                # the slot for EQUALITY with the epoch (a slot overwritten by allreduce k+2 before it was read = deadlock here)
+                for p in range(R):
+                    yield
+                    ll[p][par][r][c] = ((r, k), k)
+                for p in range(R):
+                    while ll[r][par][p][c][1] != k:
+                        assert ll[r][par][p][c][1] < k, ("ll: slot overwritten before it was read", r, c, k, p, ll[r][par][p][c])
+                        yield
+                    assert ll[r][par][p][c][0] == (p, k)
+                nb += 1; yield from grid_barrier(r, nb)
+            elif protocol == "mode2":
                 for p in range(R):
                     if p != r: cflag[p][r][c] = k
                 for p in range(R):
@@ -88,7 +101,7 @@ def run(protocol, R, C, K, seed):
     return steps
 
 def main(n_cfg=40):
-    for proto in ("mode1", "mode2", "twoshot"):
+    for proto in ("mode1", "mode2", "ll", "twoshot"):
         tot = 0
         for seed in range(n_cfg):
             tot += run(proto, R=random.Random(seed).choice([2, 3, 4]), C=random.Random(seed + 1).choice([1, 2, 5]), K=9, seed=seed)
