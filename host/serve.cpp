@@ -53,7 +53,18 @@ static ssb_engine* g_engine = nullptr;
 static ssb_info g_info;
 static std::mutex g_engine_mu;  // ssb_* calls on one engine are not re-entrant
 static std::atomic<long long> g_requests{0}, g_tokens{0}, g_errors{0};
-static std::atomic<double> g_ttft_ms_sum{0}, g_decode_ms_sum{0};
+static std::atomic<long long> g_ttft_us_sum{0}, g_decode_us_sum{0};  // integer microseconds: fetch_add is atomic
+static std::atomic<int> g_conns{0};
+static const int kMaxConns = 256;  // concurrent connections (each holds a thread); above it: 503
+// A device-side failure is not recoverable inside the process (CUDA errors are sticky; under tensor parallelism the other
+// ranks would wait for a peer that is gone): fail readiness and exit non-zero so the Deployment restarts the pod
+// (the container contract's error path: server_controller.go:280-296).
+[[noreturn]] static void fatal_exit(const std::string& why) {
+  g_ready = -1;
+  fprintf(stderr, "serve: fatal engine error, exiting for a pod restart: %s\n", why.c_str());
+  fflush(stderr);
+  _exit(1);
+}
 static std::string g_load_error;
 static ssb_tokenizer* g_tok = nullptr;  // <model_dir>/tokenizer.json, if present and supported (text prompts)
 // Tensor parallel inside the ONE container the reconciler grants N GPUs to (resources.gpu.count -> nvidia.com/gpu: N,
@@ -162,6 +173,7 @@ struct GenResult {
   double ttft_ms = 0, decode_ms = 0;
   bool hit_eos = false;  // stopped at an end-of-sequence id (which is NOT included in tokens)
   std::string error;
+  bool fatal = false;  // the engine is unusable (SSB_ECUDA, or tensor-parallel ranks failed / disagreed)
 };
 
 // Called with the ids produced since the previous call (first call: the prefill's token).  Returning false stops the
@@ -247,15 +259,19 @@ static GenResult generate_tp(const std::vector<int32_t>& prompt, int max_new, in
   for (size_t i = 1; i < n; ++i)
     th.emplace_back([&, i] {
       bool h = false;
-      run_rank(g_peers[i - 1], prompt, max_new, chunk, eos, nullptr, false, &toks[i], &h, &ttft[i], &dec[i], &errs[i], samp);
+      const int rc = run_rank(g_peers[i - 1], prompt, max_new, chunk, eos, nullptr, false, &toks[i], &h, &ttft[i], &dec[i], &errs[i], samp);
+      // the other ranks may be spinning on this rank's flags (bounded, SpinGuard): do not wait for them
+      if (rc == SSB_ECUDA) fatal_exit("rank " + std::to_string(i) + ": " + errs[i]);
       hit[i] = h;
     });
-  run_rank(g_engine, prompt, max_new, chunk, eos, sink, false, &toks[0], &r.hit_eos, &ttft[0], &dec[0], &errs[0], samp);
+  const int rc0 = run_rank(g_engine, prompt, max_new, chunk, eos, sink, false, &toks[0], &r.hit_eos, &ttft[0], &dec[0], &errs[0], samp);
+  if (rc0 == SSB_ECUDA) fatal_exit("rank 0: " + errs[0]);
   for (auto& t : th) t.join();
   for (size_t i = 0; i < n; ++i) {
     if (!errs[i].empty()) r.error = "rank " + std::to_string(i) + ": " + errs[i];
     if (i && r.error.empty() && toks[i] != toks[0]) r.error = "tensor-parallel ranks disagree on the generated ids";
   }
+  r.fatal = !r.error.empty();  // ranks out of lock-step (one failed, or ids differ): the group cannot serve the next request
   r.tokens = toks[0];
   r.ttft_ms = *std::max_element(ttft.begin(), ttft.end());
   r.decode_ms = *std::max_element(dec.begin(), dec.end());
@@ -293,7 +309,8 @@ static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int c
     return r;
   }
   std::lock_guard<std::mutex> lk(g_engine_mu);
-  run_rank(g_engine, prompt, max_new, chunk, eos, sink, true, &r.tokens, &r.hit_eos, &r.ttft_ms, &r.decode_ms, &r.error, samp);
+  const int rc = run_rank(g_engine, prompt, max_new, chunk, eos, sink, true, &r.tokens, &r.hit_eos, &r.ttft_ms, &r.decode_ms, &r.error, samp);
+  r.fatal = rc == SSB_ECUDA;
   return r;
 }
 
@@ -390,10 +407,14 @@ static void stream_response(int fd, bool oai, const std::vector<int32_t>& prompt
   if (!r.error.empty()) {
     g_errors++;
     send_all(fd, "data: " + err_json(r.error) + "\n\n");
+    if (r.fatal) {
+      send_all(fd, "data: [DONE]\n\n");
+      fatal_exit(r.error);
+    }
   } else {
     g_tokens += (long long)r.tokens.size();
-    g_ttft_ms_sum.store(g_ttft_ms_sum.load() + r.ttft_ms);
-    g_decode_ms_sum.store(g_decode_ms_sum.load() + r.decode_ms);
+    g_ttft_us_sum.fetch_add((long long)(r.ttft_ms * 1e3));
+    g_decode_us_sum.fetch_add((long long)(r.decode_ms * 1e3));
     char tail[320];
     const double tps = r.decode_ms > 0 && r.tokens.size() > 1 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
     snprintf(tail, sizeof tail,
@@ -409,7 +430,30 @@ struct InflightGuard {
   ~InflightGuard() { --g_inflight; }
 };
 
+struct ConnGuard {
+  ConnGuard() { ++g_conns; }
+  ~ConnGuard() { --g_conns; }
+};
+
+// Largest request body accepted: a prompt can never exceed max_seq_len ids (<= 11 characters each in JSON) or, as text,
+// a few bytes per token; 1 MiB floor for the fixed fields.  The JSON tree costs ~100 B per number, so an uncapped id
+// array is a cheap way to run the pod out of memory.
+static size_t max_body_bytes() {
+  const size_t per_seq = g_ready.load() == 1 ? (size_t)g_info.max_seq_len * 32 : 0;
+  return std::max<size_t>(1u << 20, per_seq);
+}
+
 static void handle(int fd) {
+  ConnGuard conn;
+  if (g_conns.load() > kMaxConns) {
+    respond(fd, 503, "Service Unavailable", err_json("too many connections"));
+    close(fd);
+    return;
+  }
+  {  // an idle or slow client must not pin a thread (and the SIGTERM drain) for ever
+    timeval tv{10, 0};
+    setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+  }
   InflightGuard guard;
   std::string req;
   char buf[8192];
@@ -428,10 +472,10 @@ static void handle(int fd) {
   {
     std::string low = req.substr(0, hdr_end);
     for (auto& c : low) c = (char)tolower(c);
-    size_t p = low.find("content-length:");
-    if (p != std::string::npos) clen = (size_t)strtoull(low.c_str() + p + 15, nullptr, 10);
+    size_t p = low.find("\r\ncontent-length:");  // a header NAME starts a line (not e.g. "x-content-length:")
+    if (p != std::string::npos) clen = (size_t)strtoull(low.c_str() + p + 17, nullptr, 10);
   }
-  if (clen > (64u << 20)) {
+  if (clen > max_body_bytes()) {
     respond(fd, 413, "Payload Too Large", err_json("body too large"));
     close(fd);
     return;
@@ -440,6 +484,11 @@ static void handle(int fd) {
     ssize_t n = recv(fd, buf, sizeof buf, 0);
     if (n <= 0) break;
     req.append(buf, (size_t)n);
+  }
+  if (req.size() < hdr_end + 4 + clen) {  // client stalled (SO_RCVTIMEO) or went away mid-body
+    respond(fd, 408, "Request Timeout", err_json("request body incomplete"));
+    close(fd);
+    return;
   }
   const std::string line = req.substr(0, req.find("\r\n"));
   const size_t sp1 = line.find(' '), sp2 = line.find(' ', sp1 + 1);
@@ -464,7 +513,7 @@ static void handle(int fd) {
              "# TYPE ssb_requests_total counter\nssb_requests_total %lld\n# TYPE ssb_generated_tokens_total counter\n"
              "ssb_generated_tokens_total %lld\n# TYPE ssb_errors_total counter\nssb_errors_total %lld\n"
              "# TYPE ssb_ttft_ms_sum counter\nssb_ttft_ms_sum %.3f\n# TYPE ssb_decode_ms_sum counter\nssb_decode_ms_sum %.3f\n",
-             g_requests.load(), g_tokens.load(), g_errors.load(), g_ttft_ms_sum.load(), g_decode_ms_sum.load());
+             g_requests.load(), g_tokens.load(), g_errors.load(), g_ttft_us_sum.load() / 1e3, g_decode_us_sum.load() / 1e3);
     respond(fd, 200, "OK", m, "text/plain; version=0.0.4");
   } else if (method == "POST" && (path == "/generate" || path == "/v1/completions")) {
     if (g_ready.load() != 1) {
@@ -545,10 +594,11 @@ static void handle(int fd) {
         if (!r.error.empty()) {
           g_errors++;
           respond(fd, 500, "Internal Server Error", err_json(r.error));
+          if (r.fatal) fatal_exit(r.error);
         } else {
           g_tokens += (long long)r.tokens.size();
-          g_ttft_ms_sum.store(g_ttft_ms_sum.load() + r.ttft_ms);
-          g_decode_ms_sum.store(g_decode_ms_sum.load() + r.decode_ms);
+          g_ttft_us_sum.fetch_add((long long)(r.ttft_ms * 1e3));
+          g_decode_us_sum.fetch_add((long long)(r.decode_ms * 1e3));
           char tail[256];
           const double tps = r.decode_ms > 0 && r.tokens.size() > 1 ? (r.tokens.size() - 1) * 1e3 / r.decode_ms : 0.0;
           snprintf(tail, sizeof tail, "\"ttft_ms\":%.3f,\"decode_ms\":%.3f,\"decode_tokens_per_sec\":%.2f", r.ttft_ms, r.decode_ms, tps);
@@ -663,12 +713,21 @@ int main(int argc, char** argv) {
       g_stream_chunk = std::max(1, (int)pj.get_int("stream_chunk", 1));
       g_stop_default = pj.get_int("stop_at_eos", 0) != 0;
       g_eos_every = std::max(1, (int)pj.get_int("eos_check_every", 16));
-      auto take_eos = [](const Json* v) {
+      // .spec.params is map[string]IntOrString (api/v1/server_types.go:30): params.json may say "eos_token_id": "2"
+      auto one_eos = [](const Json& x) {
+        if (x.kind == Json::Num) g_eos.push_back((int32_t)x.num);
+        if (x.kind == Json::Str && !x.str.empty()) {
+          char* end = nullptr;
+          const long v = strtol(x.str.c_str(), &end, 10);
+          if (end && *end == 0 && v >= 0) g_eos.push_back((int32_t)v);
+        }
+      };
+      auto take_eos = [&](const Json* v) {
         if (!v) return;
-        if (v->kind == Json::Num) g_eos.push_back((int32_t)v->num);
         if (v->kind == Json::Arr)
-          for (auto& x : v->arr)
-            if (x.kind == Json::Num) g_eos.push_back((int32_t)x.num);
+          for (auto& x : v->arr) one_eos(x);
+        else
+          one_eos(*v);
       };
       take_eos(pj.find("eos_token_id"));
       for (const char* f : {"/generation_config.json", "/config.json"}) {

@@ -75,6 +75,30 @@ SSB_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_de
 
 SSB_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// ---------------------------------------------------------------- bounded cross-GPU waits
+// Every spin on a flag another GPU has to write goes through SpinGuard::poll(): after SSB_SPIN_TIMEOUT_NS (20 s) of
+// polling the kernel traps instead of hanging.  A peer rank that died (or a protocol bug) then surfaces on the host as a
+// sticky CUDA error -> SSB_ECUDA -> the serve host exits non-zero and the Deployment restarts the pod
+// (internal/controller/server_controller.go:280-296 turns that into Serving=False), instead of every later request
+// blocking behind a kernel that never returns.  The clock is read once per 1024 polls, so the poll loop stays tight.
+#ifndef SSB_SPIN_TIMEOUT_NS
+#define SSB_SPIN_TIMEOUT_NS 20000000000ull
+#endif
+struct SpinGuard {
+  unsigned long long t0 = 0;
+  unsigned n = 0;
+  SSB_DEVINL void poll() {
+    if ((++n & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0)
+        t0 = now;
+      else if (now - t0 > SSB_SPIN_TIMEOUT_NS)
+        __trap();
+    }
+  }
+};
+
 // ---------------------------------------------------------------- warp reductions
 SSB_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -783,13 +783,12 @@ __global__ void __launch_bounds__(TP_THREADS) tp_allreduce_resid_kernel(const Tp
   }
   if (threadIdx.x < a.size && threadIdx.x != a.rank) {
     const uint32_t* f = a.peer_flags[a.rank] + threadIdx.x;
+    SpinGuard sg;
     if (a.variant & 2) {
-      while ((int32_t)(ld_relaxed_sys_u32(f) - epoch) < 0) {
-      }
+      while ((int32_t)(ld_relaxed_sys_u32(f) - epoch) < 0) sg.poll();
       __threadfence_system();
     } else {
-      while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-      }
+      while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) sg.poll();
     }
   }
   __syncthreads();
@@ -828,7 +827,9 @@ __global__ void __launch_bounds__(TP_THREADS) tp_reduce_push_kernel(const TpPush
   if (threadIdx.x < a.size) {
     const unsigned long long* f = a.flags + threadIdx.x;
     unsigned long long v;
+    SpinGuard sg;
     do {
+      sg.poll();
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
     } while (v < target);
   }

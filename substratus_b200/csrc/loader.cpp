@@ -136,10 +136,28 @@ bool ModelFiles::open_safetensors(const std::string& path, std::string* err) {
       *err = path + ": malformed entry " + kv.first;
       return false;
     }
-    for (auto& d : sh->arr) v.shape.push_back((int64_t)d.num);
+    if (sh->kind != Json::Arr) {
+      *err = path + ": shape of " + kv.first + " is not an array";
+      return false;
+    }
+    uint64_t numel = 1;
+    for (auto& d : sh->arr) {
+      if (d.kind != Json::Num || d.num < 0 || d.num != (double)(int64_t)d.num || (d.num > 0 && numel > (1ull << 48) / (uint64_t)d.num)) {
+        *err = path + ": bad dimension in the shape of " + kv.first;
+        return false;
+      }
+      v.shape.push_back((int64_t)d.num);
+      numel *= (uint64_t)d.num;
+    }
     uint64_t b = (uint64_t)off->arr[0].num, e = (uint64_t)off->arr[1].num;
     if (e < b || e > avail) {
       *err = path + ": data_offsets out of range for " + kv.first;
+      return false;
+    }
+    // a truncated or corrupt shard must fail here (SSB_EIO), not as a device-side read past the staging buffer
+    const uint64_t esz = v.dtype == DT_F32 ? 4 : (v.dtype == DT_BF16 || v.dtype == DT_F16) ? 2 : 0;
+    if (esz && numel * esz != e - b) {
+      *err = path + ": " + kv.first + " stores " + std::to_string(e - b) + " bytes but its shape and dtype need " + std::to_string(numel * esz);
       return false;
     }
     v.data = base + b;

@@ -523,8 +523,8 @@ SSB_DEVINL void tp_reduce_phase(const MegaArgs& a, int seq, int tid) {
   }
   if (tid < a.tp_size && tid != a.tp_rank) {
     const uint32_t* f = a.peer_flags[a.tp_rank] + tid;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    SpinGuard sg;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) sg.poll();
   }
   named_bar_sync(1, MG_CW * 32);
   const int total4 = a.M * a.hidden / 4;
@@ -568,8 +568,8 @@ SSB_DEVINL void tp_reduce_cta(const MegaArgs& a, int seq, int tid) {
     __threadfence_system();
     st_release_sys(a.peer_cta_flags[tid] + (size_t)a.tp_rank * MG_CTA_FLAG_STRIDE + blockIdx.x, epoch);
     const uint32_t* f = a.peer_cta_flags[a.tp_rank] + (size_t)tid * MG_CTA_FLAG_STRIDE + blockIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    SpinGuard sg;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) sg.poll();
   }
   named_bar_sync(1, MG_CW * 32);
   const int P = a.hidden >> 1;
@@ -602,6 +602,7 @@ SSB_DEVINL void tp_reduce_ll(const MegaArgs& a, int seq, uint32_t epoch, int tid
   const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
   const int np = p1 - p0;
   const uint4* base = a.peer_ll[a.tp_rank] + (size_t)(seq & 1) * (size_t)a.ll_parity_stride;
+  SpinGuard sg;
   for (int i = tid; i < a.M * np; i += MG_CW * 32) {
     const int m = i / np, p = p0 + (i - m * np);
     float2 s = make_float2(0.f, 0.f);
@@ -609,10 +610,11 @@ SSB_DEVINL void tp_reduce_ll(const MegaArgs& a, int seq, uint32_t epoch, int tid
     for (int r = 0; r < TP_MAX; ++r) {
       if (r < a.tp_size) {
         const uint4* slot = base + (size_t)r * (size_t)a.ll_src_stride + (size_t)m * P + p;
-        uint4 v;
-        do {
+        uint4 v = ld_relaxed_sys_v4(slot);
+        while (v.y != epoch || v.w != epoch) {
+          sg.poll();
           v = ld_relaxed_sys_v4(slot);
-        } while (v.y != epoch || v.w != epoch);
+        }
         s.x += __uint_as_float(v.x);
         s.y += __uint_as_float(v.z);
       }

@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(T2_THREADS) tp_allreduce2_kernel(const TpArgs2
   }
   if (tid < a.size && tid != a.rank) {
     const uint32_t* f = a.peer_flags[a.rank] + tid;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    SpinGuard sg;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) sg.poll();
   }
   __syncthreads();
   // ---- B: reduce my slice (flattened [M*hidden/4) float4 index space, contiguous per rank)
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(T2_THREADS) tp_allreduce2_kernel(const TpArgs2
   // ---- C: gather the peers' slices
   if (tid < a.size && tid != a.rank) {
     const uint32_t* f = a.peer_flags[a.rank] + T2_MAX + tid;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-    }
+    SpinGuard sg;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) sg.poll();
   }
   __syncthreads();
   for (int p = 0; p < a.size; ++p) {

@@ -38,6 +38,7 @@ static void fake_logits(uint64_t s, int vocab, float* out) {
 
 struct ssb_engine {
   int vocab = 1000, max_batch = 32, max_seq_len = 4096, tp_size = 1, tp_rank = 0;
+  int fail_code = SSB_ECUDA;  // "fake_fail_code": what the failing decode returns (SSB_ECUDA = the device is gone)
   int step_us = 0, fail_after = -1;  // "fake_step_us": sleep per decode step; "fake_fail_after": decode calls before an error
   bool connected = false;
   std::mutex mu;
@@ -64,6 +65,7 @@ int ssb_engine_create(const char* model_dir, const char* params_json, ssb_engine
     e->tp_rank = (int)pj.get_int("tp_rank", 0);
     e->step_us = (int)pj.get_int("fake_step_us", 0);
     e->fail_after = (int)pj.get_int("fake_fail_after", -1);
+    e->fail_code = (int)pj.get_int("fake_fail_code", SSB_ECUDA);
     const int load_ms = (int)pj.get_int("fake_load_ms", 0);
     if (load_ms > 0) std::this_thread::sleep_for(std::chrono::milliseconds(load_ms));
     if (pj.get_int("fake_load_error", 0) != 0) {
@@ -136,7 +138,7 @@ int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int n
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->fail_after >= 0 && e->decode_calls >= e->fail_after) {
     g_err = "fake: decode failure requested";
-    return SSB_ECUDA;
+    return e->fail_code;
   }
   ++e->decode_calls;
   for (int i = 0; i < nseq; ++i) {

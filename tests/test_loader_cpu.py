@@ -77,6 +77,22 @@ def test_safetensors_inventory_errors(tmp_path, lib):
     assert _create(tmp_path / "d").code == EIO
     open(tmp_path / "d" / "model.safetensors", "wb").write(struct.pack("<Q", 1 << 40) + raw[8:64])  # absurd header length
     assert _create(tmp_path / "d").code == EIO
+    # header claims a [512, 256] bf16 tensor but the offsets cover half of it: a corrupt shard must be an EIO here, not a
+    # device-side read past the staging buffer
+    hlen = struct.unpack("<Q", raw[:8])[0]
+    hdr = json.loads(raw[8:8 + hlen])
+    name = "model.embed_tokens.weight"
+    b, e_ = hdr[name]["data_offsets"]
+    hdr[name]["data_offsets"] = [b, b + (e_ - b) // 2]
+    nh = json.dumps(hdr).encode()
+    open(tmp_path / "d" / "model.safetensors", "wb").write(struct.pack("<Q", len(nh)) + nh + raw[8 + hlen:])
+    e = _create(tmp_path / "d")
+    assert e.code == EIO and "shape and dtype need" in str(e)
+    hdr[name]["data_offsets"] = [b, e_]
+    hdr[name]["shape"] = [-4, 256]
+    nh = json.dumps(hdr).encode()
+    open(tmp_path / "d" / "model.safetensors", "wb").write(struct.pack("<Q", len(nh)) + nh + raw[8 + hlen:])
+    assert _create(tmp_path / "d").code == EIO
     os.remove(tmp_path / "d" / "model.safetensors")
     e = _create(tmp_path / "d")
     assert e.code == EIO and "safetensors" in str(e)

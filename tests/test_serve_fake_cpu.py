@@ -209,13 +209,56 @@ def test_stream_text_is_the_plain_text_cut_at_utf8_boundaries(serve_fake, tmp_pa
 
 
 def test_decode_failure_is_reported(serve_fake, tmp_path):
-    with Server(serve_fake, tmp_path, {"fake_fail_after": 2}) as s:
+    # a per-request failure (here: the engine says ENOMEM, e.g. the KV pool is exhausted) is answered and the pod lives on
+    with Server(serve_fake, tmp_path, {"fake_fail_after": 2, "fake_fail_code": -4}) as s:
         s.wait_ready()
         ev = _sse(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 8, "stream": True})
         assert ev[-1] == "[DONE]" and "decode failure" in ev[-2]["error"] and len(ev) == 3 + 2  # first token + 2 good chunks
         code, r = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 8})
         assert code == 500 and "decode failure" in r["error"]
         assert "ssb_errors_total 2" in _req(s.port, "/metrics")[1]
+        assert _req(s.port, "/")[0] == 200 and s.p.poll() is None
+
+
+@pytest.mark.parametrize("params", [{}, {"tp_size": 2}])
+def test_device_failure_answers_then_exits_nonzero(serve_fake, tmp_path, params):
+    """a sticky device error (SSB_ECUDA) must not leave a ready-looking pod behind: the request is answered with
+    the error, then the process exits non-zero so the Deployment restarts it (server_controller.go:280-296).  Same with
+    the in-container tensor-parallel rank threads, where a healthy rank would otherwise wait for the dead one."""
+    with Server(serve_fake, tmp_path, dict(params, fake_fail_after=0)) as s:
+        s.wait_ready()
+        try:
+            code, r = _req(s.port, "/generate", {"tokens": [1, 2], "max_new_tokens": 8, "stop_at_eos": False, "temperature": 0})
+            assert code == 500 and "decode failure" in r["error"]
+        except (urllib.error.URLError, ConnectionError, json.JSONDecodeError):
+            pass  # TP: a rank thread may take the process down before the response is written
+        assert s.p.wait(timeout=10) == 1
+        assert "fatal engine error" in s.p.stderr.read()
+
+
+def test_slow_and_oversized_clients_are_bounded(serve_fake, tmp_path):
+    """body capped from max_seq_len (413), a header that merely CONTAINS 'content-length:' is not the length,
+    params.json eos ids may be strings (IntOrString)."""
+    with Server(serve_fake, tmp_path, {"fake_vocab": 100, "max_seq_len": 64, "eos_token_id": "7", "stop_at_eos": 0}) as s:
+        s.wait_ready()
+        c = socket.create_connection(("127.0.0.1", s.port))  # announce 3 MiB, send nothing: refused from the header alone
+        c.sendall(b"POST /generate HTTP/1.1\r\nHost: x\r\nContent-Length: 3145728\r\n\r\n")
+        assert c.recv(65536).startswith(b"HTTP/1.1 413")
+        c.close()
+        body = json.dumps({"tokens": [1, 2, 3], "max_new_tokens": 4}).encode()
+        c = socket.create_connection(("127.0.0.1", s.port))
+        c.sendall(b"POST /generate HTTP/1.1\r\nHost: x\r\nX-Content-Length: 3\r\nContent-Length: " + str(len(body)).encode() + b"\r\n\r\n" + body)
+        resp = b""
+        while True:
+            chunk = c.recv(65536)
+            if not chunk:
+                break
+            resp += chunk
+        c.close()
+        assert resp.startswith(b"HTTP/1.1 200") and json.loads(resp.split(b"\r\n\r\n", 1)[1])["tokens"] == fake_generate([1, 2, 3], 4, 100)
+        # a string-valued eos id in params.json is honoured: stop_at_eos requests are accepted (400 before the fix)
+        code, r = _req(s.port, "/generate", {"tokens": [1, 2, 3], "max_new_tokens": 20, "stop_at_eos": True})
+        assert code == 200 and 7 not in r["tokens"]
 
 
 @pytest.mark.parametrize("stream", [False, True])
