@@ -626,6 +626,8 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
       tc_min_rows_ = (int)params.get_int("tc_min_rows", 8);
     else
       RET(SSB_EINVAL, "params.gemm_path must be auto|gemv|tc");
+    tc_tn_prefill_ = (int)params.get_int("tc_tn_prefill", 0);  // 0 = per-projection heuristic; 128 | 256 force (tests, A/B)
+    if (tc_tn_prefill_ != 0 && tc_tn_prefill_ != 128 && tc_tn_prefill_ != 256) RET(SSB_EINVAL, "params.tc_tn_prefill must be 0, 128 or 256");
     const int h = cfg_.hidden, D = cfg_.head_dim, br = tc_weight_box_rows();
     for (auto& w : lw_) {
       CK(tc_make_tmap(&w.tm_qkv, w.wqkv, (int64_t)(Hl_ + 2 * KVHl_) * D, h, h, br));
@@ -790,11 +792,15 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
   // projections: CUDA-core GEMV (weights streamed once, M <= 4 rows per pass) or tcgen05 GEMM (tokens = UMMA N)
   const bool tc = M >= tc_min_rows_;
   const int tn = tc_pick_tn(M);
-  TcTensorMap tm_xn, tm_attn, tm_act;
+  // token-tile width per projection (prefill-sized forwards only differ): the activation tensor map's box follows it
+  auto pick = [&](int N) { return (tc_tn_prefill_ && M > 128) ? tc_tn_prefill_ : tc_pick_tn_prefill(M, N, n_sm_); };
+  const int tn_qkv = pick((Hl_ + 2 * KVHl_) * D), tn_o = pick(h), tn_gu = pick(2 * Il_), tn_down = tn_o;
+  TcTensorMap tm_xn, tm_xn_gu, tm_attn, tm_act;
   if (tc) {
-    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn));
-    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn));
-    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn));
+    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn_qkv));
+    CK(tc_make_tmap(&tm_xn_gu, xn_, M, h, h, tn_gu));
+    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn_o));
+    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn_down));
   }
   for (int l = 0; l < cfg_.layers; ++l) {
     const LayerW& w = lw_[l];
@@ -823,7 +829,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     if (tc) {
       CK(launch_rmsnorm(h_, w.ln1, xn_, M, h, cfg_.eps, lc(true)));
       prof_mark("norm");
-      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn, g, EPI_QKV_ROPE, lc(true)));
+      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn_qkv, g, EPI_QKV_ROPE, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(g, EPI_QKV_ROPE, NORM_RMS, lc(true)));
@@ -877,7 +883,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     if (tp) o.out_f32 = tp_partials_ + (size_t)((2 * l) & 1) * m_max_ * h;
     if (tp_push) set_push(o, 2 * l);
     if (tc)
-      CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_rowpar, lc(true)));
+      CK(launch_tc_gemm(w.tm_o, tm_attn, tn_o, o, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(o, epi_rowpar, NORM_NONE, lc(true)));
     prof_mark("o");
@@ -909,7 +915,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     if (tc) {
       CK(launch_rmsnorm(h_, w.ln2, xn_, M, h, cfg_.eps, lc(true)));
       prof_mark("norm");
-      CK(launch_tc_gemm(w.tm_gu, tm_xn, tn, u, EPI_SWIGLU, lc(true)));
+      CK(launch_tc_gemm(w.tm_gu, tm_xn_gu, tn_gu, u, EPI_SWIGLU, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(u, EPI_SWIGLU, NORM_RMS, lc(true)));
@@ -929,7 +935,7 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     if (tp) d.out_f32 = tp_partials_ + (size_t)((2 * l + 1) & 1) * m_max_ * h;
     if (tp_push) set_push(d, 2 * l + 1);
     if (tc)
-      CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_rowpar, lc(true)));
+      CK(launch_tc_gemm(w.tm_down, tm_act, tn_down, d, epi_rowpar, lc(true)));
     else
       CK(launch_gemv(d, epi_rowpar, NORM_NONE, lc(true)));
     prof_mark("down");
@@ -1091,12 +1097,14 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
   ++launches;
   const int n_splits = (M <= max_batch_) ? decode_splits_(M) : 1;
   const bool tc = M >= tc_min_rows_;
-  const int tn = tc_pick_tn(M);
-  TcTensorMap tm_xn, tm_attn, tm_act;
+  auto pick = [&](int N) { return (tc_tn_prefill_ && M > 128) ? tc_tn_prefill_ : tc_pick_tn_prefill(M, N, n_sm_); };
+  const int tn_qkv = pick((Hl_ + 2 * KVHl_) * D), tn_o = pick(h), tn_gu = pick(Il_), tn_down = tn_o;
+  TcTensorMap tm_xn, tm_xn_gu, tm_attn, tm_act;
   if (tc) {
-    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn));
-    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn));
-    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn));
+    CK(tc_make_tmap(&tm_xn, xn_, M, h, h, tn_qkv));
+    CK(tc_make_tmap(&tm_xn_gu, xn_, M, h, h, tn_gu));
+    CK(tc_make_tmap(&tm_attn, attn_, M, (int64_t)Hl_ * D, (int64_t)Hl_ * D, tn_o));
+    CK(tc_make_tmap(&tm_act, act_, M, Il_, Il_, tn_down));
   }
   TpArgs ta = {};
   if (tp) {
@@ -1140,7 +1148,7 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     g.kvh = KVHl_;
     if (tc) {
       CK(launch_layernorm(h_, w.ln1, w.ln1_b, xn_, M, h, cfg_.eps, lc(true)));
-      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn, g, EPI_QKV_ROPE, lc(true)));
+      CK(launch_tc_gemm(w.tm_qkv, tm_xn, tn_qkv, g, EPI_QKV_ROPE, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(g, EPI_QKV_ROPE, NORM_LN, lc(true)));
@@ -1190,7 +1198,7 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     if (tp) o.out_f32 = part_attn;
     const int epi_o = tp ? EPI_F32 : EPI_BF16;
     if (tc)
-      CK(launch_tc_gemm(w.tm_o, tm_attn, tn, o, epi_o, lc(true)));
+      CK(launch_tc_gemm(w.tm_o, tm_attn, tn_o, o, epi_o, lc(true)));
     else
       CK(launch_gemv(o, epi_o, NORM_NONE, lc(true)));
     // MLP branch on LN_mlp(x)
@@ -1208,7 +1216,7 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     u.ld_out = Il_;
     if (tc) {
       CK(launch_layernorm(h_, w.ln2, w.ln2_b, xn_, M, h, cfg_.eps, lc(true)));
-      CK(launch_tc_gemm(w.tm_gu, tm_xn, tn, u, EPI_GELU, lc(true)));
+      CK(launch_tc_gemm(w.tm_gu, tm_xn_gu, tn_gu, u, EPI_GELU, lc(true)));
       ++launches;
     } else {
       CK(launch_gemv(u, EPI_GELU, NORM_LN, lc(true)));
@@ -1230,7 +1238,7 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     }
     const int epi_d = tp ? EPI_F32 : EPI_RESID2;
     if (tc)
-      CK(launch_tc_gemm(w.tm_down, tm_act, tn, d, epi_d, lc(true)));
+      CK(launch_tc_gemm(w.tm_down, tm_act, tn_down, d, epi_d, lc(true)));
     else
       CK(launch_gemv(d, epi_d, NORM_NONE, lc(true)));
     launches += 5;

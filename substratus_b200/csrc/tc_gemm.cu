@@ -5,7 +5,7 @@
 // computed transposed so the WEIGHT rows ride the 128 TMEM lanes:  D[128 weight rows, TN tokens] += A * B^T with
 //   A = W tile  [128 x 64]  (K-major, TMA 128B-swizzled)      -> UMMA M = 128
 //   B = X tile  [TN  x 64]  (K-major, TMA 128B-swizzled)      -> UMMA N = TN (16..256)
-// Tokens are the UMMA N dimension, so the same kernel serves prefill (TN = 128/256, tensor-pipe bound) and batched
+// Tokens are the UMMA N dimension, so the same kernel serves prefill (TN = 128 / 256, tensor-pipe bound) and batched
 // decode (TN = 16/32, HBM bound: weights stream HBM -> TMA -> smem -> tensor core without touching registers).
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> fused RoPE/KV-append | SwiGLU | residual, same math as gemv_epilogue).
@@ -481,7 +481,20 @@ cudaError_t tc_make_tmap(TcTensorMap* out, const bf16* ptr, int64_t rows, int64_
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Token-tile width (UMMA N).  Decode-sized forwards: the smallest tile that holds the batch (stream-K kernel).
 int tc_pick_tn(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
+// Prefill-sized forwards choose per projection between 128- and 256-token tiles.  A 128 x 256 tile ingests 48 KiB of
+// operands per k-block for twice the FLOPs of a 128 x 128 tile's 32 KiB (87 vs 64 FLOP per byte through the L2 -> SM path
+// that bounds this kernel, profiles/r01_tcgen05_ncu_summary.txt: tensor pipe 21-36 % active) and halves the re-reads of a
+// weight tile (one read per token tile) — but it also halves the tile count, and the persistent grid runs whole waves:
+// pick the width with the smaller  waves x per-tile cost  (cost 1.0 vs 1.5, the operand bytes), 128 on a tie.
+int tc_pick_tn_prefill(int M, int N, int n_sm) {
+  if (M <= 128) return tc_pick_tn(M);
+  const long long nt = (N + TC_BM - 1) / TC_BM;
+  const long long t128 = nt * ((M + 127) / 128), t256 = nt * ((M + 255) / 256);
+  const long long w128 = (t128 + n_sm - 1) / n_sm, w256 = (t256 + n_sm - 1) / n_sm;
+  return 3 * w256 < 2 * w128 ? 256 : 128;
+}
 int tc_weight_box_rows() { return TC_BM; }
 
 template <int TN, int EPI>
@@ -514,6 +527,7 @@ static cudaError_t launch_tc_e(int tn, const TcTensorMap& tmA, const TcTensorMap
     case 32: return launch_tc_t<32, EPI>(tmA, tmB, a, lc);
     case 64: return launch_tc_t<64, EPI>(tmA, tmB, a, lc);
     case 128: return launch_tc_t<128, EPI>(tmA, tmB, a, lc);
+    case 256: return launch_tc_t<256, EPI>(tmA, tmB, a, lc);
   }
   return cudaErrorInvalidValue;
 }

@@ -9,6 +9,7 @@ struct alignas(64) TcTensorMap {
 // 2-D K-major bf16 tensor map over global [rows, cols] (row pitch ld elements); TMA box = [box_rows, 64], 128B swizzle
 cudaError_t tc_make_tmap(TcTensorMap* out, const bf16* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int tc_pick_tn(int M);          // token-tile width (UMMA N) for M token rows: 16 | 32 | 64 | 128
+int tc_pick_tn_prefill(int M, int N, int n_sm);  // per projection [N out rows]: 128 | 256 above 128 token rows (waves x tile cost)
 int tc_weight_box_rows();       // 128
 // Y = X * W^T with the fused epilogue `epi` (GemvEpi); tmA = weights (box 128 rows), tmB = activations (box tn rows)
 cudaError_t launch_tc_gemm(const TcTensorMap& tmA, const TcTensorMap& tmB, int tn, const GemvArgs& a, int epi, const LaunchCfg& lc);

@@ -216,6 +216,28 @@ def test_chunked_prefill_and_block_boundaries(Engine, tmp_path):
     assert ok and exact >= 1, msg
 
 
+def test_prefill_256_token_tiles(Engine, tmp_path):
+    """128 x 256 tcgen05 tiles (UMMA N = 256, both accumulators = all 512 TMEM columns) against 128 x 128 tiles and the
+    oracle: 300- and 257-token prompts (ragged second tile, OOB rows zero-filled), K tail (I = 1376 = 21.5 k-blocks)."""
+    cfg = synth.TINY_GQA
+    sd = synth.llama_state_dict(cfg, 19)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(12)
+    prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (300, 257)]
+    res = {}
+    for tn in (128, 256):
+        with Engine(str(tmp_path), {"max_batch": 4, "max_seq_len": 320, "gemm_path": "tc", "tc_tn_prefill": tn, "prefill_chunk": 1024}) as e:
+            res[tn] = e.generate(prompts, 3, want_logits=True)
+    err = rel_err(res[256][1], res[128][1])
+    _diag(f"[prefill tn256 vs tn128] logits rel err {err:.3e}; tokens equal: {np.array_equal(res[256][0], res[128][0])}")
+    assert err < 1e-2, err
+    l32 = _teacher_forced_logits(cfg, sd, torch.float32, prompts, res[256][0])
+    lbf = _teacher_forced_logits(cfg, sd, torch.bfloat16, prompts, res[256][0])
+    lg = np.transpose(res[256][1], (1, 0, 2))
+    _assert_parity([[rel_err(lg[i, s_], l32[i, s_]) for s_ in range(3)] for i in range(2)],
+                   [[rel_err(lbf[i, s_], l32[i, s_]) for s_ in range(3)] for i in range(2)], "prefill 256-token tiles")
+
+
 def test_errors_and_slot_reuse(Engine, tmp_path):
     from substratus_b200 import SsbError
 
