@@ -826,7 +826,7 @@ def main():
 
 
 # engine default for "tp_mega" under tensor parallelism (csrc/engine.cu): 3 = persistent kernel with the push exchange
-TP_MEGA_DEFAULT = 0
+TP_MEGA_DEFAULT = 3
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch (ncu --set full, profiles/)
 MEGA_TRAFFIC_BYTES = {("llama2-7b", 1, 1): 13.494e9}
 

@@ -463,7 +463,10 @@ int Engine::alloc_runtime(const Json& params) {
       TRY(dmalloc(&tp2_done_, 1));
       CK(cudaMemset(tp2_done_, 0, sizeof(unsigned)));
     }
-    tp_mega_mode_ = D == 128 && !cfg_.falcon ? (int)params.get_int("tp_mega", 0) : 0;
+    // decode under tensor parallelism: 3 (default) = the persistent kernel with the 16-byte {value, epoch} push exchange
+    // (measured on 2 x B200, Llama-2-7B: 512 tok/s vs 428 for the multi-kernel path "tp_mega": 0, 436 / 395 for the
+    // flag + pull variants 1 / 2 — profiles/r02_tp_bench_n2.jsonl); Llama-family head size only
+    tp_mega_mode_ = D == 128 && !cfg_.falcon ? (int)params.get_int("tp_mega", 3) : 0;
     if (tp_mega_mode_ == 2) {
       tp_off_ctaflags_ = tp_pool_bytes_;
       tp_pool_bytes_ += 8 * 256 * sizeof(uint32_t);
@@ -535,9 +538,8 @@ int Engine::alloc_runtime(const Json& params) {
     }
   }
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
-  // under tensor parallelism the persistent kernel is opt-in ("tp_mega": 1): its in-kernel allreduce (mega.h) was
-  // written after the last multi-GPU session and has not run on hardware yet
-  const bool tp_mega = tp_size_ > 1 && params.get_int("tp_mega", 0) != 0 && D == 128;
+  // under tensor parallelism the persistent kernel carries the allreduce itself ("tp_mega", see above; 0 = multi-kernel path)
+  const bool tp_mega = tp_size_ > 1 && tp_mega_mode_ != 0;
   use_mega_ = params.get_int("use_mega", 1) != 0 && (tp_size_ == 1 || tp_mega) && !cfg_.falcon && !prof_fwd_;
   if (use_mega_) {
     const int group = cfg_.heads / cfg_.kv_heads, ag = mega_attn_group(group);
@@ -558,9 +560,11 @@ int Engine::alloc_runtime(const Json& params) {
       TRY(dmalloc(&mega_part_ml_, units * ag * 2));
       TRY(dmalloc(&mega_counters_, (size_t)4 * Hl_));
       CK(cudaMemset(mega_counters_, 0, (size_t)4 * Hl_ * sizeof(int)));
-      if (params.get_int("mega_prof", 0)) {
-        TRY(dmalloc(&mega_prof_, 1024));
-        CK(cudaMemset(mega_prof_, 0, 1024 * sizeof(unsigned long long)));
+      if (params.get_int("mega_prof", 0)) {  // 1: CTA 0 stamps its phases; 2: every CTA does (arrival skew across the SMs)
+        mega_prof_all_ = params.get_int("mega_prof", 0) >= 2;
+        const size_t n = mega_prof_all_ ? (size_t)n_sm_ * 1024 : 1024;
+        TRY(dmalloc(&mega_prof_, n));
+        CK(cudaMemset(mega_prof_, 0, n * sizeof(unsigned long long)));
       }
       TRY(dmalloc(&mega_bar_, 1024));  // [0] barrier counter, [1] exit counter, [32 + 32 g] group counters of the tree-barrier experiment
       CK(cudaMemset(mega_bar_, 0, 1024 * sizeof(unsigned)));
@@ -626,6 +630,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
       tc_min_rows_ = (int)params.get_int("tc_min_rows", 8);
     else
       RET(SSB_EINVAL, "params.gemm_path must be auto|gemv|tc");
+    mega_attn_tile_ = params.get_int("mega_attn_tile", 1) != 0;
     tc_tn_prefill_ = (int)params.get_int("tc_tn_prefill", 0);  // 0 = per-projection heuristic; 128 | 256 force (tests, A/B)
     if (tc_tn_prefill_ != 0 && tc_tn_prefill_ != 128 && tc_tn_prefill_ != 256) RET(SSB_EINVAL, "params.tc_tn_prefill must be 0, 128 or 256");
     const int h = cfg_.hidden, D = cfg_.head_dim, br = tc_weight_box_rows();
@@ -1319,7 +1324,12 @@ int Engine::forward_mega(int B) {
   a.grid_bar = mega_bar_;
   a.k_max = mega_k_max_;
   a.prof = mega_prof_;
+  a.prof_all = mega_prof_all_ ? 1 : 0;
+  if (mega_prof_all_) CK(cudaMemsetAsync(mega_prof_, 0, (size_t)n_sm_ * 1024 * sizeof(unsigned long long), stream_));
   a.n_stages = mega_pick_stages(B == 1 ? 1 : (B == 2 ? 2 : 4), mega_k_max_);
+  // GQA groups of 8: CTA-tile attention when the K/V tile fits the activation staging area (params "mega_attn_tile": 0 = off)
+  a.attn_cta_tile = (a.attn_g == 8 && mega_attn_tile_ &&
+                     (size_t)(B == 1 ? 1 : (B == 2 ? 2 : 4)) * mega_k_max_ * sizeof(bf16) >= mega_attn_tile_bytes(D)) ? 1 : 0;
   if (a.n_stages == 0) RET(SSB_EINVAL, "decode step does not fit the persistent kernel's shared memory");
   if (tp_size_ > 1) {  // "tp_mega": allreduce inside the kernel, same exchange pool / epochs as launch_tp_allreduce_resid
     a.tp_size = tp_size_;
@@ -1720,6 +1730,24 @@ void Engine::timing_reset() { timing_ = ssb_timing{}; }
 
 int Engine::debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols) {
   const std::string nm = name ? name : "";
+  if (nm == "mega_prof_all") {  // [n_ctas][1024]: per-CTA phase stamps of the LAST step in us from the earliest one; column 1023 = %smid
+    if (!mega_prof_ || !mega_prof_all_) RET(SSB_ESTATE, "engine was not created with params.mega_prof=2");
+    if (n < (int64_t)n_sm_ * 1024) RET(SSB_EINVAL, "destination too small");
+    CK(cudaSetDevice(device_));
+    std::vector<unsigned long long> t((size_t)n_sm_ * 1024);
+    CK(cudaMemcpy(t.data(), mega_prof_, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < n_sm_; ++c)
+      if (t[(size_t)c * 1024] && t[(size_t)c * 1024] < t0) t0 = t[(size_t)c * 1024];
+    for (int c = 0; c < n_sm_; ++c)
+      for (int i = 0; i < 1024; ++i) {
+        const unsigned long long v = t[(size_t)c * 1024 + i];
+        dst[(size_t)c * 1024 + i] = i == 1023 ? (float)v : (v ? (float)((double)(v - t0) * 1e-3) : -1.0f);
+      }
+    *rows = n_sm_;
+    *cols = 1024;
+    return SSB_OK;
+  }
   if (nm == "mega_prof") {  // phase timestamps of CTA 0 of the LAST persistent decode step, in microseconds from its start
     if (!mega_prof_) RET(SSB_ESTATE, "engine was not created with params.mega_prof=1");
     if (n < 1024) RET(SSB_EINVAL, "destination too small");

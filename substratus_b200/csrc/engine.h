@@ -92,6 +92,8 @@ class Engine {
   int* mega_counters_ = nullptr;
   unsigned* mega_bar_ = nullptr;
   unsigned long long* mega_prof_ = nullptr;
+  bool mega_prof_all_ = false;
+  bool mega_attn_tile_ = true;
   int mega_max_chunks_ = 0, mega_k_max_ = 0;
   int tc_tn_prefill_ = 0;  // params "tc_tn_prefill": force the prefill token-tile width (0 = heuristic)
   int tc_min_rows_ = 8;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)

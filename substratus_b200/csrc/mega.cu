@@ -43,19 +43,20 @@ SSB_DEVINL unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define MG_STAMP()                                                          \
-  do {                                                                      \
-    if (a.prof && blockIdx.x == 0 && tid == 0 && n_prof < 1024) a.prof[n_prof++] = gtimer(); \
+#define MG_STAMP()                                                                                                  \
+  do {                                                                                                              \
+    if (a.prof && (blockIdx.x == 0 || a.prof_all) && tid == 0 && n_prof < 1023)                                     \
+      a.prof[(a.prof_all ? (size_t)blockIdx.x * 1024 : 0) + n_prof++] = gtimer();                                   \
   } while (0)
 
 // grid-wide barrier among the consumer threads of all CTAs (the producer warp does not take part)
-// MG_SYNC_LIGHT=1 (compile-time experiment for round 2, `make NVFLAGS+=-DMG_SYNC_LIGHT=1`; never run on hardware):
+// MG_SYNC_LIGHT=1 (default since round 2; 0 = the fence + atomicAdd + fence form of round 1):
 // arrive with ONE release-reduction instead of fence.sc + atomic, leave through the acquire load alone.  The CTA barrier
 // before it makes the other consumer threads' writes visible to thread 0, whose gpu-scope release is cumulative; the
 // CTA barrier after the acquire hands the observed writes on to them.  160 barriers per 7B token, so every 0.1 us
 // saved per barrier is 0.5 % of the step.
 #ifndef MG_SYNC_LIGHT
-#define MG_SYNC_LIGHT 0
+#define MG_SYNC_LIGHT 1  // round 2, measured on B200: 1.42 us vs 1.71 us per barrier in isolation (tools/ubench_gridbar), +1.5 % decode tokens/s, bit-identical
 #endif
 // MG_SYNC_TREE=1 (compile-time experiment, variant library "synctree"; never run on hardware): two-level arrival.
 // 148 CTAs adding to ONE L2 address serialise (the microarchitecture notes give ~27 clk per same-address atomic from
@@ -108,15 +109,17 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
   named_bar_sync(1, MG_CW * 32);
 }
 
-// MG_L2_AHEAD=N (compile-time experiment, variant library "l2ahead"; never run on hardware): the shared-memory ring holds
-// 192 KiB = 4.3 us of this SM's HBM share, but the gap QKV -> barrier -> attention -> barrier -> x staging is ~16 us, so
-// HBM idles for most of it.  With N > 0 every producer warp walks the SAME weight stream a second time, N ring fills
-// ahead of its copies, issuing `cp.async.bulk.prefetch.L2` for the rows it will copy later: while the ring is full the
-// next N x 32 KiB per SM (N = 10: 47 MB chip-wide, L2 is 126 MB) keep streaming HBM -> L2, and the later bulk copies
-// hit L2, which an SM can drain at twice its HBM share.  Prefetches change no result (bit-identity gate applies).
-#ifndef MG_L2_AHEAD
-#define MG_L2_AHEAD 0
-#endif
+// MG_L2_AHEAD = N (default 14; 0 disables): stall-driven L2 lookahead.  The shared-memory ring holds 192 KiB = 4.3 us of
+// this SM's HBM share, but the consumers stop taking weights for ~18 us per layer around the attention phase (QKV ->
+// barrier -> attention -> barrier -> staging) and for 3-7 us at every other barrier, so HBM used to idle ~18 us of an
+// 85 us layer (round-2 phase timeline, profiles/r02_*).  Now a producer warp that finds the ring full does not just wait:
+// while the `empty` barrier has not flipped it walks the SAME weight stream ahead of its copies and issues
+// `cp.async.bulk.prefetch.L2` for the rows it will copy later, up to N ring fills ahead (N x 32 KiB per SM: 14 -> 66 MB
+// chip-wide of the 126 MB L2).  HBM keeps streaming into L2 through the gap; afterwards the bulk copies hit L2, which
+// feeds an SM at about twice its HBM share (LTS cap ~6300 B/clk chip-wide), and the consumers (1.9x the HBM rate at batch
+// 1, tools/ubench_fma) catch up.  In steady streaming the ring is never full, so no prefetch is issued and nothing is
+// touched twice.  Round 1's fixed-distance variant (one prefetch per copy, N fills ahead) only shifted the stream and
+// measured no gain (0.691 vs 0.700).  Prefetches change no result: bit-identical to the default build.
 SSB_DEVINL void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
@@ -126,6 +129,7 @@ struct Ahead {
   const bf16* W = nullptr;
   int K = 0, ps = 0, p1 = 0, kc = 0, nk = 0;
   bool live = true;
+  int dist = 0;  // ring fills the cursor is ahead of the copy cursor
   SSB_DEVINL void open_next(const MegaArgs& a) {  // advance to the next matrix in which this CTA owns rows
     for (;;) {
       ++idx;
@@ -153,7 +157,7 @@ struct Ahead {
       if (ps < p1) return;
     }
   }
-  SSB_DEVINL void step(const MegaArgs& a, int lane, int pw) {  // prefetch one ring fill, move on
+  SSB_DEVINL void step(const MegaArgs& a, int lane, int pw, bool issue) {  // move one ring fill on (prefetching it if `issue`)
     if (live && idx < 0) open_next(a);
     if (!live) return;
     constexpr int RPP = MG_ROWS / MG_PW;
@@ -162,7 +166,7 @@ struct Ahead {
     const int mine = max(0, min(RPP, nr - r0));
     const int k0 = kc * MG_KC;
     const int len = min(MG_KC, K - k0);
-    if (lane < mine) prefetch_l2_bulk(W + (size_t)(2 * ps + r0 + lane) * K + k0, (uint32_t)(len * 2));
+    if (issue && lane < mine) prefetch_l2_bulk(W + (size_t)(2 * ps + r0 + lane) * K + k0, (uint32_t)(len * 2));
     if (++kc == nk) {
       kc = 0;
       ps += MG_CW;
@@ -184,9 +188,20 @@ SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
 #if MG_L2_AHEAD > 0
-      ah.step(ma, lane, pw);  // keep the L2 prefetch cursor MG_L2_AHEAD fills ahead of this copy
-#endif
+      // ring full: use the wait to pull the stream further into L2 (see MG_L2_AHEAD above)
+      while (!mbar_try_wait(&empty[r.stage], r.phase ^ 1)) {
+        if (ah.live && ah.dist < MG_L2_AHEAD) {
+          ah.step(ma, lane, pw, true);
+          ++ah.dist;
+        }
+      }
+      if (ah.dist > 0)
+        --ah.dist;  // this copy consumes one prefetched fill
+      else
+        ah.step(ma, lane, pw, false);  // cursor stays level with the copies
+#else
       mbar_wait(&empty[r.stage], r.phase ^ 1);
+#endif
       constexpr int RPP = MG_ROWS / MG_PW;
       const int r0 = pw * RPP;
       const int mine = max(0, min(RPP, nr - r0));
@@ -497,6 +512,170 @@ SSB_DEVINL void attention_phase(const MegaArgs& a, const bf16* kcache, const bf1
   }
 }
 
+// ---------------------------------------------------------------- consumers: paged attention for GQA groups of 8 (Llama-2-70B
+// 64/8, Falcon-40B 128/8): one (row, KV head, context split) per CTA.  The K/V rows of the split are staged ONCE in shared
+// memory (the activation staging area is free during this phase) and consumer warp g computes query head g against the
+// tile — the scheme of attn_gqa_kernel (attn_gqa.cu).  The per-warp variant above gives a G = 8 unit only 4 tokens
+// (register budget), i.e. 144 context chunks at ctx 576 whose partials ONE warp then merges serially: measured ~60 us of
+// a 420 us Llama-2-70B layer.  Here the context is cut into about gridDim.x / (rows * KV heads) splits (18 of 32 tokens
+// at 70B), so the last-arriving CTA merges 18 partials with one warp per head.
+constexpr int MG_ATT_TILE = 32;  // tokens staged per pass: 2 x 32 x D bf16 = 16 KiB at D = 128
+template <int D>
+SSB_DEVINL void attention_phase_cta(const MegaArgs& a, const bf16* kcache, const bf16* vcache, bf16* tile, int* sm_flag, int tid, int warp,
+                                    int lane) {
+  constexpr int G = 8, LPR = D / 8, RPW = 32 / LPR, T = MG_ATT_TILE;
+  static_assert(MG_CW == 8 || MG_CW == 12, "one consumer warp per query head of the group");
+  bf16(*sK)[D] = reinterpret_cast<bf16(*)[D]>(tile);
+  bf16(*sV)[D] = reinterpret_cast<bf16(*)[D]>(tile + (size_t)T * D);
+  const int HU = a.n_heads / G;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int HD = a.n_heads * D;
+  const int BS = a.block_size;
+  const int n_ctas = gridDim.x;
+  int want = n_ctas / max(1, a.M * HU);  // context splits per (row, KV head) so that the units about fill the grid
+  want = max(1, min(want, a.max_chunks));
+  int base = 0;
+  for (int m = 0; m < a.M; ++m) {
+    const int ctx = __ldcg(a.row_pos + m) + 1;
+    int chunk = (ctx + want - 1) / want;
+    chunk = ((chunk + T - 1) / T) * T;
+    const int n_active = (ctx + chunk - 1) / chunk;
+    const int n_units = HU * n_active;
+    const int slot = a.row_slot[m];
+    const int* bt = a.block_table + (size_t)slot * a.bt_stride;
+    for (int u = (((int)blockIdx.x - base) % n_ctas + n_ctas) % n_ctas; u < n_units; u += n_ctas) {
+      const int hu = u / n_active, sp = u - hu * n_active;
+      const int kvh = (hu * G) / a.group;
+      const int t_begin = sp * chunk, t_end = min(ctx, t_begin + chunk);
+      const bool head_on = warp < G;
+      float q[8];
+      {
+        const uint4 v = ldcg128(a.q + (size_t)m * HD + (hu * G + (head_on ? warp : 0)) * D + li * 8);
+        const uint32_t uu[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q[2 * i] = bf_lo(uu[i]);
+          q[2 * i + 1] = bf_hi(uu[i]);
+        }
+      }
+      float mx = -1e30f, l = 0.f, acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int p0 = t_begin; p0 < t_end; p0 += T) {
+        const int np = min(T, t_end - p0);
+        named_bar_sync(1, MG_CW * 32);  // previous tile (or previous unit / phase) fully consumed
+        for (int i = tid; i < np * LPR; i += MG_CW * 32) {
+          const int tt = i / LPR, c = i - tt * LPR;
+          const int t = p0 + tt;
+          const size_t off = (((size_t)bt[t / BS] * a.kvh + kvh) * BS + (t % BS)) * D + c * 8;
+          const uint4 kq = ldcg128(kcache + off), vq = ldcg128(vcache + off);
+          *reinterpret_cast<uint4*>(&sK[tt][c * 8]) = kq;
+          *reinterpret_cast<uint4*>(&sV[tt][c * 8]) = vq;
+        }
+        named_bar_sync(1, MG_CW * 32);
+        if (head_on) {
+          for (int tb = 0; tb < np; tb += RPW) {  // warp-uniform trip count (full-mask shuffles below)
+            const int tt = tb + sub;
+            const bool tv = tt < np;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (tv) {
+              kv = *reinterpret_cast<const uint4*>(&sK[tt][li * 8]);
+              vv = *reinterpret_cast<const uint4*>(&sV[tt][li * 8]);
+            }
+            const uint32_t ku[4] = {kv.x, kv.y, kv.z, kv.w};
+            const uint32_t vu[4] = {vv.x, vv.y, vv.z, vv.w};
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              d = fmaf(q[2 * i], bf_lo(ku[i]), d);
+              d = fmaf(q[2 * i + 1], bf_hi(ku[i]), d);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (!tv) continue;
+            const float sc = bf16r(bf16r(d) * a.scale);
+            const float mn = fmaxf(mx, sc);
+            const float corr = __expf(mx - mn), pw = __expf(sc - mn);
+            mx = mn;
+            l = l * corr + pw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[2 * i] = fmaf(pw, bf_lo(vu[i]), acc[2 * i] * corr);
+              acc[2 * i + 1] = fmaf(pw, bf_hi(vu[i]), acc[2 * i + 1] * corr);
+            }
+          }
+        }
+      }
+      // merge the RPW token sub-groups of the warp
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, l, o);
+        const float mn = fmaxf(mx, om);
+        const float wa = __expf(mx - mn), wb = __expf(om - mn);
+        l = l * wa + ol * wb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+          acc[i] = acc[i] * wa + oa * wb;
+        }
+        mx = mn;
+      }
+      const size_t pidx = ((size_t)m * HU + hu) * a.max_chunks + sp;
+      if (n_active == 1) {
+        if (head_on && sub == 0) {
+          const float inv = 1.0f / l;
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = pack_bf16(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+          *reinterpret_cast<uint4*>(a.attn + (size_t)m * HD + (hu * G + warp) * D + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        continue;
+      }
+      if (head_on && sub == 0) {
+        float* po = a.part_o + (pidx * G + warp) * D + li * 8;
+        *reinterpret_cast<float4*>(po) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(po + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        if (li == 0) {
+          a.part_ml[(pidx * G + warp) * 2] = mx;
+          a.part_ml[(pidx * G + warp) * 2 + 1] = l;
+        }
+      }
+      __threadfence();
+      named_bar_sync(1, MG_CW * 32);
+      if (tid == 0) *sm_flag = (atomicAdd(&a.counters[m * HU + hu], 1) == n_active - 1);
+      named_bar_sync(1, MG_CW * 32);
+      if (!*sm_flag) continue;
+      __threadfence();
+      if (head_on) {  // warp g merges head g over the splits; a lane owns 4 dims
+        const size_t pb = ((size_t)m * HU + hu) * a.max_chunks;
+        for (int dd = lane * 4; dd < D; dd += 128) {
+          float M2 = -1e30f;
+          for (int c = 0; c < n_active; ++c) M2 = fmaxf(M2, __ldcg(&a.part_ml[((pb + c) * G + warp) * 2]));
+          float L2 = 0.f;
+          float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < n_active; ++c) {
+            const float w = __expf(__ldcg(&a.part_ml[((pb + c) * G + warp) * 2]) - M2);
+            L2 += __ldcg(&a.part_ml[((pb + c) * G + warp) * 2 + 1]) * w;
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(a.part_o + ((pb + c) * G + warp) * D + dd));
+            O.x += o.x * w;
+            O.y += o.y * w;
+            O.z += o.z * w;
+            O.w += o.w * w;
+          }
+          const float inv = 1.0f / L2;
+          uint2 o;
+          o.x = pack_bf16(O.x * inv, O.y * inv);
+          o.y = pack_bf16(O.z * inv, O.w * inv);
+          *reinterpret_cast<uint2*>(a.attn + (size_t)m * HD + (hu * G + warp) * D + dd) = o;
+        }
+      }
+      if (tid == 0) a.counters[m * HU + hu] = 0;
+    }
+    base = (base + n_units) % n_ctas;
+  }
+}
+
 // system-scope accessors for the cross-GPU exchange (same PTX as the allreduce kernel in kernels.cu)
 constexpr int TP_MAX = 8;
 SSB_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -652,9 +831,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     const uint64_t pol = policy_evict_first();
     const int pw = warp - MG_CW;
     Ahead ah;
-#if MG_L2_AHEAD > 0
-    for (int i = 0; i < MG_L2_AHEAD; ++i) ah.step(a, lane, pw);
-#endif
+
     for (int l = 0; l < a.n_layers; ++l) {
       const MegaLayer& w = a.layers[l];
       produce(w.wqkv, a.q_rows + 2 * a.kv_rows, h, tiles, full, empty, a.n_stages, r, pol, lane, pw, a, ah);
@@ -669,6 +846,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   // ================================================================== consumers
   pdl_wait();
   int n_prof = 0;
+  if (a.prof && a.prof_all && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.prof[(size_t)blockIdx.x * 1024 + 1023] = smid;
+  }
   MG_STAMP();
   unsigned n_sync = 0;
   const unsigned n_ctas = gridDim.x;
@@ -719,7 +901,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 3
     // ---- attention
-    attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+    if constexpr (G == 8) {
+      if (a.attn_cta_tile)
+        attention_phase_cta<D>(a, w.kcache, w.vcache, xs, reinterpret_cast<int*>(red + 16), tid, warp, lane);
+      else
+        attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+    } else {
+      attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+    }
     MG_STAMP();  // 4: attention done
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 5
@@ -937,3 +1126,4 @@ cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc) {
 
 int mega_attn_group(int group) { return (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1; }
 int mega_attn_chunk(int head_dim, int g) { return (32 / (head_dim / 8)) * (g <= 2 ? 8 : 2); }
+size_t mega_attn_tile_bytes(int head_dim) { return (size_t)2 * MG_ATT_TILE * head_dim * 2; }

@@ -29,7 +29,8 @@ struct MegaArgs {
   int *hist, *step, *fwd_counter;
   unsigned* grid_bar;  // [2], zero on entry and on exit
   int n_stages, k_max;
-  unsigned long long* prof;  // optional [1024] globaltimer stamps of CTA 0 (debug_taps engines only)
+  unsigned long long* prof;  // optional globaltimer stamps (params.mega_prof): [1024] of CTA 0, or with prof_all [n_ctas][1024]
+                             // (entry 1023 of a CTA's row = its %smid) — per-phase arrival skew across the SMs
   // ---- tensor parallel (params.json "tp_mega": 1; new fields stay at the END so the single-GPU instantiations keep
   // their parameter layout).  tp_size > 1 selects decode_mega_kernel<.., TP=true>: the row-parallel projections (o,
   // down) leave fp32 partials in this rank's exchange buffer and every allreduce is
@@ -55,10 +56,13 @@ struct MegaArgs {
   // ll[parity][src rank][row][pair] (uint4), CTA c of every rank owns the same pair range, so only same-index CTAs talk.
   uint4* const* peer_ll;             // [tp_size] peer-mapped receive buffers
   long long ll_parity_stride, ll_src_stride;  // in uint4 units
+  int prof_all;                      // params.mega_prof = 2: every CTA stamps
+  int attn_cta_tile;                 // GQA groups of 8: one (row, KV head, split) per CTA with K/V staged in shared memory
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);
 int mega_pick_stages(int bt, int k_max);  // 0 if the step does not fit
 int mega_attn_group(int group);
 int mega_attn_chunk(int head_dim, int g);  // tokens per attention unit
+size_t mega_attn_tile_bytes(int head_dim);  // shared memory the CTA-tile attention stages K/V in (must fit the activation area)
 cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc);

@@ -238,6 +238,34 @@ def test_prefill_256_token_tiles(Engine, tmp_path):
                    [[rel_err(lbf[i, s_], l32[i, s_]) for s_ in range(3)] for i in range(2)], "prefill 256-token tiles")
 
 
+@pytest.mark.parametrize("d", [128, 64])
+def test_persistent_kernel_gqa8_cta_tile_attention(Engine, tmp_path, d):
+    """GQA groups of 8 (Llama-2-70B 64/8, Falcon-40B 128/8 class) in the persistent decode kernel: one (row, KV head, context
+    split) per CTA with K/V staged in shared memory (mega.cu attention_phase_cta).  Contexts of 40 / 300 / 900 tokens (1, several
+    and ~29 splits; tiles of 32 tokens crossing 16-token KV blocks), batch 1 and a ragged batch of 2, against the oracle and
+    against the per-warp attention path ("mega_attn_tile": 0)."""
+    cfg = dict(synth.TINY_GQA, hidden_size=16 * d, num_attention_heads=16, num_key_value_heads=2, intermediate_size=8192,
+               num_hidden_layers=2, vocab_size=1000, max_position_embeddings=1024)
+    sd = synth.llama_state_dict(cfg, 23)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(31)
+    mk = lambda n: torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist()
+    cases = [[mk(40)], [mk(300)], [mk(900)], [mk(150), mk(333)]]
+    for prompts in cases:
+        res = {}
+        for tile in (1, 0):
+            with Engine(str(tmp_path), {"max_batch": 2, "max_seq_len": 1000, "mega_attn_tile": tile}) as e:
+                res[tile] = e.generate(prompts, 4, want_logits=True)
+        err = rel_err(res[1][1], res[0][1])
+        assert err < 1e-2, (len(prompts[0]), err)  # same math, different split of the context
+        l32 = _teacher_forced_logits(cfg, sd, torch.float32, prompts, res[1][0])
+        lbf = _teacher_forced_logits(cfg, sd, torch.bfloat16, prompts, res[1][0])
+        lg = np.transpose(res[1][1], (1, 0, 2))
+        n = len(prompts)
+        _assert_parity([[rel_err(lg[i, s_], l32[i, s_]) for s_ in range(4)] for i in range(n)],
+                       [[rel_err(lbf[i, s_], l32[i, s_]) for s_ in range(4)] for i in range(n)], f"gqa8 d{d} cta-tile attention ctx {[len(p) for p in prompts]}")
+
+
 def test_errors_and_slot_reuse(Engine, tmp_path):
     from substratus_b200 import SsbError
 

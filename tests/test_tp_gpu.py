@@ -42,18 +42,16 @@ def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
         dist.destroy_process_group()
 
 
-# {"tp_mega": 1}: the persistent decode kernel with its in-kernel allreduce (csrc/mega.h).  Written after the round-1
-# multi-GPU budget was spent, never run on hardware: a cross-GPU spin-wait bug would hang the box, so it only runs when
-# SSB_EXPERIMENTAL=1 is set (tools/r2_tp_mega.sh runs it under a short timeout).
+# Decode exchange modes (csrc/mega.h): "tp_mega" 0 = multi-kernel path with the one-shot pull allreduce kernel, 1 / 2 = persistent
+# kernel with grid-wide / per-CTA flag + pull, 3 (engine default) = persistent kernel with the 16-byte {value, epoch} push.
+# {"tp_two_shot": 1}: reduce-scatter + bf16 gather allreduce for prefill-sized forwards (csrc/tp_twoshot.cu).
+# All of them first ran on 2 x B200 in round 2 (profiles/r02_tp_parity_n2.log).
 @pytest.mark.parametrize("world", [2, 4])
-# {"tp_two_shot": 1}: reduce-scatter + bf16 gather allreduce for prefill-sized forwards (csrc/tp_twoshot.cu), same status.
-@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv", "tp_mega": 0}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
                                   {"gemm_path": "tc", "tp_two_shot": 1, "tp_two_shot_min_rows": 16}, {"gemm_path": "gemv", "tp_mega": 2},
-                                  {"gemm_path": "gemv", "tp_mega": 3}],
-                         ids=["gemv", "tc", "exp_tp_mega", "exp_two_shot", "exp_tp_mega2", "exp_tp_mega3"])
+                                  {"gemm_path": "gemv", "tp_mega": 3}, {}],
+                         ids=["gemv_multikernel", "tc", "tp_mega1", "two_shot", "tp_mega2", "tp_mega3", "default"])
 def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
-    if (mode.get("tp_mega") or mode.get("tp_two_shot")) and os.environ.get("SSB_EXPERIMENTAL") != "1":
-        pytest.skip("experimental (set SSB_EXPERIMENTAL=1)")
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     from substratus_b200 import Engine
@@ -79,7 +77,13 @@ def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
         assert not isinstance(toks, str), f"rank {r}: {toks}"
         assert np.array_equal(toks, res[0][1]), f"rank {r} diverged"
     ltp = res[0][2]
-    assert rel_err(ltp[0], l1[0]) < 1.5e-2  # fp32 cross-rank sum order + bf16 rounding flips; measured 6.6e-3
+    # TP-N vs TP1 on identical inputs (first step): only the fp32 cross-rank summation order and the bf16 rounding flips it
+    # causes differ.  Measured on 2 x B200 in round 1: 6.6e-3; bound = 1.5 x that ("tighten toward the measured value")
+    e1 = rel_err(ltp[0], l1[0])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_tp.txt", "a") as f:
+        f.write(f"[tp{world} {mode}] first-step logits rel err vs TP1 {e1:.3e}\n")
+    assert e1 < 1e-2, e1
     ref32 = llama_ref.LlamaRef(cfg, sd, torch.float32).forward(torch.tensor([prompts[1]]))[0, -1].numpy()
     refbf = llama_ref.LlamaRef(cfg, sd, torch.bfloat16).forward(torch.tensor([prompts[1]]))[0, -1].float().numpy()
     assert rel_err(ltp[0, 1], ref32) <= rel_err(refbf, ref32) + 1e-3
