@@ -723,7 +723,7 @@ def main():
                     "ms_per_launch": m["step_ms"]}
     else:
         dom = kern["gate_up"]
-        roofline = {"bound": "hbm", "kernel": "gate/up projection (gemv_kernel for <= 4 rows, tc_gemm_sk_kernel tcgen05 stream-K above)",
+        roofline = {"bound": "hbm", "kernel": "gate/up projection (proj_rows_kernel for <= 4 rows, tc_gemm_sk_kernel tcgen05 stream-K above)",
                     "achieved": dom["gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": dom["gbs"] / peak_gbs, "traffic": None,
                     "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
     roofline.update({"peak_source": peak_src, "per_kernel_class_gbs": {k: round(v["gbs"], 1) for k, v in kern.items()},

@@ -64,13 +64,19 @@ typedef struct ssb_timing {
  * params_reconciler.go:36-53), may be NULL or "{}".  Recognised params:
  *   "max_batch" (32), "max_seq_len" (config's), "kv_block_size" (16), "kv_blocks" (auto),
  *   "weights": "file" | "synthetic" (seeded hash weights at config.json's shapes; "seed"),
- *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank), "allreduce": "p2p" | "nccl",
+ *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank),
  *   "use_pdl" (1), "use_graph" (1), "use_mega" (1: persistent single-kernel decode step at batch <= 4),
  *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (8), "tc_streamk" (1), "prefill_chunk" (1024),
+ *   "tc_tn_prefill" (0 = per-projection heuristic | 128 | 256: token-tile width of the prefill GEMMs),
  *   "attn_splits" (0 = heuristic; context splits of the decode attention kernels, a sweep knob),
- *   experimental, off by default, never run on hardware yet: "tp_mega" (persistent kernel under
- *   tensor parallelism with an in-kernel allreduce), "tp_two_shot" / "tp_two_shot_min_rows" (reduce-scatter + gather
- *   allreduce for prefill-sized forwards), "tp_push" (push-model allreduce, measured slower).
+ *   "mega_attn_tile" (1: CTA-tile attention for GQA groups of 8 inside the persistent kernel),
+ *   tensor-parallel decode exchange, "tp_mega": 3 (default: the persistent kernel pushes 16-byte {value, epoch} words into
+ *   every rank's receive slots over NVLink peer memory and polls its own) | 1, 2 (flag + pull inside the persistent kernel,
+ *   grid-wide / per CTA) | 0 (multi-kernel step with the one-shot pull allreduce kernel); prefill-sized forwards always
+ *   use the allreduce kernels: one-shot pull, or "tp_two_shot": 1 with "tp_two_shot_min_rows" (reduce-scatter + bf16
+ *   gather); "tp_push" (push-model allreduce kernel, measured slower).  All cross-GPU waits are bounded (20 s, then the
+ *   kernel traps and the call returns SSB_ECUDA).  There is no NCCL call on the data path; the NCCL baseline the engine's
+ *   exchange is measured against is tools/nccl_ar_bench.py.
  * Keys the engine does not know are ignored (the serve host keeps its own keys in the same file: "batching",
  * "batch_tick", "stream_chunk", "stop_at_eos", "eos_token_id", "eos_check_every").
  * With tp_size > 1 the engine is usable only after ssb_tp_connect(). */

@@ -396,6 +396,69 @@ std::string Engine::prof_report() {
   return s + "}";
 }
 
+// Per-SM streaming speed for the persistent kernel's row shares (mega.cu: part_range).  params "sm_balance": 1 (default)
+// calibrate | 0 equal shares; "sm_balance_gain" (1.0): exponent applied to the measured speed ratio.
+int Engine::calibrate_sm_weights(const Json& params) {
+  if (params.get_int("sm_balance", 1) == 0 || n_sm_ > 200) return SSB_OK;
+  const size_t per_cta = (size_t)8 << 20;  // 8 MiB per SM: 1.2 GB per pass, far beyond the 126 MB L2
+  const size_t bytes = per_cta * (size_t)n_sm_;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (free_b < bytes + ((size_t)2 << 30)) return SSB_OK;  // no room: equal shares
+  void* buf = nullptr;
+  unsigned long long* d_out = nullptr;
+  CK(cudaMalloc(&buf, bytes));
+  CK(cudaMalloc(&d_out, (size_t)n_sm_ * 2 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(buf, 0x3c, bytes, stream_));
+  const int reps = 5;
+  std::vector<double> t_sm(256, 0.0);
+  std::vector<int> n_smv(256, 0);
+  std::vector<unsigned long long> h((size_t)n_sm_ * 2);
+  for (int r = 0; r < reps; ++r) {
+    CK(launch_sm_calib(buf, per_cta, n_sm_, d_out, stream_));
+    CK(cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    if (r < 2) continue;  // warm-up passes (clocks, page tables)
+    for (int b = 0; b < n_sm_; ++b) {
+      const unsigned sm = (unsigned)h[2 * b] & 255u;
+      t_sm[sm] += (double)h[2 * b + 1];
+      n_smv[sm] += 1;
+    }
+  }
+  cudaFree(buf);
+  cudaFree(d_out);
+  double mean = 0.0;
+  int cnt = 0;
+  for (int i = 0; i < 256; ++i)
+    if (n_smv[i]) {
+      t_sm[i] /= n_smv[i];
+      mean += t_sm[i];
+      ++cnt;
+    }
+  if (cnt < n_sm_) return SSB_OK;  // some SM never ran a calibration CTA: keep equal shares
+  mean /= cnt;
+  const double gain = params.get_num("sm_balance_gain", 1.0);
+  std::vector<float> w(256, 1.0f);
+  double wmin = 1e9, wmax = 0;
+  for (int i = 0; i < 256; ++i)
+    if (n_smv[i]) {
+      double v = pow(mean / t_sm[i], gain);
+      v = std::min(1.25, std::max(0.8, v));
+      w[i] = (float)v;
+      wmin = std::min(wmin, v);
+      wmax = std::max(wmax, v);
+    }
+  TRY(dmalloc(&sm_weight_, 256));
+  TRY(dmalloc(&cta_weight_, 256));
+  CK(cudaMemcpy(sm_weight_, w.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemset(cta_weight_, 0, 256 * sizeof(float)));
+  char buf2[256];
+  snprintf(buf2, sizeof buf2, "{\"sms\": %d, \"mean_us_per_8MiB\": %.2f, \"speed_min\": %.4f, \"speed_max\": %.4f, \"gain\": %.2f}", cnt, mean * 1e-3,
+           wmin, wmax, gain);
+  sm_calib_report_ = buf2;
+  return SSB_OK;
+}
+
 int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
@@ -619,6 +682,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   if (prof_fwd_) use_pdl_ = use_graph_ = false;  // event marks between launches need plain stream order
   TRY(alloc_weights());
   TRY(fill_weights(model_dir, wmode == "synthetic", (uint64_t)params.get_int("seed", 0), false));
+  if (params.get_int("use_mega", 1) != 0 && !cfg_.falcon) TRY(calibrate_sm_weights(params));  // before the KV pool takes the free HBM
   TRY(alloc_runtime(params));
   {
     const std::string gp = params.get_str("gemm_path", "auto");  // "auto" | "gemv" (CUDA cores only) | "tc" (tcgen05 always)
@@ -1328,6 +1392,10 @@ int Engine::forward_mega(int B) {
   if (mega_prof_all_) CK(cudaMemsetAsync(mega_prof_, 0, (size_t)n_sm_ * 1024 * sizeof(unsigned long long), stream_));
   a.n_stages = mega_pick_stages(B == 1 ? 1 : (B == 2 ? 2 : 4), mega_k_max_);
   // GQA groups of 8: CTA-tile attention when the K/V tile fits the activation staging area (params "mega_attn_tile": 0 = off)
+  a.sm_weight = sm_weight_;
+  a.cta_weight = cta_weight_;
+  a.attn_coop = (a.attn_g < 8 && mega_attn_tile_ &&
+                 (size_t)(B == 1 ? 1 : (B == 2 ? 2 : 4)) * mega_k_max_ * sizeof(bf16) >= mega_attn_coop_bytes(D, a.attn_g)) ? 1 : 0;
   a.attn_cta_tile = (a.attn_g == 8 && mega_attn_tile_ &&
                      (size_t)(B == 1 ? 1 : (B == 2 ? 2 : 4)) * mega_k_max_ * sizeof(bf16) >= mega_attn_tile_bytes(D)) ? 1 : 0;
   if (a.n_stages == 0) RET(SSB_EINVAL, "decode step does not fit the persistent kernel's shared memory");
@@ -1730,6 +1798,17 @@ void Engine::timing_reset() { timing_ = ssb_timing{}; }
 
 int Engine::debug_read(const char* name, float* dst, int64_t n, int* rows, int* cols) {
   const std::string nm = name ? name : "";
+  if (nm == "sm_weight") {  // [1][256] calibrated per-SM streaming speed (1.0 = mean), all ones if calibration was skipped
+    if (n < 256) RET(SSB_EINVAL, "destination too small");
+    CK(cudaSetDevice(device_));
+    if (sm_weight_)
+      CK(cudaMemcpy(dst, sm_weight_, 256 * sizeof(float), cudaMemcpyDeviceToHost));
+    else
+      for (int i = 0; i < 256; ++i) dst[i] = 1.0f;
+    *rows = 1;
+    *cols = 256;
+    return SSB_OK;
+  }
   if (nm == "mega_prof_all") {  // [n_ctas][1024]: per-CTA phase stamps of the LAST step in us from the earliest one; column 1023 = %smid
     if (!mega_prof_ || !mega_prof_all_) RET(SSB_ESTATE, "engine was not created with params.mega_prof=2");
     if (n < (int64_t)n_sm_ * 1024) RET(SSB_EINVAL, "destination too small");

@@ -94,6 +94,10 @@ class Engine {
   unsigned long long* mega_prof_ = nullptr;
   bool mega_prof_all_ = false;
   bool mega_attn_tile_ = true;
+  float* sm_weight_ = nullptr;   // [256] per-SM streaming speed (calibrate_sm_weights), null = equal shares
+  float* cta_weight_ = nullptr;  // [n_sm] scratch of the persistent kernel
+  std::string sm_calib_report_;  // JSON summary of the calibration (ssb_debug_profile-style, tools)
+  int calibrate_sm_weights(const Json& params);
   int mega_max_chunks_ = 0, mega_k_max_ = 0;
   int tc_tn_prefill_ = 0;  // params "tc_tn_prefill": force the prefill token-tile width (0 = heuristic)
   int tc_min_rows_ = 8;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)

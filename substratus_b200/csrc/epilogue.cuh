@@ -86,6 +86,72 @@ SSB_DEVINL void gemv_epilogue(const GemvArgs& a, int pair, int m, float v0, floa
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue inputs fetched at the START of a row-pair pass (GEMV kernels).  The residual / position / RoPE-table / block-table
+// reads are one or two DEPENDENT L2 round trips (~0.4-1 us); done after the K loop they sit on the critical path of every
+// pass of every consumer warp (a QKV pass of the persistent kernel is only ~1.6 us of streaming).  They depend on nothing the
+// pass computes, so the lane that will run the epilogue for row m issues them before the first weight chunk and the K loop
+// hides them.  Safe with out == resid: a pair's residual element is written by this pair's own epilogue only.
+struct EpiPre {
+  uint32_t r;    // EPI_RESID: residual word (2 x bf16)
+  int pos, blk;  // EPI_QKV_ROPE: position of the row, KV block of that position
+  uint32_t cs;   // EPI_QKV_ROPE: packed cos | sin of (pos, j)
+};
+template <int EPI>
+SSB_DEVINL EpiPre epi_prefetch(const GemvArgs& a, int pair, int m) {
+  EpiPre p = {0u, 0, 0, 0u};
+  if constexpr (EPI == EPI_RESID) {
+    p.r = __ldcg(reinterpret_cast<const uint32_t*>(a.resid + (size_t)m * a.ld_out + 2 * pair));
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int half = a.head_dim >> 1;
+    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+    p.pos = __ldcg(a.row_pos + m);
+    if (pair < q_pairs + k_pairs) {
+      const int pp = pair < q_pairs ? pair : pair - q_pairs;
+      p.cs = a.rope_cs[(size_t)p.pos * half + (pp % half)];
+    }
+    if (pair >= q_pairs) p.blk = a.block_table[(size_t)a.row_slot[m] * a.bt_stride + p.pos / a.block_size];
+  }
+  return p;
+}
+// same math and rounding points as gemv_epilogue for the two epilogues that have prefetched inputs
+template <int BT, int EPI>
+SSB_DEVINL void gemv_epilogue_pre(const GemvArgs& a, int pair, int m, float v0, float v1, const EpiPre& pre) {
+  if constexpr (EPI == EPI_RESID) {
+    const size_t o = (size_t)m * a.ld_out + 2 * pair;
+    *reinterpret_cast<uint32_t*>(a.out_bf16 + o) = pack_bf16(bf16r(v0) + bf_lo(pre.r), bf16r(v1) + bf_hi(pre.r));
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int hd = a.head_dim, half = hd >> 1;
+    const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+    const int pos = pre.pos;
+    if (pair < q_pairs + k_pairs) {
+      const bool is_q = pair < q_pairs;
+      const int pp = is_q ? pair : pair - q_pairs;
+      const int head = pp / half, j = pp - head * half;
+      const float c = bf_lo(pre.cs), s = bf_hi(pre.cs);
+      const float x0 = bf16r(v0), x1 = bf16r(v1);
+      const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
+      const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
+      if (is_q) {
+        bf16* q = a.q_out + (size_t)m * a.q_rows + head * hd + j;
+        q[0] = __float2bfloat16_rn(y0);
+        q[half] = __float2bfloat16_rn(y1);
+      } else {
+        bf16* k = a.kcache + (((size_t)pre.blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+        k[0] = __float2bfloat16_rn(y0);
+        k[half] = __float2bfloat16_rn(y1);
+      }
+    } else {
+      const int e = 2 * (pair - q_pairs - k_pairs);
+      const int head = e / hd, j = e - head * hd;
+      bf16* v = a.vcache + (((size_t)pre.blk * a.kvh + head) * a.block_size + (pos % a.block_size)) * hd + j;
+      *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
+    }
+  } else {
+    gemv_epilogue<BT, EPI>(a, pair, m, v0, v1);
+  }
+}
+
 // Eight tokens at once for one row pair (tensor-core kernels: a thread owns a weight row across the token tile).
 // The per-token epilogue above does dependent global loads (residual, position, rope table, block table) followed by a
 // store; out_bf16 may alias resid, so the compiler cannot hoist the next token's loads above the previous store and

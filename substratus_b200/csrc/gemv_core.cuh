@@ -1,4 +1,4 @@
-// gemv_core.cuh — the consumer inner loop shared by gemv_kernel (kernels.cu) and decode_mega_kernel (mega.cu):
+// gemv_core.cuh — the consumer inner loop shared by proj_rows_kernel (kernels.cu) and decode_mega_kernel (mega.cu):
 // one warp, two weight rows (w0, w1) of one K-chunk staged in shared memory, BT activation rows in shared memory.
 // Full chunks (1024 elements) take a fully unrolled path: all 8+4*BT 128-bit shared loads are issued before the first
 // FMA, and every (row, 256-element sub-chunk) has its own accumulator so no FMA chain is longer than 8 (measured: the

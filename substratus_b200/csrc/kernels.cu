@@ -8,7 +8,7 @@
 //   attention    HF:models/llama/modeling_llama.py:199-221 (scores rounded to bf16, * d^-1/2 in bf16, fp32 softmax)
 //   greedy pick  HF:generation/utils.py:2762,2793 (logits.float(), argmax)
 //
-// The dominant kernel is gemv_kernel: y[M<=4, N] = x * W^T with W streamed from HBM exactly once through a
+// The dominant kernel is proj_rows_kernel: y[M<=4, N] = x * W^T with W streamed from HBM exactly once through a
 // TMA-engine (cp.async.bulk) -> shared-memory mbarrier ring, consumed by 8 warps with fp32 FMAs and warp-shuffle
 // reductions; norm prologue and RoPE/KV-append/SwiGLU/residual epilogues are fused.  It is HBM-bound:
 // algorithmic bytes per launch = 2*N*K.
@@ -17,7 +17,7 @@
 #include <cstring>
 
 // =====================================================================================================================
-// gemv_kernel
+// proj_rows_kernel
 // =====================================================================================================================
 constexpr int GV_CW = 8;                        // consumer warps
 constexpr int GV_PW = 4;                        // producer warps: the compiler lowers per-lane cp.async.bulk to a serial
@@ -46,7 +46,7 @@ int gemv_pick_bt(int M, int K) {
 #include "gemv_core.cuh"
 
 template <int BT, int EPI, int NORM>
-__global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
+__global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   bf16* tiles = reinterpret_cast<bf16*>(smem_raw);            // [STAGES][ROWS][KC]
   bf16* xs = tiles + GV_STAGES * GV_ROWS * GV_KC;             // [BT][K]
@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
       float acc0[BT], acc1[BT];
 #pragma unroll
       for (int b = 0; b < BT; ++b) acc0[b] = acc1[b] = 0.f;
+      // the epilogue's dependent global reads, issued now and hidden by the K loop (epilogue.cuh: EpiPre)
+      [[maybe_unused]] EpiPre pre = {0u, 0, 0, 0u};
+      if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+        if (valid && lane < BT && m0 + lane < a.M) pre = epi_prefetch<EPI>(a, pair, m0 + lane);
+      }
       for (int kc = 0; kc < nk; ++kc) {
         const int k0 = kc * GV_KC;
         const int len = min(GV_KC, K - k0);
@@ -238,7 +243,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const GemvArgs a) {
             v1 = s1;
           }
         }
-        if (lane < BT && m0 + lane < a.M) gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
+        if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+          if (lane < BT && m0 + lane < a.M) gemv_epilogue_pre<BT, EPI>(a, pair, m0 + lane, v0, v1, pre);
+        } else {
+          if (lane < BT && m0 + lane < a.M) gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
+        }
       }
     }
     if constexpr (EPI == EPI_F32_PUSH) {
@@ -273,13 +282,13 @@ static cudaError_t launch_gemv_t(const GemvArgs& a, const LaunchCfg& lc) {
   const size_t smem = gemv_smem_bytes(BT, a.K);
   static unsigned long long attr_mask = 0;  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(proj_rows_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
   const int P = a.N / 2;
   int gx = lc.n_sm < P ? lc.n_sm : P;
   dim3 grid(gx, (a.M + BT - 1) / BT);
-  return launch_ex(gemv_kernel<BT, EPI, NORM>, grid, dim3(GV_THREADS), smem, lc, a);
+  return launch_ex(proj_rows_kernel<BT, EPI, NORM>, grid, dim3(GV_THREADS), smem, lc, a);
 }
 
 template <int EPI, int NORM>
@@ -871,4 +880,47 @@ cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc) {
   int grid = (total4 + TP_THREADS * 2 - 1) / (TP_THREADS * 2);
   grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
   return launch_ex(tp_allreduce_resid_kernel, dim3(grid), dim3(TP_THREADS), 0, lc, a);
+}
+
+
+// =====================================================================================================================
+// Per-SM streaming-speed calibration (engine creation, once per device): one CTA per SM (the shared-memory request keeps
+// it to one), all resident at once so HBM is saturated the way the persistent decode kernel saturates it; every CTA
+// streams its own slice of a scratch buffer much larger than L2 and reports %smid and its elapsed time.  SMs farther
+// from their L2 slices / across the die boundary get a smaller share of the bandwidth — systematically.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256, 1) sm_calib_kernel(const uint4* __restrict__ src, size_t n16_per_cta, unsigned long long* __restrict__ out) {
+  extern __shared__ uint8_t calib_smem[];
+  const uint4* p = src + (size_t)blockIdx.x * n16_per_cta;
+  unsigned long long t0, t1;
+  __syncthreads();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t sink = 0;
+  for (size_t i = threadIdx.x; i + 7 * 256 < n16_per_cta; i += 8 * 256) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + i + (size_t)u * 256);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sink ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+  }
+  __syncthreads();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    out[2 * blockIdx.x] = smid;
+    out[2 * blockIdx.x + 1] = t1 - t0;
+  }
+  if (sink == 0x12345678u) calib_smem[threadIdx.x] = 1;  // keep the loads
+}
+
+cudaError_t launch_sm_calib(const void* src, size_t bytes_per_cta, int n_ctas, unsigned long long* out, cudaStream_t s) {
+  static unsigned long long attr_mask = 0;
+  const int smem = 160 * 1024;  // > half of an SM's shared memory: one CTA per SM
+  if (first_launch_on_device(attr_mask)) {
+    cudaError_t e = cudaFuncSetAttribute(sm_calib_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+  }
+  sm_calib_kernel<<<n_ctas, 256, smem, s>>>(reinterpret_cast<const uint4*>(src), bytes_per_cta / 16, out);
+  return cudaGetLastError();
 }

@@ -8,7 +8,7 @@
 //     embed | per layer: RMSNorm+QKV+RoPE+KV-append | paged attention | O+residual | RMSNorm+gate/up+SwiGLU |
 //     down+residual | final RMSNorm + lm_head | greedy pick
 // separated by grid-wide barriers (atomic counter in L2).  While consumers sit in a barrier or in the attention phase
-// the producer keeps the ring full, so HBM stays busy.  Math and rounding points are identical to gemv_kernel /
+// the producer keeps the ring full, so HBM stays busy.  Math and rounding points are identical to proj_rows_kernel /
 // attn_decode_kernel (HF:models/llama/modeling_llama.py:62-67,138-221,292-332; HF:generation/utils.py:2762,2793).
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -30,6 +30,29 @@ struct Ring {
   int stage;
   uint32_t phase;
 };
+
+// ---------------------------------------------------------------- row partition of a projection over the CTAs
+// Every CTA streams the rows [p0, p1) (in row PAIRS) of every matrix.  Equal shares leave a systematic skew: measured on
+// B200 with every CTA stamping its phases (tools/mega_skew.py, Llama-2-7B), the same SMs (TPC pairs, e.g. 10/11, 26/27,
+// 74/75) arrive 2-3 us late at EVERY weight phase — the between-SM L2 / die distance variance — and the barrier waits for
+// them: 3.9 + 2.8 + 5.1 + 3.6 us of first-to-last spread per layer.  With MegaArgs::sm_weight (per-SM streaming speed,
+// calibrated once per device at engine creation) the shares are proportional to the speed of the SM a CTA actually runs on:
+// CTA b publishes the weight of ITS %smid, and after the first grid barrier every CTA builds the same cumulative table
+// (same data, same arithmetic) — keyed by blockIdx, so it stays a partition whatever the block -> SM placement is.
+constexpr int MG_MAX_CTAS = 200;
+__shared__ uint32_t s_cumq[MG_MAX_CTAS + 1];  // cumulative share of the CTAs before b, as a 32-bit binary fraction
+__shared__ float s_cw[MG_MAX_CTAS];
+__shared__ uint64_t s_part_bar;               // producers wait here for the table
+__shared__ int s_weighted;
+SSB_DEVINL void part_range(int P, int& p0, int& p1) {
+  if (!s_weighted) {
+    p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
+    p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  } else {
+    p0 = (int)(((unsigned long long)P * s_cumq[blockIdx.x]) >> 32);
+    p1 = blockIdx.x + 1 == gridDim.x ? P : (int)(((unsigned long long)P * s_cumq[blockIdx.x + 1]) >> 32);
+  }
+}
 
 SSB_DEVINL uint4 ldcg128(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 SSB_DEVINL unsigned ld_acquire_gpu(const unsigned* p) {
@@ -150,8 +173,7 @@ struct Ahead {
         K = m == 1 ? a.q_rows : m == 3 ? a.inter : a.hidden;
       }
       const int P = N >> 1;
-      ps = (int)(((long long)blockIdx.x * P) / gridDim.x);
-      p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+      part_range(P, ps, p1);
       nk = (K + MG_KC - 1) / MG_KC;
       kc = 0;
       if (ps < p1) return;
@@ -179,8 +201,8 @@ struct Ahead {
 SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
                         uint64_t pol, int lane, int pw, [[maybe_unused]] const MegaArgs& ma, [[maybe_unused]] Ahead& ah) {
   const int P = N >> 1;
-  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
-  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  int p0, p1;
+  part_range(P, p0, p1);
   const int nk = (K + MG_KC - 1) / MG_KC;
   for (int ps = p0; ps < p1; ps += MG_CW) {
     const int nr = 2 * min(MG_CW, p1 - ps);
@@ -268,7 +290,7 @@ SSB_DEVINL void stage_x(const bf16* x, int ldx, int M, int K, const bf16* norm_w
   named_bar_sync(1, MG_CW * 32);
 }
 
-// ---------------------------------------------------------------- consumers: one projection (same loop as gemv_kernel)
+// ---------------------------------------------------------------- consumers: one projection (same loop as proj_rows_kernel)
 constexpr int EPI_LL = 100;  // mega-only epilogue: "tp_mega": 3 push exchange (see mega.h)
 struct LlCtx {
   const MegaArgs* ma;
@@ -289,8 +311,8 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
                         int warp, int lane, [[maybe_unused]] const LlCtx* ll = nullptr) {
   const int K = a.K;
   const int P = a.N >> 1;
-  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
-  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  int p0, p1;
+  part_range(P, p0, p1);
   const int nk = (K + MG_KC - 1) / MG_KC;
   for (int ps = p0; ps < p1; ps += MG_CW) {
     const int pair = ps + warp;
@@ -298,6 +320,11 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
     float acc0[BT], acc1[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc0[b] = acc1[b] = 0.f;
+    // the epilogue's dependent global reads, issued now and hidden by the K loop (epilogue.cuh: EpiPre)
+    [[maybe_unused]] EpiPre pre = {0u, 0, 0, 0u};
+    if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+      if (valid && lane < BT && lane < a.M) pre = epi_prefetch<EPI>(a, pair, lane);
+    }
     for (int kc = 0; kc < nk; ++kc) {
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
@@ -334,6 +361,8 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
           for (int rk = 0; rk < 8; ++rk)
             if (rk < ma.tp_size) st_relaxed_sys_v4(ma.peer_ll[rk] + o, w);  // own slot included: the reduce reads all ranks alike
         }
+      } else if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+        if (lane < BT && lane < a.M) gemv_epilogue_pre<BT, EPI>(a, pair, lane, v0, v1, pre);
       } else {
         if (lane < BT && lane < a.M) gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
       }
@@ -509,6 +538,196 @@ SSB_DEVINL void attention_phase(const MegaArgs& a, const bf16* kcache, const bf1
       if (lane == 0) a.counters[m * HU + hu] = 0;
     }
     base = (base + n_units) % nw;
+  }
+}
+
+// ---------------------------------------------------------------- consumers: paged attention, CTA-cooperative form for small
+// groups (G = 1, 2, 4 query heads per unit; Llama-2-7B / 13B are G = 1).  One (row, head unit, context split) per CTA: the
+// 8 consumer warps take consecutive token slices of the split, keep the per-warp online softmax of attention_phase, and
+// combine their 8 partial states through shared memory (the activation staging area is free in this phase).  Only ONE
+// partial per CTA reaches global memory and a (row, head unit) has at most 8 of them, merged by the last-arriving CTA with
+// 128 threads in parallel.  The per-warp form above leaves 36 partials per head at ctx 576 for ONE warp to merge serially:
+// measured on B200 (tools/mega_skew.py, Llama-2-7B) the attention phase took 5.3 us on average but its last CTA arrived
+// 9.9 us after its first — the merge tail — and the barrier behind it waited 6.4 us.
+template <int D, int G>
+SSB_DEVINL void attention_phase_coop(const MegaArgs& a, const bf16* kcache, const bf16* vcache, float* sm, int* sm_flag, int tid, int warp,
+                                     int lane) {
+  constexpr int LPR = D / 8, RPW = 32 / LPR;
+  // load batch of a warp: 20 tokens at G = 1 / D = 128, so that a 512..640-token context cut into 4 splits x 8 warps
+  // (18-20 tokens per warp) is ONE batch of loads, i.e. one memory latency
+  constexpr int UNR = (G == 1) ? 10 : (G == 2) ? 4 : 2;
+  constexpr int TB = RPW * UNR;  // tokens per load batch of a warp
+  constexpr int GD = G * D;
+  const int HU = a.n_heads / G;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int HD = a.n_heads * D;
+  const int BS = a.block_size;
+  const int n_ctas = gridDim.x;
+  float* sm_ml = sm;                   // [MG_CW][G][2]
+  float* sm_o = sm + MG_CW * G * 2;    // [MG_CW][G*D]
+  int want = n_ctas / max(1, a.M * HU);  // context splits per (row, head unit): fill the grid, at most 8 partials to merge
+  want = max(1, min(want, min(8, a.max_chunks)));
+  int base = 0;
+  for (int m = 0; m < a.M; ++m) {
+    const int ctx = __ldcg(a.row_pos + m) + 1;
+    int slen = (ctx + want - 1) / want;                        // tokens per split ...
+    slen = ((slen + MG_CW * RPW - 1) / (MG_CW * RPW)) * (MG_CW * RPW);  // ... a whole number of RPW-token groups per warp
+    const int n_active = (ctx + slen - 1) / slen;
+    const int wlen = slen / MG_CW;                             // tokens per warp
+    const int n_units = HU * n_active;
+    const int slot = a.row_slot[m];
+    const int* bt = a.block_table + (size_t)slot * a.bt_stride;
+    for (int u = (((int)blockIdx.x - base) % n_ctas + n_ctas) % n_ctas; u < n_units; u += n_ctas) {
+      const int hu = u / n_active, sp = u - hu * n_active;
+      const int kvh = (hu * G) / a.group;
+      const int t_begin = sp * slen + warp * wlen;
+      const int t_end = min(ctx, t_begin + wlen);
+      float q[G][8];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint4 v = ldcg128(a.q + (size_t)m * HD + (hu * G + g) * D + li * 8);
+        const uint32_t uu[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q[g][2 * i] = bf_lo(uu[i]);
+          q[g][2 * i + 1] = bf_hi(uu[i]);
+        }
+      }
+      float mx[G], l[G], acc[G][8];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        mx[g] = -1e30f;
+        l[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+      }
+      for (int tb = t_begin; tb < t_end; tb += TB) {  // warp-uniform bounds
+        uint4 kq[UNR], vq[UNR];
+        bool tvq[UNR];
+#pragma unroll
+        for (int x = 0; x < UNR; ++x) {
+          const int t = tb + x * RPW + sub;
+          tvq[x] = t < t_end;
+          kq[x] = make_uint4(0, 0, 0, 0);
+          vq[x] = make_uint4(0, 0, 0, 0);
+          if (tvq[x]) {
+            const int blk = bt[t / BS];
+            const size_t off = (((size_t)blk * a.kvh + kvh) * BS + (t % BS)) * D + li * 8;
+            kq[x] = ldcg128(kcache + off);
+            vq[x] = ldcg128(vcache + off);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < UNR; ++x) {
+          if (tb + x * RPW >= t_end) break;  // warp-uniform
+          const uint32_t ku[4] = {kq[x].x, kq[x].y, kq[x].z, kq[x].w};
+          const uint32_t vu[4] = {vq[x].x, vq[x].y, vq[x].z, vq[x].w};
+          float kf[8], vf[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            kf[2 * i] = bf_lo(ku[i]);
+            kf[2 * i + 1] = bf_hi(ku[i]);
+            vf[2 * i] = bf_lo(vu[i]);
+            vf[2 * i + 1] = bf_hi(vu[i]);
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d = fmaf(q[g][i], kf[i], d);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (!tvq[x]) continue;
+            const float sc = bf16r(bf16r(d) * a.scale);
+            const float mn = fmaxf(mx[g], sc);
+            const float corr = __expf(mx[g] - mn);
+            const float pw = __expf(sc - mn);
+            mx[g] = mn;
+            l[g] = l[g] * corr + pw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pw, vf[i], acc[g][i] * corr);
+          }
+        }
+      }
+      // merge the RPW token sub-groups of the warp (lanes li + k*LPR hold the same dims of different tokens)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, mx[g], o);
+          const float ol = __shfl_xor_sync(0xffffffffu, l[g], o);
+          const float mn = fmaxf(mx[g], om);
+          const float wa = __expf(mx[g] - mn), wb = __expf(om - mn);
+          l[g] = l[g] * wa + ol * wb;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float oa = __shfl_xor_sync(0xffffffffu, acc[g][i], o);
+            acc[g][i] = acc[g][i] * wa + oa * wb;
+          }
+          mx[g] = mn;
+        }
+      }
+      // ---- combine the 8 warps through shared memory (a warp whose slice is empty contributes m = -1e30, l = 0)
+      named_bar_sync(1, MG_CW * 32);  // previous unit's readers are done with sm_*
+      if (sub == 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float* po = sm_o + (size_t)warp * GD + g * D + li * 8;
+          *reinterpret_cast<float4*>(po) = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+          *reinterpret_cast<float4*>(po + 4) = make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]);
+          if (li == 0) {
+            sm_ml[(warp * G + g) * 2] = mx[g];
+            sm_ml[(warp * G + g) * 2 + 1] = l[g];
+          }
+        }
+      }
+      named_bar_sync(1, MG_CW * 32);
+      const size_t pidx = ((size_t)m * HU + hu) * a.max_chunks + sp;
+      for (int e = tid; e < GD; e += MG_CW * 32) {  // thread e owns output dim e of the unit
+        const int g = e / D;
+        float M2 = -1e30f;
+#pragma unroll
+        for (int w = 0; w < MG_CW; ++w) M2 = fmaxf(M2, sm_ml[(w * G + g) * 2]);
+        float L2 = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < MG_CW; ++w) {
+          const float wt = __expf(sm_ml[(w * G + g) * 2] - M2);
+          L2 += sm_ml[(w * G + g) * 2 + 1] * wt;
+          O += sm_o[(size_t)w * GD + e] * wt;
+        }
+        if (n_active == 1) {
+          a.attn[(size_t)m * HD + (size_t)hu * GD + e] = __float2bfloat16_rn(O / L2);
+        } else {
+          a.part_o[pidx * GD + e] = O;
+          if (e % D == 0) {
+            a.part_ml[(pidx * G + g) * 2] = M2;
+            a.part_ml[(pidx * G + g) * 2 + 1] = L2;
+          }
+        }
+      }
+      if (n_active == 1) continue;
+      __threadfence();
+      named_bar_sync(1, MG_CW * 32);
+      if (tid == 0) *sm_flag = (atomicAdd(&a.counters[m * HU + hu], 1) == n_active - 1);
+      named_bar_sync(1, MG_CW * 32);
+      if (!*sm_flag) continue;
+      __threadfence();
+      const size_t pb = ((size_t)m * HU + hu) * a.max_chunks;
+      for (int e = tid; e < GD; e += MG_CW * 32) {
+        const int g = e / D;
+        float M2 = -1e30f;
+        for (int c = 0; c < n_active; ++c) M2 = fmaxf(M2, __ldcg(&a.part_ml[((pb + c) * G + g) * 2]));
+        float L2 = 0.f, O = 0.f;
+        for (int c = 0; c < n_active; ++c) {
+          const float wt = __expf(__ldcg(&a.part_ml[((pb + c) * G + g) * 2]) - M2);
+          L2 += __ldcg(&a.part_ml[((pb + c) * G + g) * 2 + 1]) * wt;
+          O += __ldcg(&a.part_o[(pb + c) * GD + e]) * wt;
+        }
+        a.attn[(size_t)m * HD + (size_t)hu * GD + e] = __float2bfloat16_rn(O / L2);
+      }
+      if (tid == 0) a.counters[m * HU + hu] = 0;
+    }
+    base = (base + n_units) % n_ctas;
   }
 }
 
@@ -777,8 +996,8 @@ SSB_DEVINL void tp_reduce_cta(const MegaArgs& a, int seq, int tid) {
 // push of the allreduce in between, which this CTA issues only after the grid barrier that follows these reads.
 SSB_DEVINL void tp_reduce_ll(const MegaArgs& a, int seq, uint32_t epoch, int tid) {
   const int P = a.hidden >> 1;
-  const int p0 = (int)(((long long)blockIdx.x * P) / gridDim.x);
-  const int p1 = (int)(((long long)(blockIdx.x + 1) * P) / gridDim.x);
+  int p0, p1;
+  part_range(P, p0, p1);  // the pairs this CTA computed and pushed (consume<EPI_LL>); other ranks may cut differently
   const int np = p1 - p0;
   const uint4* base = a.peer_ll[a.tp_rank] + (size_t)(seq & 1) * (size_t)a.ll_parity_stride;
   SpinGuard sg;
@@ -815,11 +1034,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = a.hidden;
 
+  const bool weighted = a.sm_weight != nullptr && a.cta_weight != nullptr && a.tp_mode != 2 && gridDim.x <= MG_MAX_CTAS;
   if (tid == 0) {
     for (int s = 0; s < a.n_stages; ++s) {
       mbar_init(&full[s], MG_PW);
       mbar_init(&empty[s], MG_CW);
     }
+    mbar_init(&s_part_bar, 1);
+    s_weighted = 0;  // the embedding phase and the table build run before the table exists
     fence_mbar_init();
   }
   __syncthreads();
@@ -831,6 +1053,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     const uint64_t pol = policy_evict_first();
     const int pw = warp - MG_CW;
     Ahead ah;
+    if (weighted) mbar_wait(&s_part_bar, 0);  // row shares by SM speed: built by the consumers after the first grid barrier
 
     for (int l = 0; l < a.n_layers; ++l) {
       const MegaLayer& w = a.layers[l];
@@ -858,6 +1081,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     *a.step += 1;
     if (a.fwd_counter) *a.fwd_counter += 1;
   }
+  if (weighted && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.cta_weight[blockIdx.x] = a.sm_weight[smid & 255u];
+  }
   // embedding gather, distributed over all consumer threads of the grid
   {
     const int per_row = h / 8;
@@ -867,6 +1095,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     }
   }
   grid_sync(a.grid_bar, n_sync, n_ctas);
+  if (weighted) {  // every CTA builds the same cumulative-share table from the same published weights
+    if (warp == 0) {
+      for (unsigned i = lane; i < n_ctas; i += 32) s_cw[i] = __ldcg(a.cta_weight + i);
+      __syncwarp();
+      if (lane == 0) {
+        double tot = 0.0;
+        for (unsigned i = 0; i < n_ctas; ++i) tot += (double)s_cw[i];
+        double cum = 0.0;
+        for (unsigned i = 0; i < n_ctas; ++i) {
+          s_cumq[i] = (uint32_t)fmin(4294967295.0, cum / tot * 4294967296.0);
+          cum += (double)s_cw[i];
+        }
+        s_cumq[n_ctas] = 0xFFFFFFFFu;
+        s_weighted = 1;
+      }
+    }
+    named_bar_sync(1, MG_CW * 32);
+    if (tid == 0) mbar_arrive(&s_part_bar);  // releases the producers (the mbarrier arrive orders the table before their reads)
+  }
   // epoch of allreduce `seq` of this forward = ll_epoch0 + seq (never 0; the forward counter was bumped above and is
   // visible through the grid barrier)
   [[maybe_unused]] uint32_t ll_epoch0 = 0;
@@ -907,7 +1154,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
       else
         attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
     } else {
-      attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
+      if (a.attn_coop)
+        attention_phase_coop<D, G>(a, w.kcache, w.vcache, reinterpret_cast<float*>(xs), reinterpret_cast<int*>(red + 16), tid, warp, lane);
+      else
+        attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
     }
     MG_STAMP();  // 4: attention done
     grid_sync(a.grid_bar, n_sync, n_ctas);
@@ -1047,10 +1297,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 }
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages) {
-  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128 + (MG_CW > 8 ? 128 : 0);
+  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128 + (MG_CW > 8 ? 128 : 0);  // dynamic part
 }
 
 int mega_pick_stages(int bt, int k_max) {
+  // 227 KiB per CTA in all; ~1.7 KiB of that is static (the row-share table s_cumq / s_cw), so 225 KiB for the dynamic part
   int s = 6;
   while (s > 2 && mega_smem_bytes(bt, k_max, s) > 225 * 1024) --s;
   return mega_smem_bytes(bt, k_max, s) <= 225 * 1024 ? s : 0;
@@ -1061,7 +1312,7 @@ static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
   const size_t smem = mega_smem_bytes(BT, a.k_max, a.n_stages);
   static unsigned long long attr_mask = 0;  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);  // + ~1.7 KiB static <= 227 KiB
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1127,3 +1378,4 @@ cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc) {
 int mega_attn_group(int group) { return (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1; }
 int mega_attn_chunk(int head_dim, int g) { return (32 / (head_dim / 8)) * (g <= 2 ? 8 : 2); }
 size_t mega_attn_tile_bytes(int head_dim) { return (size_t)2 * MG_ATT_TILE * head_dim * 2; }
+size_t mega_attn_coop_bytes(int head_dim, int g) { return (size_t)MG_CW * g * (head_dim + 2) * sizeof(float); }

@@ -58,11 +58,15 @@ struct MegaArgs {
   long long ll_parity_stride, ll_src_stride;  // in uint4 units
   int prof_all;                      // params.mega_prof = 2: every CTA stamps
   int attn_cta_tile;                 // GQA groups of 8: one (row, KV head, split) per CTA with K/V staged in shared memory
+  int attn_coop;                     // groups of 1 / 2 / 4: one (row, head unit, split) per CTA, warps combined through shared memory
+  const float* sm_weight;            // [256] relative streaming speed of each SM (by %smid), null = equal row shares
+  float* cta_weight;                 // [n_ctas] scratch: the weight of the SM each CTA of THIS launch runs on
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);
 int mega_pick_stages(int bt, int k_max);  // 0 if the step does not fit
 int mega_attn_group(int group);
 int mega_attn_chunk(int head_dim, int g);  // tokens per attention unit
+size_t mega_attn_coop_bytes(int head_dim, int g);  // shared memory of the CTA-cooperative attention (groups of 1 / 2 / 4)
 size_t mega_attn_tile_bytes(int head_dim);  // shared memory the CTA-tile attention stages K/V in (must fit the activation area)
 cudaError_t launch_decode_mega(const MegaArgs& a, const LaunchCfg& lc);

@@ -61,6 +61,8 @@ def _oracle(cfg, sd, prompts, ngen):
 def _teacher_forced_logits(cfg, sd, dtype, prompt_rows, forced):
     """Logits of `dtype` oracle when fed the SAME continuation `forced` ([nseq, n]) — so that step-s logits of two
     implementations are comparable even after their own greedy picks would diverge."""
+    if len({len(p) for p in prompt_rows}) > 1:  # ragged batch: one sequence at a time
+        return np.concatenate([_teacher_forced_logits(cfg, sd, dtype, [p], np.asarray(forced)[i:i + 1]) for i, p in enumerate(prompt_rows)])
     ref = llama_ref.LlamaRef(cfg, sd, dtype)
     ids = torch.tensor(prompt_rows)
     out = [ref.forward(ids)[:, -1].float()]
@@ -236,6 +238,34 @@ def test_prefill_256_token_tiles(Engine, tmp_path):
     lg = np.transpose(res[256][1], (1, 0, 2))
     _assert_parity([[rel_err(lg[i, s_], l32[i, s_]) for s_ in range(3)] for i in range(2)],
                    [[rel_err(lbf[i, s_], l32[i, s_]) for s_ in range(3)] for i in range(2)], "prefill 256-token tiles")
+
+
+@pytest.mark.parametrize("kv,inter", [(8, 4096), (4, 8192), (2, 11008)], ids=["mha", "gqa2", "gqa4"])
+def test_persistent_kernel_cooperative_attention(Engine, tmp_path, kv, inter):
+    """Groups of 1 / 2 / 4 query heads in the persistent decode kernel: one (row, head unit, context split) per CTA, the 8
+    consumer warps combine their online-softmax states through shared memory (mega.cu attention_phase_coop; the tiny
+    models of the other tests are too narrow for its staging area and keep the per-warp form).  Contexts of 9 / 300 / 900
+    tokens, batch 1 and a ragged batch of 3, against the oracle and the per-warp path ("mega_attn_tile": 0)."""
+    cfg = dict(synth.TINY_GQA, hidden_size=1024, num_attention_heads=8, num_key_value_heads=kv, intermediate_size=inter,
+               num_hidden_layers=2, vocab_size=1000, max_position_embeddings=1024)
+    sd = synth.llama_state_dict(cfg, 37)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(41)
+    mk = lambda n: torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist()
+    for prompts in ([mk(9)], [mk(300)], [mk(900)], [mk(17), mk(150), mk(333)]):
+        res = {}
+        for tile in (1, 0):
+            with Engine(str(tmp_path), {"max_batch": 4, "max_seq_len": 1000, "mega_attn_tile": tile}) as e:
+                res[tile] = e.generate(prompts, 4, want_logits=True)
+        err = rel_err(res[1][1], res[0][1])
+        assert err < 1e-2, ([len(p) for p in prompts], err)  # same math, different split of the context
+        l32 = _teacher_forced_logits(cfg, sd, torch.float32, prompts, res[1][0])
+        lbf = _teacher_forced_logits(cfg, sd, torch.bfloat16, prompts, res[1][0])
+        lg = np.transpose(res[1][1], (1, 0, 2))
+        n = len(prompts)
+        _assert_parity([[rel_err(lg[i, s_], l32[i, s_]) for s_ in range(4)] for i in range(n)],
+                       [[rel_err(lbf[i, s_], l32[i, s_]) for s_ in range(4)] for i in range(n)],
+                       f"cooperative attention kv={kv} ctx {[len(p) for p in prompts]}")
 
 
 @pytest.mark.parametrize("d", [128, 64])

@@ -44,3 +44,37 @@ def test_opt_cpu_reference_container(tmp_path):
         assert r["choices"][0]["tokens"] == want.tolist()
     finally:
         srv.shutdown()
+
+
+def test_opt_125m_real_shapes_through_the_cpu_container(tmp_path):
+    """BASELINE config 1 at its REAL shapes (examples/facebook-opt-125m/base-server.yaml:1-8: no resources => CPU): h768 L12
+    H12 ffn3072 V50272, random init (no checkpoints offline), one greedy request through `/v1/completions` equals HF
+    generate() id for id, and the response carries the timing fields bench.py's opt_125m_cpu_container sub-object reports."""
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    (tmp_path / "config.json").write_text(json.dumps(bench.WORKLOADS["opt-125m"]))
+    ref_server.State.ready = False
+    srv = ref_server.serve(str(tmp_path), 0, "float32")
+    port = srv.server_address[1]
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        for _ in range(1200):
+            try:
+                if _req(f"http://127.0.0.1:{port}/")[0] == 200:
+                    break
+            except Exception:
+                pass
+            time.sleep(0.1)
+        assert ref_server.State.ready and sum(p.numel() for p in ref_server.State.model.parameters()) > 120e6
+        prompt = torch.tensor([bench.synthetic_prompts(50272, 1, 16)[0]])
+        st, r = _req(f"http://127.0.0.1:{port}/v1/completions", {"prompt": prompt[0].tolist(), "max_tokens": 8})
+        assert st == 200 and r["usage"] == {"prompt_tokens": 16, "completion_tokens": 8}
+        assert r["decode_tokens_per_sec"] > 0 and r["ttft_ms"] > 0
+        with torch.no_grad():
+            want = ref_server.State.model.generate(prompt, max_new_tokens=8, do_sample=False, pad_token_id=1)[0, 16:]
+        assert r["choices"][0]["tokens"] == want.tolist()
+    finally:
+        srv.shutdown()

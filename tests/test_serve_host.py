@@ -234,10 +234,18 @@ def test_serve_stream_and_batching_on_the_real_engine(tmp_path):
         with cf.ThreadPoolExecutor(6) as ex:  # concurrent: requests share decode calls (ragged lengths, late joiners)
             conc = list(ex.map(lambda pr: _get(base + "/generate", {"tokens": pr, "max_new_tokens": 9})[1]["tokens"], prompts))
             streamed = list(ex.map(stream, prompts))
-        # batch-mates change the GEMM path (GEMV below 8 rows, tensor-core tiles above), so a rounding-level tie may flip
-        # a greedy pick and everything after it: most sequences must still agree completely with their solo run
-        for got in (conc, streamed):
+        # batch-mates change the GEMM schedule (GEMV below 8 rows, tensor-core tiles above), so a rounding-level tie may flip
+        # a greedy pick and everything after it.  The strict statement that survives that: EVERY id of EVERY sequence is the
+        # fp32 oracle's greedy pick for its own context, or a tie within bf16 noise (util.assert_greedy_valid) — and most
+        # sequences still equal their solo run id for id.
+        from util import assert_greedy_valid
+
+        sd = synth.llama_state_dict(cfg, 3)
+        for name, got in (("solo", plain), ("concurrent", conc), ("concurrent streamed", streamed)):
             assert all(len(a) == 9 and all(0 <= t < cfg["vocab_size"] for t in a) for a in got)
-            assert sum(a == b for a, b in zip(got, plain)) >= 3, (got, plain)
+            exact = assert_greedy_valid(cfg, sd, prompts, got, name)
+            assert exact >= 9 * len(prompts) - 6, (name, exact)
+        for got in (conc, streamed):
+            assert sum(a == b for a, b in zip(got, plain)) >= 4, (got, plain)
     finally:
         p.kill()

@@ -87,3 +87,45 @@ def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     ref32 = llama_ref.LlamaRef(cfg, sd, torch.float32).forward(torch.tensor([prompts[1]]))[0, -1].numpy()
     refbf = llama_ref.LlamaRef(cfg, sd, torch.bfloat16).forward(torch.tensor([prompts[1]]))[0, -1].float().numpy()
     assert rel_err(ltp[0, 1], ref32) <= rel_err(refbf, ref32) + 1e-3
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv"}, {"gemm_path": "tc"}], ids=["gemv", "tc"])
+def test_falcon_tp_matches_tp1_and_oracle(tmp_path, world, mode):
+    """BASELINE config 4 is Falcon-40B at TP2 / TP4: the Falcon layout under tensor parallelism (fused QKV sharded by KV
+    group, ONE allreduce per layer for the parallel block: attention and MLP partials are summed locally first) against
+    TP1 and the Falcon oracle."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from oracle import falcon_ref as fr
+    from substratus_b200 import Engine
+
+    cfg = dict(fr.TINY_FALCON, hidden_size=512, num_attention_heads=8, num_kv_heads=4)
+    sd = fr.falcon_state_dict(cfg, 29)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd)
+    gen = torch.Generator().manual_seed(6)
+    prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (21, 37)]
+    ngen = 6
+    with Engine(str(tmp_path), dict(mode, max_batch=4, max_seq_len=160)) as e:
+        t1, l1 = e.generate(prompts, ngen, want_logits=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, str(tmp_path), prompts, ngen, mode, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in ps], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+    for r, toks, _ in res:
+        assert not isinstance(toks, str), f"rank {r}: {toks}"
+        assert np.array_equal(toks, res[0][1]), f"rank {r} diverged"
+    ltp = res[0][2]
+    e1 = rel_err(ltp[0], l1[0])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_tp.txt", "a") as f:
+        f.write(f"[falcon tp{world} {mode}] first-step logits rel err vs TP1 {e1:.3e}\n")
+    assert e1 < 1.5e-2, e1
+    ref32 = fr.FalconRef(cfg, sd, torch.float32).forward(torch.tensor([prompts[1]]))[0, -1].numpy()
+    refbf = fr.FalconRef(cfg, sd, torch.bfloat16).forward(torch.tensor([prompts[1]]))[0, -1].float().numpy()
+    assert rel_err(ltp[0, 1], ref32) <= 1.5 * rel_err(refbf, ref32) + 1e-3

@@ -37,3 +37,32 @@ def rel_err(a, ref):
     a = np.asarray(a, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.abs(a - ref).max() / np.abs(ref).max())
+
+
+def assert_greedy_valid(cfg, sd, prompts, toks, what=""):
+    """Every id in toks[i] must be a valid greedy pick for ITS OWN context: the fp32 oracle, teacher-forced with the ids
+    under test, must either pick the same id or separate the two candidates by less than the bf16 noise (4 x the largest
+    bf16-vs-fp32 logit difference of the oracle itself).  Unlike comparing with a solo run, this holds however batch-mates
+    change the GEMM schedule.  Returns the number of exact matches."""
+    import torch
+
+    from oracle import llama_ref
+
+    exact = 0
+    r32 = llama_ref.LlamaRef(cfg, sd, torch.float32)
+    rbf = llama_ref.LlamaRef(cfg, sd, torch.bfloat16)
+    for p, t in zip(prompts, toks):
+        ids = torch.tensor([list(p) + [int(x) for x in t[:-1]]])
+        r32.reset()
+        rbf.reset()
+        l32 = r32.forward(ids)[0, len(p) - 1:].float().numpy()
+        lbf = rbf.forward(ids)[0, len(p) - 1:].float().numpy()
+        noise = 4 * float(np.abs(lbf - l32).max())
+        for s_, tok in enumerate(t):
+            want = int(l32[s_].argmax())
+            if want == int(tok):
+                exact += 1
+                continue
+            gap = float(l32[s_, want] - l32[s_, int(tok)])
+            assert gap < noise, f"{what}: prompt len {len(p)} step {s_}: got {tok}, fp32 oracle picks {want} with margin {gap:.4g} >= noise {noise:.4g}"
+    return exact

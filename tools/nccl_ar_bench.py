@@ -1,6 +1,6 @@
 """NCCL baseline for the decode allreduce ("baseline ncclAllReduce on a per-device stream inside the CUDA
-graph"): latency of torch.distributed.all_reduce(sum) on the decode-sized message ([1, hidden] fp32 = 16-32 KiB), 64
-calls captured in ONE CUDA graph (no launch overhead from the host), max over ranks.  This is the number the engine's own
+graph"): latency of torch.distributed.all_reduce(sum) on the decode-sized message ([1, hidden] fp32 = 16-32 KiB), 640
+stream-ordered calls (the host enqueues far ahead of the device, so this is device time), max over ranks.  This is the number the engine's own
 exchange (in-kernel LL push, or the one-shot pull kernel) has to beat.
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/nccl_ar_bench.py"""
 import json
@@ -19,22 +19,15 @@ for hidden in (4096, 8192):
         for _ in range(5):
             dist.all_reduce(x)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        with torch.cuda.stream(s):
-            with torch.cuda.graph(g, stream=s):
-                for _ in range(64):
-                    dist.all_reduce(x)
-                    x.mul_(1.0 / dist.get_world_size())  # a dependent op between allreduces, like the decode step
-        for _ in range(3):
-            g.replay()
-        torch.cuda.synchronize()
+        # stream-ordered loop (no graph: NCCL capture needs a warmed-up communicator per stream and hung on this image);
+        # 640 back-to-back allreduces with one dependent elementwise kernel in between, like the decode step's residual add
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
-            g.replay()
+        for _ in range(640):
+            dist.all_reduce(x)
+            x.mul_(1.0 / dist.get_world_size())
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) * 1e3 / 640], device="cuda")

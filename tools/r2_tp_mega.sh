@@ -6,7 +6,7 @@
 #   gpurun --gpus 2 --timeout 900 -- 'bash tools/r2_tp_mega.sh 2'
 #   gpurun --gpus 4 --timeout 1200 -- 'bash tools/r2_tp_mega.sh 4 llama2-70b'
 # A variant library applies to every rank when exported: SSB_LIB_VARIANT=fhfma bash tools/r2_tp_mega.sh 4 llama2-70b
-# (the mixed-FMA projection loop also serves gemv_kernel, i.e. the default TP decode path).
+# (the mixed-FMA projection loop also serves proj_rows_kernel, i.e. the default TP decode path).
 set -u
 N=${1:-2}
 WL=${2:-llama2-7b}
