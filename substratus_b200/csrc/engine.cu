@@ -535,14 +535,15 @@ int Engine::alloc_runtime(const Json& params) {
       tp_pool_bytes_ += 8 * 256 * sizeof(uint32_t);
       TRY(dmalloc(&d_peer_cta_flags_, 8));
     }
-    if (tp_mega_mode_ == 3) {
+    tp_ll_ = params.get_int("tp_ll", 1) != 0;  // decode-sized allreduce of the multi-kernel path: LL push kernel (0 = one-shot pull)
+    if (tp_mega_mode_ == 3 || tp_ll_) {
       tp_off_ll_ = (tp_pool_bytes_ + 255) & ~(size_t)255;
       tp_pool_bytes_ = tp_off_ll_ + 2 * 8 * 4 * (size_t)(h / 2) * sizeof(uint4);
       TRY(dmalloc(&d_peer_ll_, 8));
     }
     TRY(dmalloc(&tp_pool_, tp_pool_bytes_));
     if (tp_mega_mode_ == 2) CK(cudaMemset(tp_pool_ + tp_off_ctaflags_, 0, 8 * 256 * sizeof(uint32_t)));
-    if (tp_mega_mode_ == 3) CK(cudaMemset(tp_pool_ + tp_off_ll_, 0, tp_pool_bytes_ - tp_off_ll_));  // epoch 0 = never written
+    if (tp_off_ll_) CK(cudaMemset(tp_pool_ + tp_off_ll_, 0, tp_pool_bytes_ - tp_off_ll_));  // epoch 0 = never written
     CK(cudaMemset(tp_pool_ + tp_off_flags_, 0, 128));
     tp_partials_ = (float*)tp_pool_;
     tp_recv_ = (float*)(tp_pool_ + tp_off_recv_);
@@ -815,6 +816,13 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
     ta.out = h_;
     ta.variant = 1;  // st.release.sys alone orders the partials before the flag (measured 1.4 us faster than fence + store)
   }
+  // decode-sized forwards (<= 4 rows): the allreduce kernel pushes 16-byte {value, epoch} words and polls its own slots
+  // (one NVLink one-way latency) instead of flag + pull (kernels.cu: tp_allreduce_ll_kernel)
+  const bool tp_ll = tp && tp_ll_ && tp_off_ll_ && M <= 4 && !tp_push;
+  TpLlArgs tl = {};
+  tl.peer_ll = d_peer_ll_;
+  tl.src_stride = 4LL * (h / 2);
+  tl.parity_stride = 8 * tl.src_stride;
   // experimental: prefill-sized forwards reduce-scatter + gather bf16 slices instead of pulling every peer's full partial
   const bool tp_two = tp && tp_two_shot_ && M >= tp_two_shot_min_rows_;
   TpArgs2 t2 = {};
@@ -965,7 +973,10 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
       ++launches;
     } else if (tp) {
       ta.seq_in_step = 2 * l;
-      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      if (tp_ll)
+        CK(launch_tp_allreduce_ll(ta, tl, lc(true)));
+      else
+        CK(launch_tp_allreduce_resid(ta, lc(true)));
       ++launches;
     }
 
@@ -1017,7 +1028,10 @@ int Engine::forward(int M, int n_logit_rows, bool decode_mode) {
       ++launches;
     } else if (tp) {
       ta.seq_in_step = 2 * l + 1;
-      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      if (tp_ll)
+        CK(launch_tp_allreduce_ll(ta, tl, lc(true)));
+      else
+        CK(launch_tp_allreduce_resid(ta, lc(true)));
       ++launches;
     }
     launches += 5;
@@ -1313,7 +1327,15 @@ int Engine::forward_falcon(int M, int n_logit_rows, bool decode_mode) {
     launches += 5;
     if (tp) {
       ta.seq_in_step = l;
-      CK(launch_tp_allreduce_resid(ta, lc(true)));
+      if (tp_ll_ && tp_off_ll_ && M <= 4) {
+        TpLlArgs tl = {};
+        tl.peer_ll = d_peer_ll_;
+        tl.src_stride = 4LL * (h / 2);
+        tl.parity_stride = 8 * tl.src_stride;
+        CK(launch_tp_allreduce_ll(ta, tl, lc(true)));
+      } else {
+        CK(launch_tp_allreduce_resid(ta, lc(true)));
+      }
       ++launches;
     }
     if (taps_ && l == 0) {
@@ -1509,6 +1531,12 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
   }
   int variant = 0;       // "allreduce@v<bits>[n]": latency experiments, trailing 'n' = no PDL
   bool bench_pdl = true;
+  bool bench_ll = false;
+  if (w == "allreduce_ll" || w == "allreduce_lln") {
+    bench_ll = true;
+    bench_pdl = w.back() != 'n';
+    w = "allreduce";
+  }
   if (w.rfind("allreduce@v", 0) == 0) {
     variant = atoi(w.c_str() + 11);
     if (w.back() == 'n') bench_pdl = false;
@@ -1671,7 +1699,16 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       ta.out = h_;
       ta.variant = variant;
       bytes = (int64_t)(tp_size_ - 1) * rows * h * 4;
-      CK(launch_tp_allreduce_resid(ta, lc(bench_pdl)));
+      if (bench_ll) {  // "allreduce_ll": the LL push kernel (decode-sized forwards of the multi-kernel path)
+        if (!tp_off_ll_ || rows > 4) RET(SSB_ESTATE, "allreduce_ll needs params.tp_ll / tp_mega 3 and rows <= 4");
+        TpLlArgs tl = {};
+        tl.peer_ll = d_peer_ll_;
+        tl.src_stride = 4LL * (h / 2);
+        tl.parity_stride = 8 * tl.src_stride;
+        CK(launch_tp_allreduce_ll(ta, tl, lc(bench_pdl)));
+      } else {
+        CK(launch_tp_allreduce_resid(ta, lc(bench_pdl)));
+      }
     } else {
       RET(SSB_EINVAL, "unknown kernel '" + w + "' (qkv|o|gate_up|down|lm_head|attn|allreduce)");
     }
@@ -1775,7 +1812,7 @@ int Engine::tp_connect(const void* all, int n) {
     for (int r = 0; r < n; ++r) pc[r] = (uint32_t*)(pool[r] + tp_off_ctaflags_);
     CK(cudaMemcpy(d_peer_cta_flags_, pc.data(), 8 * sizeof(uint32_t*), cudaMemcpyHostToDevice));
   }
-  if (tp_mega_mode_ == 3) {
+  if (tp_off_ll_) {
     std::vector<uint4*> pl(8, nullptr);
     for (int r = 0; r < n; ++r) pl[r] = (uint4*)(pool[r] + tp_off_ll_);
     CK(cudaMemcpy(d_peer_ll_, pl.data(), 8 * sizeof(uint4*), cudaMemcpyHostToDevice));

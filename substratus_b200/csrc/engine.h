@@ -150,6 +150,7 @@ class Engine {
   uint32_t** d_peer_cta_flags_ = nullptr;
   // "tp_mega": 3 — LL push receive buffers [2 parity][8 src][4 rows][hidden/2] uint4, appended to the exchange pool
   size_t tp_off_ll_ = 0;
+  bool tp_ll_ = true;  // params "tp_ll": LL push allreduce kernel for decode-sized forwards of the multi-kernel path
   uint4** d_peer_ll_ = nullptr;
   // taps
   bf16 *tap_q0_ = nullptr, *tap_attn0_ = nullptr, *tap_h0_ = nullptr;

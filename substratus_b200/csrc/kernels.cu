@@ -866,6 +866,66 @@ __global__ void __launch_bounds__(TP_THREADS) tp_reduce_push_kernel(const TpPush
   }
 }
 
+// LL push allreduce for decode-sized forwards of the multi-kernel path (Falcon, "use_mega": 0, "tp_mega": 0): thread =
+// one (row, pair).  It reads its fp32 partial pair (this rank's projection output), stores {v0, epoch, v1, epoch} into slot
+// [parity][rank][row][pair] of EVERY rank (own included) with one 16-byte store each, then polls its own slots of all source
+// ranks until both epoch halves match, sums in rank order (bit-identical on every rank), adds the residual.  No flag, no
+// fence, no remote read: one NVLink one-way latency.  Slot reuse: parity double-buffering + stream order (a rank launches
+// allreduce k+2 after its k+1 completed, which needed every peer's k+1 pushes, issued after that peer finished reading k).
+SSB_DEVINL void st_relaxed_sys_v4(uint4* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SSB_DEVINL uint4 ld_relaxed_sys_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(TP_THREADS) tp_allreduce_ll_kernel(const TpArgs a, const TpLlArgs l) {
+  pdl_wait();  // this rank's partials (previous kernel) are complete and visible
+  pdl_launch_dependents();
+  const uint32_t epoch = (uint32_t)(*a.tp_step) * (uint32_t)a.n_per_step + (uint32_t)a.seq_in_step + 1u;
+  const int parity = a.seq_in_step & 1;
+  const int P = a.hidden >> 1;
+  const int total = a.M * P;
+  const float* mine = a.peer_partials[a.rank] + (size_t)parity * a.parity_stride;
+  const size_t base = (size_t)parity * (size_t)l.parity_stride;
+  SpinGuard sg;
+  for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < total; i += gridDim.x * TP_THREADS) {
+    const int m = i / P, p = i - m * P;
+    const float2 v = *reinterpret_cast<const float2*>(mine + (size_t)m * a.hidden + 2 * p);
+    const uint4 w = make_uint4(__float_as_uint(v.x), epoch, __float_as_uint(v.y), epoch);
+    const size_t o = base + (size_t)a.rank * (size_t)l.src_stride + (size_t)m * P + p;
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r)
+      if (r < a.size) st_relaxed_sys_v4(l.peer_ll[r] + o, w);
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TP_MAX; ++r) {
+      if (r < a.size) {
+        const uint4* slot = l.peer_ll[a.rank] + base + (size_t)r * (size_t)l.src_stride + (size_t)m * P + p;
+        uint4 x = ld_relaxed_sys_v4(slot);
+        while (x.y != epoch || x.w != epoch) {
+          sg.poll();
+          x = ld_relaxed_sys_v4(slot);
+        }
+        s.x += __uint_as_float(x.x);
+        s.y += __uint_as_float(x.z);
+      }
+    }
+    const size_t ho = (size_t)m * a.hidden + 2 * (size_t)p;
+    const uint32_t rv = *reinterpret_cast<const uint32_t*>(a.resid + ho);
+    *reinterpret_cast<uint32_t*>(a.out + ho) = pack_bf16(bf16r(s.x) + bf_lo(rv), bf16r(s.y) + bf_hi(rv));
+  }
+}
+
+cudaError_t launch_tp_allreduce_ll(const TpArgs& a, const TpLlArgs& l, const LaunchCfg& lc) {
+  if (a.size > TP_MAX || (a.hidden & 1) || a.M > 4 || !l.peer_ll) return cudaErrorInvalidValue;
+  const int total = a.M * (a.hidden >> 1);
+  int grid = (total + TP_THREADS - 1) / TP_THREADS;  // every thread spins: all CTAs must be co-resident (<= 64 CTAs of 256 threads)
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  return launch_ex(tp_allreduce_ll_kernel, dim3(grid), dim3(TP_THREADS), 0, lc, a, l);
+}
+
 cudaError_t launch_tp_reduce_push(const TpPushArgs& a, const LaunchCfg& lc) {
   if (a.size > TP_MAX || (a.hidden & 3)) return cudaErrorInvalidValue;
   const int total4 = a.M * a.hidden / 4;
@@ -884,43 +944,61 @@ cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc) {
 
 
 // =====================================================================================================================
-// Per-SM streaming-speed calibration (engine creation, once per device): one CTA per SM (the shared-memory request keeps
-// it to one), all resident at once so HBM is saturated the way the persistent decode kernel saturates it; every CTA
-// streams its own slice of a scratch buffer much larger than L2 and reports %smid and its elapsed time.  SMs farther
-// from their L2 slices / across the die boundary get a smaller share of the bandwidth — systematically.
+// Per-SM streaming-speed calibration (engine creation, once per device): one CTA per SM, all resident at once so HBM is
+// loaded the way the persistent decode kernel loads it, and every CTA streams its own slice of a scratch buffer much larger
+// than L2 EXACTLY like that kernel's producer: 2 KiB bulk copies into a ring of six 32 KiB stages, a stage re-armed as soon
+// as its bytes have landed — 192 KiB in flight per SM, no consumer.  An SM whose loaded HBM latency is longer (far-die
+// TPCs) is latency-bound at that depth and streams slower; a plain LDG stream does not show it (the first calibration of
+// round 2 measured equal times).  out[2b] = %smid of CTA b, out[2b+1] = ns for bytes_per_cta.
 // =====================================================================================================================
-__global__ void __launch_bounds__(256, 1) sm_calib_kernel(const uint4* __restrict__ src, size_t n16_per_cta, unsigned long long* __restrict__ out) {
-  extern __shared__ uint8_t calib_smem[];
-  const uint4* p = src + (size_t)blockIdx.x * n16_per_cta;
-  unsigned long long t0, t1;
-  __syncthreads();
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  uint32_t sink = 0;
-  for (size_t i = threadIdx.x; i + 7 * 256 < n16_per_cta; i += 8 * 256) {
-    uint4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + i + (size_t)u * 256);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) sink ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+__global__ void __launch_bounds__(128, 1) sm_calib_kernel(const uint8_t* __restrict__ src, size_t bytes_per_cta, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t calib_smem[];
+  constexpr int NS = 6, STAGE = 32 * 1024, ROW = 2048, RPS = STAGE / ROW;
+  uint64_t* full = reinterpret_cast<uint64_t*>(calib_smem + NS * STAGE);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
   }
   __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const uint8_t* p = src + (size_t)blockIdx.x * bytes_per_cta;
+  const size_t n_fills = bytes_per_cta / STAGE;
+  const uint64_t pol = policy_evict_first();
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  int stage = 0;
+  uint32_t phase = 0;
+  for (size_t f = 0; f < n_fills; ++f) {
+    if (f >= NS) mbar_wait(&full[stage], phase ^ 1);  // the previous fill of this stage has landed
+    if (lane == 0) mbar_expect_tx(&full[stage], STAGE);
+    __syncwarp();
+    if (lane < RPS) bulk_g2s_hint(calib_smem + (size_t)stage * STAGE + lane * ROW, p + f * STAGE + (size_t)lane * ROW, ROW, &full[stage], pol);
+    if (++stage == NS) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+  for (int s = 0; s < NS && (size_t)s < n_fills; ++s) {  // drain: the last fill of every stage
+    const size_t fills_s = (n_fills - s + NS - 1) / NS;
+    mbar_wait(&full[s], (uint32_t)((fills_s - 1) & 1));
+  }
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     out[2 * blockIdx.x] = smid;
     out[2 * blockIdx.x + 1] = t1 - t0;
   }
-  if (sink == 0x12345678u) calib_smem[threadIdx.x] = 1;  // keep the loads
 }
 
 cudaError_t launch_sm_calib(const void* src, size_t bytes_per_cta, int n_ctas, unsigned long long* out, cudaStream_t s) {
   static unsigned long long attr_mask = 0;
-  const int smem = 160 * 1024;  // > half of an SM's shared memory: one CTA per SM
+  const int smem = 6 * 32 * 1024 + 64;  // the ring: also keeps it to one CTA per SM
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(sm_calib_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
   }
-  sm_calib_kernel<<<n_ctas, 256, smem, s>>>(reinterpret_cast<const uint4*>(src), bytes_per_cta / 16, out);
+  sm_calib_kernel<<<n_ctas, 128, smem, s>>>(reinterpret_cast<const uint8_t*>(src), bytes_per_cta, out);
   return cudaGetLastError();
 }

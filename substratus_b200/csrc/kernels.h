@@ -138,6 +138,13 @@ struct TpArgs {
                                  // into the peers' slots, read locally)
 };
 cudaError_t launch_tp_allreduce_resid(const TpArgs& a, const LaunchCfg& lc);
+// decode-sized (M <= 4) allreduce + residual with the LL wire format (16-byte {v0, epoch, v1, epoch} pushed into every
+// rank's receive slots [parity][src][row][pair], receiver polls its own slots): same TpArgs (partials, epoch, residual)
+struct TpLlArgs {
+  uint4* const* peer_ll;                 // [size] peer-mapped receive buffers
+  long long parity_stride, src_stride;   // in uint4 units
+};
+cudaError_t launch_tp_allreduce_ll(const TpArgs& a, const TpLlArgs& l, const LaunchCfg& lc);
 
 // two-shot allreduce for prefill-sized activations (tp_twoshot.cu; params "tp_two_shot", experimental): each rank
 // reduces its 1/size slice and the bf16 slices are gathered through `peer_gather` (one [rows_max][hidden] bf16 buffer per

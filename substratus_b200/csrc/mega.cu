@@ -210,6 +210,15 @@ SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
 #if MG_L2_AHEAD > 0
+#if MG_L2_MIN_AHEAD > 0
+      // keep a floor of prefetched fills ahead of the copies even in steady streaming: an SM whose loaded HBM latency exceeds
+      // what 192 KiB in flight covers (the far-die TPCs: tools/mega_skew.py) is latency-bound on the ring alone; with the
+      // next fills already in L2 its copies complete at L2 latency
+      while (ah.live && ah.dist < MG_L2_MIN_AHEAD) {
+        ah.step(ma, lane, pw, true);
+        ++ah.dist;
+      }
+#endif
       // ring full: use the wait to pull the stream further into L2 (see MG_L2_AHEAD above)
       while (!mbar_try_wait(&empty[r.stage], r.phase ^ 1)) {
         if (ah.live && ah.dist < MG_L2_AHEAD) {

@@ -42,15 +42,16 @@ def _worker(rank, world, port, model_dir, prompts, ngen, mode, q):
         dist.destroy_process_group()
 
 
-# Decode exchange modes (csrc/mega.h): "tp_mega" 0 = multi-kernel path with the one-shot pull allreduce kernel, 1 / 2 = persistent
+# Decode exchange modes (csrc/mega.h): "tp_mega" 0 = multi-kernel path with an allreduce kernel per row-parallel projection
+# ("tp_ll": 1 LL push kernel for <= 4 rows, default; 0 one-shot pull kernel), 1 / 2 = persistent
 # kernel with grid-wide / per-CTA flag + pull, 3 (engine default) = persistent kernel with the 16-byte {value, epoch} push.
 # {"tp_two_shot": 1}: reduce-scatter + bf16 gather allreduce for prefill-sized forwards (csrc/tp_twoshot.cu).
 # All of them first ran on 2 x B200 in round 2 (profiles/r02_tp_parity_n2.log).
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", [{"gemm_path": "gemv", "tp_mega": 0}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
+@pytest.mark.parametrize("mode", [{"gemm_path": "gemv", "tp_mega": 0}, {"gemm_path": "gemv", "tp_mega": 0, "tp_ll": 0}, {"gemm_path": "tc"}, {"gemm_path": "gemv", "tp_mega": 1},
                                   {"gemm_path": "tc", "tp_two_shot": 1, "tp_two_shot_min_rows": 16}, {"gemm_path": "gemv", "tp_mega": 2},
                                   {"gemm_path": "gemv", "tp_mega": 3}, {}],
-                         ids=["gemv_multikernel", "tc", "tp_mega1", "two_shot", "tp_mega2", "tp_mega3", "default"])
+                         ids=["gemv_multikernel_ll", "gemv_multikernel_pull", "tc", "tp_mega1", "two_shot", "tp_mega2", "tp_mega3", "default"])
 def test_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -12,7 +12,7 @@ d = tempfile.mkdtemp()
 json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
 e = Engine(d, {"weights": "synthetic", "max_batch": 4, "max_seq_len": 128, "tp_size": world, "tp_rank": rank, "device": lr})
 tp.connect(e)
-for name in ("allreduce@v0", "allreduce@v1", "allreduce@v2", "allreduce@v3", "allreduce@v0n", "allreduce@v3n", "allreduce@v4", "allreduce@v6", "allreduce@v7", "allreduce@v7n"):
+for name in ("allreduce_ll", "allreduce_lln", "allreduce@v0", "allreduce@v1", "allreduce@v2", "allreduce@v3", "allreduce@v0n", "allreduce@v3n", "allreduce@v4", "allreduce@v6", "allreduce@v7", "allreduce@v7n"):
     dist.barrier()
     ms, _ = e.bench_kernel(name, rows=1, ctx=64, iters=300)
     t = tp.max_over_ranks(ms)

@@ -12,7 +12,8 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 cfg = bench.WORKLOADS[wl]
 d = tempfile.mkdtemp()
 json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
-e = Engine(d, {"weights": "synthetic", "max_batch": 4, "max_seq_len": 700, "mega_prof": 2})
+extra = json.loads(sys.argv[3]) if len(sys.argv) > 3 else {}
+e = Engine(d, dict({"weights": "synthetic", "max_batch": 4, "max_seq_len": 700, "mega_prof": 2}, **extra))
 rng = np.random.default_rng(0)
 prompts = [rng.integers(0, cfg["vocab_size"], 512).tolist() for _ in range(B)]
 sids = [e.seq_create() for _ in range(B)]
@@ -46,4 +47,9 @@ print("latest CTAs (sum over the 4 weight phases of mean lateness vs the first a
 print("  " + ", ".join(f"cta{c}/sm{smid[c]}:{late[c]:.1f}" for c in order[:10]))
 print("earliest: " + ", ".join(f"cta{c}/sm{smid[c]}:{late[c]:.1f}" for c in order[-6:]))
 print(f"lateness: mean {late.mean():.2f} std {late.std():.2f} max {late.max():.2f} us per layer")
+wsm = e.debug_read("sm_weight")[0]
+wc = wsm[smid]
+dur = sum((per[:, 2:, k] - per[:, 2:, k - 1]).mean(1) for k in (1, 6, 9, 12))
+print(f"calibrated SM speed: min {wc.min():.3f} max {wc.max():.3f}; weight-phase time per CTA: min {dur.min():.1f} median {np.median(dur):.1f} max {dur.max():.1f} us; "
+      f"corr(speed, time) = {np.corrcoef(wc, dur)[0, 1]:.2f} (with shares ~ speed a good calibration flattens the times)")
 np.save(os.path.join("gpurun_out", f"mega_skew_{wl}_b{B}.npy"), t) if os.path.isdir("gpurun_out") else None
