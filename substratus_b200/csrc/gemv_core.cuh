@@ -16,17 +16,19 @@
 #endif
 // acc += lo(w)*lo(x); acc += hi(w)*hi(x)   (in this order)
 SSB_DEVINL float fma2_bf16(uint32_t w, uint32_t x, float acc) {
-#if GEMV_MIXED_FMA
   asm("{\n\t.reg .b16 wl, wh, xl, xh;\n\tmov.b32 {wl, wh}, %1;\n\tmov.b32 {xl, xh}, %2;\n\t"
       "fma.rn.f32.bf16 %0, wl, xl, %0;\n\tfma.rn.f32.bf16 %0, wh, xh, %0;\n\t}"
       : "+f"(acc)
       : "r"(w), "r"(x));
   return acc;
-#else
-  acc = fmaf(bf_lo(w), bf_lo(x), acc);
-  return fmaf(bf_hi(w), bf_hi(x), acc);
-#endif
 }
+// Which loop a tile height uses.  Measured on B200, Llama-2-7B persistent kernel (round 2, profiles/r02_variant_sweep.txt
+// and run 5): the mixed FMA is 3 % SLOWER at 1 row (the loop is not issue-bound there and FHFMA with two packed operands
+// issues no faster than FFMA) and 19 % FASTER at 4 rows (the x-operand unpack is paid per row).  Both are bit-identical.
+template <int BT>
+struct GemvMixed {
+  static constexpr bool value = GEMV_MIXED_FMA != 0 || BT >= 2;
+};
 
 template <int BT>
 SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__ w1, const bf16* __restrict__ xs, int K, int k0, int len,
@@ -52,16 +54,16 @@ SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-#if GEMV_MIXED_FMA
-          s0 = fma2_bf16(u0[i], xu[i], s0);
-          s1 = fma2_bf16(u1[i], xu[i], s1);
-#else
-          const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
-          s0 = fmaf(bf_lo(u0[i]), xl, s0);
-          s0 = fmaf(bf_hi(u0[i]), xh, s0);
-          s1 = fmaf(bf_lo(u1[i]), xl, s1);
-          s1 = fmaf(bf_hi(u1[i]), xh, s1);
-#endif
+          if constexpr (GemvMixed<BT>::value) {
+            s0 = fma2_bf16(u0[i], xu[i], s0);
+            s1 = fma2_bf16(u1[i], xu[i], s1);
+          } else {
+            const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
+            s0 = fmaf(bf_lo(u0[i]), xl, s0);
+            s0 = fmaf(bf_hi(u0[i]), xh, s0);
+            s1 = fmaf(bf_lo(u1[i]), xl, s1);
+            s1 = fmaf(bf_hi(u1[i]), xh, s1);
+          }
         }
         p0[it] = s0;
         p1[it] = s1;
@@ -82,16 +84,16 @@ SSB_DEVINL void gemv_chunk(const bf16* __restrict__ w0, const bf16* __restrict__
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-#if GEMV_MIXED_FMA
-          s0 = fma2_bf16(u0[i], xu[i], s0);
-          s1 = fma2_bf16(u1[i], xu[i], s1);
-#else
-          const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
-          s0 = fmaf(bf_lo(u0[i]), xl, s0);
-          s0 = fmaf(bf_hi(u0[i]), xh, s0);
-          s1 = fmaf(bf_lo(u1[i]), xl, s1);
-          s1 = fmaf(bf_hi(u1[i]), xh, s1);
-#endif
+          if constexpr (GemvMixed<BT>::value) {
+            s0 = fma2_bf16(u0[i], xu[i], s0);
+            s1 = fma2_bf16(u1[i], xu[i], s1);
+          } else {
+            const float xl = bf_lo(xu[i]), xh = bf_hi(xu[i]);
+            s0 = fmaf(bf_lo(u0[i]), xl, s0);
+            s0 = fmaf(bf_hi(u0[i]), xh, s0);
+            s1 = fmaf(bf_lo(u1[i]), xl, s1);
+            s1 = fmaf(bf_hi(u1[i]), xh, s1);
+          }
         }
         acc0[b] += s0;
         acc1[b] += s1;

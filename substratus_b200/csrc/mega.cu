@@ -143,6 +143,13 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
 // 1, tools/ubench_fma) catch up.  In steady streaming the ring is never full, so no prefetch is issued and nothing is
 // touched twice.  Round 1's fixed-distance variant (one prefetch per copy, N fills ahead) only shifted the stream and
 // measured no gain (0.691 vs 0.700).  Prefetches change no result: bit-identical to the default build.
+#ifndef MG_L2_AHEAD
+#define MG_L2_AHEAD 14
+#endif
+// MG_L2_MIN_AHEAD = N: additionally keep N fills prefetched ahead of the copies in steady streaming (see produce()).
+#ifndef MG_L2_MIN_AHEAD
+#define MG_L2_MIN_AHEAD 0
+#endif
 SSB_DEVINL void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
