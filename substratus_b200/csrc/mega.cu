@@ -24,7 +24,19 @@ constexpr int MG_PW = 4;                      // producer warps (one warp issues
 constexpr int MG_THREADS = (MG_CW + MG_PW) * 32;
 constexpr int MG_ROWS = 2 * MG_CW;
 constexpr int MG_KC = 1024;
-constexpr int MG_STAGE_ELEMS = MG_ROWS * MG_KC;  // 32 KiB of bf16
+// MG_MMA = 1: the consumers multiply on the tensor pipe (mma.sync m16n8k16, the batch rows as the N = 8 columns) instead of
+// unpack + FFMA on the CUDA cores.  One ldmatrix.x4 + one HMMA retire a 16 x 16 weight tile (512 B) where the FMA loop needs
+// ~25 instructions: the FMA consumers top out at ~50 GB/s per SM — barely above the 44.5 GB/s HBM share, so a stall is never
+// caught up and the L2 lookahead has nothing to feed — and at 4 rows they are the bottleneck outright (0.44 of the
+// roofline).  Stage rows are padded to 1032 elements so that the eight rows of an 8 x 8 ldmatrix tile fall into different
+// bank groups.  fp32 accumulation happens in the tensor pipe: the summation ORDER differs from the FMA loop (results
+// are not bit-identical to it; both meet the oracle tolerance — tests/test_parity_gpu.py, test_fullwidth_gpu.py).
+#ifndef MG_MMA
+#define MG_MMA 1  // default since round 2 (run 7, Llama-2-7B): 371.6 vs 360.9 tok/s at 1 row, 628 vs 591 at 2, 997 vs 893 at 4
+#endif
+constexpr int MG_RS = MG_MMA ? MG_KC + 8 : MG_KC;   // row stride inside a stage (elements)
+constexpr int MG_STAGE_ELEMS = MG_ROWS * MG_RS;     // 32 KiB of bf16 (+ 256 B of padding with MG_MMA)
+constexpr int MG_RED_FLOATS = MG_MMA ? 2 * MG_CW * 16 * 4 : 0;  // cross-warp reduction of the K slices, double-buffered by pass
 
 struct Ring {
   int stage;
@@ -132,7 +144,7 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
   named_bar_sync(1, MG_CW * 32);
 }
 
-// MG_L2_AHEAD = N (default 14; 0 disables): stall-driven L2 lookahead.  The shared-memory ring holds 192 KiB = 4.3 us of
+// MG_L2_AHEAD = N (0 = off, the default — see the measurement next to the #define): stall-driven L2 lookahead.  The shared-memory ring holds 192 KiB = 4.3 us of
 // this SM's HBM share, but the consumers stop taking weights for ~18 us per layer around the attention phase (QKV ->
 // barrier -> attention -> barrier -> staging) and for 3-7 us at every other barrier, so HBM used to idle ~18 us of an
 // 85 us layer (round-2 phase timeline, profiles/r02_*).  Now a producer warp that finds the ring full does not just wait:
@@ -144,7 +156,8 @@ SSB_DEVINL void grid_sync(unsigned* bar, unsigned& n_done, unsigned n_ctas) {
 // touched twice.  Round 1's fixed-distance variant (one prefetch per copy, N fills ahead) only shifted the stream and
 // measured no gain (0.691 vs 0.700).  Prefetches change no result: bit-identical to the default build.
 #ifndef MG_L2_AHEAD
-#define MG_L2_AHEAD 14
+#define MG_L2_AHEAD 0  // OFF: measured slower in every form (runs 6-7: stall-driven 14 / 8: 355 vs 361 tok/s; floor of 4: 329; with the
+                       // tensor-pipe consumers 366.6 vs 371.6) — the prefetch + copy pair costs more L2 / TMA work than the gaps it fills
 #endif
 // MG_L2_MIN_AHEAD = N: additionally keep N fills prefetched ahead of the copies in steady streaming (see produce()).
 #ifndef MG_L2_MIN_AHEAD
@@ -246,7 +259,7 @@ SSB_DEVINL void produce(const bf16* W, int N, int K, bf16* tiles, uint64_t* full
       if (lane == 0) mbar_expect_tx(&full[r.stage], (uint32_t)(mine * len * 2));
       __syncwarp();
       if (lane < mine)
-        bulk_g2s_hint(tiles + ((size_t)r.stage * MG_ROWS + r0 + lane) * MG_KC, W + (size_t)(2 * ps + r0 + lane) * K + k0,
+        bulk_g2s_hint(tiles + ((size_t)r.stage * MG_ROWS + r0 + lane) * MG_RS, W + (size_t)(2 * ps + r0 + lane) * K + k0,
                       (uint32_t)(len * 2), &full[r.stage], pol);
       if (++r.stage == n_stages) {
         r.stage = 0;
@@ -322,9 +335,122 @@ SSB_DEVINL uint4 ld_relaxed_sys_v4(const uint4* p) {
   return v;
 }
 
+SSB_DEVINL void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+SSB_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+#if MG_MMA
+// One projection on the tensor pipe.  A stage = 16 weight rows x 1024 k; warp w multiplies ALL 16 rows by the k slice
+// [128 w, 128 w + 128) of the chunk (8 k-steps of m16n8k16: A = ldmatrix.x4 of the padded stage, B = the staged activations,
+// batch row n = column n of the 8), accumulating its slice over the chunks of the pass in one 16 x 8 fp32 fragment.  At the
+// end of the pass the 8 slices are summed through shared memory in warp order and warp w runs the epilogue of pair w, lane
+// b = batch row b — the same (pair, row) -> (warp, lane) ownership as the FMA form, so the epilogues, their prefetched
+// inputs and the LL push are unchanged.  k beyond the chunk length contributes nothing: whole k-steps are skipped and the
+// activation fragment is zero there (the ring is zero-filled at kernel start, so stale weights are finite).
 template <int BT, int EPI>
 SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        int warp, int lane, [[maybe_unused]] const LlCtx* ll = nullptr) {
+                        int warp, int lane, float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr) {
+  static_assert(MG_CW == 8 && MG_KC == 1024, "8 k slices of 128");
+  const int K = a.K;
+  const int P = a.N >> 1;
+  int p0, p1;
+  part_range(P, p0, p1);
+  const int nk = (K + MG_KC - 1) / MG_KC;
+  const int kw0 = warp * (MG_KC / MG_CW);
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lko = (lane >> 4) * 8;  // ldmatrix source row / k offset of this lane
+  const int bn = lane >> 2, bk = (lane & 3) * 2;                               // B fragment: batch row, k pair
+  int pass = 0;
+  for (int ps = p0; ps < p1; ps += MG_CW, ++pass) {
+    const int pair = ps + warp;
+    const bool valid = pair < p1;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    [[maybe_unused]] EpiPre pre = {0u, 0, 0, 0u};
+    if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+      if (valid && lane < BT && lane < a.M) pre = epi_prefetch<EPI>(a, pair, lane);
+    }
+    for (int kc = 0; kc < nk; ++kc) {
+      const int k0 = kc * MG_KC;
+      const int len = min(MG_KC, K - k0);
+      mbar_wait(&full[r.stage], r.phase);
+      const uint32_t st = smem_u32(tiles + (size_t)r.stage * MG_STAGE_ELEMS) + (uint32_t)(lrow * MG_RS + kw0 + lko) * 2u;
+      const bf16* xrow = xs + (size_t)(bn < BT ? bn : 0) * K + k0 + kw0 + bk;
+      if (len == MG_KC) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+          ldmatrix_x4(a0, a1, a2, a3, st + (uint32_t)ks * 32u);
+          if (bn < BT) {
+            b0 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16);
+            b1 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16 + 8);
+          }
+          mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
+        }
+      } else {
+        for (int ks = 0; ks < 8; ++ks) {
+          const int kk = kw0 + ks * 16;
+          if (kk >= len) break;  // warp-uniform
+          uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+          ldmatrix_x4(a0, a1, a2, a3, st + (uint32_t)ks * 32u);
+          if (bn < BT) {
+            if (kk + bk < len) b0 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16);
+            if (kk + bk + 8 < len) b1 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16 + 8);
+          }
+          mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[r.stage]);
+      if (++r.stage == n_stages) {
+        r.stage = 0;
+        r.phase ^= 1;
+      }
+    }
+    // ---- sum the 8 k slices: fragment element (row, col) lives in lane 4*(row % 8) + col/2, register (row/8)*2 + col%2
+    float* rs = red_s + (size_t)(pass & 1) * (MG_CW * 16 * 4) + (size_t)warp * 64;
+    {
+      const int col = (lane & 3) * 2, row = lane >> 2;
+      if (col < BT) {
+        rs[row * 4 + col] = c[0];
+        rs[(row + 8) * 4 + col] = c[2];
+      }
+      if (col + 1 < BT) {
+        rs[row * 4 + col + 1] = c[1];
+        rs[(row + 8) * 4 + col + 1] = c[3];
+      }
+    }
+    named_bar_sync(1, MG_CW * 32);
+    if (valid && lane < BT && lane < a.M) {
+      const float* rb = red_s + (size_t)(pass & 1) * (MG_CW * 16 * 4);
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < MG_CW; ++w) {  // fixed order: deterministic
+        v0 += rb[w * 64 + (2 * warp) * 4 + lane];
+        v1 += rb[w * 64 + (2 * warp + 1) * 4 + lane];
+      }
+      if constexpr (EPI == EPI_LL) {
+        const MegaArgs& ma = *ll->ma;
+        const uint4 w = make_uint4(__float_as_uint(v0), ll->epoch, __float_as_uint(v1), ll->epoch);
+        const size_t o = ll->off + (size_t)lane * (size_t)(ma.hidden >> 1) + (size_t)pair;
+#pragma unroll
+        for (int rk = 0; rk < 8; ++rk)
+          if (rk < ma.tp_size) st_relaxed_sys_v4(ma.peer_ll[rk] + o, w);
+      } else if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
+        gemv_epilogue_pre<BT, EPI>(a, pair, lane, v0, v1, pre);
+      } else {
+        gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
+      }
+    }
+  }
+}
+#else
+template <int BT, int EPI>
+SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
+                        int warp, int lane, [[maybe_unused]] float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr) {
   const int K = a.K;
   const int P = a.N >> 1;
   int p0, p1;
@@ -346,8 +472,8 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
       const int len = min(MG_KC, K - k0);
       mbar_wait(&full[r.stage], r.phase);
       if (valid) {
-        const bf16* w0 = tiles + ((size_t)r.stage * MG_ROWS + 2 * warp) * MG_KC;
-        const bf16* w1 = w0 + MG_KC;
+        const bf16* w0 = tiles + ((size_t)r.stage * MG_ROWS + 2 * warp) * MG_RS;
+        const bf16* w1 = w0 + MG_RS;
         gemv_chunk<BT>(w0, w1, xs, K, k0, len, lane, acc0, acc1);
       }
       __syncwarp();
@@ -385,6 +511,8 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
     }
   }
 }
+
+#endif  // MG_MMA
 
 // ---------------------------------------------------------------- consumers: paged attention, one (row, head unit, 16-token
 // chunk) per warp; all K/V loads of the chunk are issued before any is consumed; the last-arriving warp of a
@@ -1047,9 +1175,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t)BT * a.k_max);
   uint64_t* empty = full + a.n_stages;
   float* red = reinterpret_cast<float*>(empty + a.n_stages);
+  [[maybe_unused]] float* red_s = red + 32 + (MG_CW > 8 ? 32 : 0);  // MG_MMA: [2][MG_CW][16][4] k-slice partial sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = a.hidden;
 
+#if MG_MMA
+  for (size_t i = threadIdx.x; i < (size_t)a.n_stages * MG_STAGE_ELEMS / 8; i += MG_THREADS)
+    reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);  // k tails multiply stale ring contents by zero: keep them finite
+#endif
   const bool weighted = a.sm_weight != nullptr && a.cta_weight != nullptr && a.tp_mode != 2 && gridDim.x <= MG_MAX_CTAS;
   if (tid == 0) {
     for (int s = 0; s < a.n_stages; ++s) {
@@ -1159,7 +1292,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.kcache = w.kcache;
     g.vcache = w.vcache;
     MG_STAMP();  // 1: x staged
-    consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     MG_STAMP();  // 2: qkv consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 3
@@ -1190,10 +1323,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l) & 1) * (size_t)a.parity_stride;
       if (a.tp_mode == 3) {
         const LlCtx lx = {&a, ll_epoch0 + (uint32_t)(2 * l), (size_t)((2 * l) & 1) * (size_t)a.ll_parity_stride + (size_t)a.tp_rank * (size_t)a.ll_src_stride};
-        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, &lx);
+        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s, &lx);
         tp_reduce_ll(a, 2 * l, lx.epoch, tid);
       } else {
-      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
       }
       if (a.tp_mode == 3) {
       } else if (a.tp_mode == 2) {
@@ -1203,7 +1336,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
         tp_reduce_phase(a, 2 * l, tid);
       }
     } else {
-      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     }
     MG_STAMP();  // 7: o consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
@@ -1215,7 +1348,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.out_bf16 = a.act;
     g.ld_out = a.inter;
     MG_STAMP();  // 9: x staged
-    consume<BT, EPI_SWIGLU>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+    consume<BT, EPI_SWIGLU>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     MG_STAMP();  // 10: gate/up consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 11
@@ -1231,10 +1364,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l + 1) & 1) * (size_t)a.parity_stride;
       if (a.tp_mode == 3) {
         const LlCtx lx = {&a, ll_epoch0 + (uint32_t)(2 * l + 1), (size_t)((2 * l + 1) & 1) * (size_t)a.ll_parity_stride + (size_t)a.tp_rank * (size_t)a.ll_src_stride};
-        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, &lx);
+        consume<BT, EPI_LL>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s, &lx);
         tp_reduce_ll(a, 2 * l + 1, lx.epoch, tid);
       } else {
-      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      consume<BT, EPI_F32>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
       }
       if (a.tp_mode == 3) {
       } else if (a.tp_mode == 2) {
@@ -1244,7 +1377,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
         tp_reduce_phase(a, 2 * l + 1, tid);
       }
     } else {
-      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+      consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     }
     MG_STAMP();  // 13: down consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
@@ -1256,7 +1389,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   g.K = h;
   g.out_f32 = a.logits;
   g.ld_out = a.vocab;
-  consume<BT, EPI_F32_BF16R>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane);
+  consume<BT, EPI_F32_BF16R>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
   grid_sync(a.grid_bar, n_sync, n_ctas);
   // ---- greedy pick: CTA m handles row m (lowest index wins ties)
   if ((int)blockIdx.x < a.M) {
@@ -1313,7 +1446,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 }
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages) {
-  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128 + (MG_CW > 8 ? 128 : 0);  // dynamic part
+  return (size_t)n_stages * MG_STAGE_ELEMS * 2 + (size_t)bt * k_max * 2 + 2 * (size_t)n_stages * 8 + 128 + (MG_CW > 8 ? 128 : 0) +
+         (size_t)MG_RED_FLOATS * 4;  // dynamic part
 }
 
 int mega_pick_stages(int bt, int k_max) {
