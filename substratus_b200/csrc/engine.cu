@@ -461,6 +461,47 @@ int Engine::calibrate_sm_weights(const Json& params) {
   return SSB_OK;
 }
 
+// Self-tuning of the persistent kernel's row shares.  The kernel accumulated, per CTA, the time thread 0 spent in the four
+// weight phases of every layer (stage_x done -> last pair consumed) over the steps of the decode call that just finished,
+// and the %smid it ran on.  All CTAs enter a phase together (grid barrier), so that time IS the arrival lateness the next
+// barrier waits for.  share_i <- share_i * (mean t / t_i)^0.7, renormalised, clamped to [0.75, 1.3]; a few rounds flatten the
+// arrival spread (measured before: the slowest SM arrived 6.6 us per layer after the mean one).  Then tuning stops and the
+// kernel runs without the stamps.
+int Engine::tune_sm_weights(int nsteps) {
+  if (tune_rounds_left_ <= 0 || !tune_out_ || !sm_weight_) return SSB_OK;
+  std::vector<float> t((size_t)n_sm_ * 4);
+  CK(cudaMemcpy(t.data(), tune_out_, t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(tune_out_, 0, t.size() * sizeof(float)));
+  if (nsteps < 8) return SSB_OK;  // too little signal: wait for a longer call
+  double mean = 0.0;
+  int cnt = 0;
+  for (int c = 0; c < n_sm_; ++c)
+    if (t[4 * c + 2] > 0.f && t[4 * c] > 0.f) {
+      mean += t[4 * c] / t[4 * c + 2];
+      ++cnt;
+    }
+  if (cnt < n_sm_) return SSB_OK;
+  mean /= cnt;
+  double wsum = 0.0;
+  std::vector<float> w = h_sm_weight_;
+  std::vector<char> seen(256, 0);
+  for (int c = 0; c < n_sm_; ++c) {
+    const int sm = (int)t[4 * c + 1] & 255;
+    if (seen[sm]) return SSB_OK;  // two CTAs reported one SM (placement changed mid-call): skip this round
+    seen[sm] = 1;
+    const double ti = t[4 * c] / t[4 * c + 2];
+    w[sm] = (float)(w[sm] * pow(mean / ti, 0.7));
+  }
+  for (int i = 0; i < 256; ++i)
+    if (seen[i]) wsum += w[i];
+  for (int i = 0; i < 256; ++i)
+    if (seen[i]) w[i] = (float)std::min(1.3, std::max(0.75, (double)w[i] * cnt / wsum));
+  h_sm_weight_ = w;
+  CK(cudaMemcpy(sm_weight_, w.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+  --tune_rounds_left_;
+  return SSB_OK;
+}
+
 int Engine::decode_splits_(int M) const {
   const int group = cfg_.heads / cfg_.kv_heads;
   const int gc = (group % 8 == 0) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
@@ -631,6 +672,22 @@ int Engine::alloc_runtime(const Json& params) {
         const size_t n = mega_prof_all_ ? (size_t)n_sm_ * 1024 : 1024;
         TRY(dmalloc(&mega_prof_, n));
         CK(cudaMemset(mega_prof_, 0, n * sizeof(unsigned long long)));
+      }
+      tune_rounds_left_ = (int)params.get_int("sm_tune", 4);
+      if (tune_rounds_left_ > 0 && n_sm_ <= 200) {
+        if (!sm_weight_) {  // no ring calibration ("sm_balance"): start from equal shares
+          TRY(dmalloc(&sm_weight_, 256));
+          TRY(dmalloc(&cta_weight_, 256));
+          std::vector<float> ones(256, 1.0f);
+          CK(cudaMemcpy(sm_weight_, ones.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+          CK(cudaMemset(cta_weight_, 0, 256 * sizeof(float)));
+        }
+        h_sm_weight_.assign(256, 1.0f);
+        CK(cudaMemcpy(h_sm_weight_.data(), sm_weight_, 256 * sizeof(float), cudaMemcpyDeviceToHost));
+        TRY(dmalloc(&tune_out_, (size_t)n_sm_ * 4));
+        CK(cudaMemset(tune_out_, 0, (size_t)n_sm_ * 4 * sizeof(float)));
+      } else {
+        tune_rounds_left_ = 0;
       }
       TRY(dmalloc(&mega_bar_, 1024));  // [0] barrier counter, [1] exit counter, [32 + 32 g] group counters of the tree-barrier experiment
       CK(cudaMemset(mega_bar_, 0, 1024 * sizeof(unsigned)));
@@ -1418,6 +1475,7 @@ int Engine::forward_mega(int B) {
   // GQA groups of 8: CTA-tile attention when the K/V tile fits the activation staging area (params "mega_attn_tile": 0 = off)
   a.sm_weight = sm_weight_;
   a.cta_weight = cta_weight_;
+  a.tune_out = tune_rounds_left_ > 0 ? tune_out_ : nullptr;
   a.attn_coop = (a.attn_g < 8 && mega_attn_tile_ &&
                  (size_t)(B == 1 ? 1 : (B == 2 ? 2 : 4)) * mega_k_max_ * sizeof(bf16) >= mega_attn_coop_bytes(D, a.attn_g)) ? 1 : 0;
   a.attn_cta_tile = (a.attn_g == 8 && mega_attn_tile_ &&
@@ -1511,6 +1569,7 @@ int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int ns
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
   timing_.decode_ms = ms;
+  if (mega && tune_rounds_left_ > 0) TRY(tune_sm_weights(nsteps));
   for (int i = 0; i < nseq; ++i) {
     for (int s = 0; s < nsteps; ++s) out_tok[(size_t)i * nsteps + s] = hist[(size_t)s * nseq + i];
     slots_[seq_ids[i]].len += nsteps;

@@ -96,6 +96,12 @@ class Engine {
   bool mega_attn_tile_ = true;
   float* sm_weight_ = nullptr;   // [256] per-SM streaming speed (calibrate_sm_weights), null = equal shares
   float* cta_weight_ = nullptr;  // [n_sm] scratch of the persistent kernel
+  // self-tuned row shares (params "sm_tune": rounds, default 4): after each of the first decode calls the host reads how long every
+  // CTA spent in the weight phases and moves row share from the slow SMs to the fast ones (engine.cu: tune_sm_weights)
+  float* tune_out_ = nullptr;
+  int tune_rounds_left_ = 0;
+  std::vector<float> h_sm_weight_;
+  int tune_sm_weights(int nsteps);
   std::string sm_calib_report_;  // JSON summary of the calibration (ssb_debug_profile-style, tools)
   int calibrate_sm_weights(const Json& params);
   int mega_max_chunks_ = 0, mega_k_max_ = 0;

@@ -78,6 +78,15 @@ SSB_DEVINL unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// self-tuning of the row shares (MegaArgs::tune_out): thread 0 of every CTA times its four weight phases
+#define MG_TUNE_BEGIN()                          \
+  do {                                           \
+    if (a.tune_out && tid == 0) t_tune = gtimer(); \
+  } while (0)
+#define MG_TUNE_END()                                                  \
+  do {                                                                 \
+    if (a.tune_out && tid == 0) tune_ns += (float)(gtimer() - t_tune); \
+  } while (0)
 #define MG_STAMP()                                                                                                  \
   do {                                                                                                              \
     if (a.prof && (blockIdx.x == 0 || a.prof_all) && tid == 0 && n_prof < 1023)                                     \
@@ -1218,6 +1227,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
   // ================================================================== consumers
   pdl_wait();
   int n_prof = 0;
+  [[maybe_unused]] unsigned long long t_tune = 0;
+  [[maybe_unused]] float tune_ns = 0.f;
   if (a.prof && a.prof_all && tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1292,7 +1303,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.kcache = w.kcache;
     g.vcache = w.vcache;
     MG_STAMP();  // 1: x staged
+    MG_TUNE_BEGIN();
     consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
+    MG_TUNE_END();
     MG_STAMP();  // 2: qkv consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 3
@@ -1319,6 +1332,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.resid = a.h;
     g.ld_out = h;
     MG_STAMP();  // 6: x staged
+    MG_TUNE_BEGIN();
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l) & 1) * (size_t)a.parity_stride;
       if (a.tp_mode == 3) {
@@ -1338,6 +1352,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     } else {
       consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     }
+    MG_TUNE_END();
     MG_STAMP();  // 7: o consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 8
@@ -1348,7 +1363,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.out_bf16 = a.act;
     g.ld_out = a.inter;
     MG_STAMP();  // 9: x staged
+    MG_TUNE_BEGIN();
     consume<BT, EPI_SWIGLU>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
+    MG_TUNE_END();
     MG_STAMP();  // 10: gate/up consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 11
@@ -1360,6 +1377,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.resid = a.h;
     g.ld_out = h;
     MG_STAMP();  // 12: x staged
+    MG_TUNE_BEGIN();
     if constexpr (TP) {
       g.out_f32 = a.peer_partials[a.tp_rank] + (size_t)((2 * l + 1) & 1) * (size_t)a.parity_stride;
       if (a.tp_mode == 3) {
@@ -1379,6 +1397,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     } else {
       consume<BT, EPI_RESID>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
     }
+    MG_TUNE_END();
     MG_STAMP();  // 13: down consumed
     grid_sync(a.grid_bar, n_sync, n_ctas);
     MG_STAMP();  // 14 (= 0 of the next layer)
@@ -1430,6 +1449,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
       a.hist[(size_t)(__ldcg(a.step)) * a.M + m] = bi;
       a.row_pos[m] += 1;
     }
+  }
+  if (a.tune_out && tid == 0) {  // [cta][4]: accumulated ns in the weight phases, %smid, launches, -
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    float* to = a.tune_out + 4 * (size_t)blockIdx.x;
+    to[0] += tune_ns;
+    to[1] = (float)smid;
+    to[2] += 1.f;
   }
   // leave the barrier counter at zero for the next launch: the last CTA through resets it
   if (tid == 0) {

@@ -61,6 +61,7 @@ struct MegaArgs {
   int attn_coop;                     // groups of 1 / 2 / 4: one (row, head unit, split) per CTA, warps combined through shared memory
   const float* sm_weight;            // [256] relative streaming speed of each SM (by %smid), null = equal row shares
   float* cta_weight;                 // [n_ctas] scratch: the weight of the SM each CTA of THIS launch runs on
+  float* tune_out;                   // [n_ctas][4] or null: per-CTA time spent in the weight phases (self-tuning of sm_weight)
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);

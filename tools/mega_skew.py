@@ -18,6 +18,9 @@ rng = np.random.default_rng(0)
 prompts = [rng.integers(0, cfg["vocab_size"], 512).tolist() for _ in range(B)]
 sids = [e.seq_create() for _ in range(B)]
 nxt, _ = e.prefill(sids, prompts)
+for _ in range(5):  # lets the self-tuning of the row shares ("sm_tune" rounds) settle before the profiled call
+    out, _ = e.decode(sids, nxt, 16)
+    nxt = out[:, -1]
 e.decode(sids, nxt, 16)
 t = e.debug_read("mega_prof_all")           # [n_ctas, 1024] us, -1 = unset; col 1023 = smid
 smid = t[:, 1023].astype(int)
