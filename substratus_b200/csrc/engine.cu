@@ -673,7 +673,7 @@ int Engine::alloc_runtime(const Json& params) {
         TRY(dmalloc(&mega_prof_, n));
         CK(cudaMemset(mega_prof_, 0, n * sizeof(unsigned long long)));
       }
-      tune_rounds_left_ = (int)params.get_int("sm_tune", 4);
+      tune_rounds_left_ = (int)params.get_int("sm_tune", 0);  // needs a library built with -DMG_TUNE=1 (variant "tune"); off by default
       if (tune_rounds_left_ > 0 && n_sm_ <= 200) {
         if (!sm_weight_) {  // no ring calibration ("sm_balance"): start from equal shares
           TRY(dmalloc(&sm_weight_, 256));

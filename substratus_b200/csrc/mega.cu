@@ -79,6 +79,11 @@ SSB_DEVINL unsigned long long gtimer() {
   return t;
 }
 // self-tuning of the row shares (MegaArgs::tune_out): thread 0 of every CTA times its four weight phases
+#ifndef MG_TUNE
+#define MG_TUNE 0  // compiled OUT by default: the eight predicated timer reads alone cost 3 % of the batch-1 step (run 9: 359 vs 371 tok/s
+                   // with tuning disabled at run time) and the tuned shares did not pay for it (flatter per-CTA totals, same per-phase spread)
+#endif
+#if MG_TUNE
 #define MG_TUNE_BEGIN()                          \
   do {                                           \
     if (a.tune_out && tid == 0) t_tune = gtimer(); \
@@ -87,11 +92,23 @@ SSB_DEVINL unsigned long long gtimer() {
   do {                                                                 \
     if (a.tune_out && tid == 0) tune_ns += (float)(gtimer() - t_tune); \
   } while (0)
+#else
+#define MG_TUNE_BEGIN() do {} while (0)
+#define MG_TUNE_END() do {} while (0)
+#endif
+// MG_PROF = 0 compiles the phase stamps out (variant library "noprof": what the 14 predicated stamps per layer cost)
+#ifndef MG_PROF
+#define MG_PROF 1
+#endif
+#if MG_PROF
 #define MG_STAMP()                                                                                                  \
   do {                                                                                                              \
     if (a.prof && (blockIdx.x == 0 || a.prof_all) && tid == 0 && n_prof < 1023)                                     \
       a.prof[(a.prof_all ? (size_t)blockIdx.x * 1024 : 0) + n_prof++] = gtimer();                                   \
   } while (0)
+#else
+#define MG_STAMP() do {} while (0)
+#endif
 
 // grid-wide barrier among the consumer threads of all CTAs (the producer warp does not take part)
 // MG_SYNC_LIGHT=1 (default since round 2; 0 = the fence + atomicAdd + fence form of round 1):
@@ -1226,7 +1243,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 
   // ================================================================== consumers
   pdl_wait();
-  int n_prof = 0;
+  [[maybe_unused]] int n_prof = 0;
   [[maybe_unused]] unsigned long long t_tune = 0;
   [[maybe_unused]] float tune_ns = 0.f;
   if (a.prof && a.prof_all && tid == 0) {
