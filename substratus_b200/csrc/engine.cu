@@ -560,7 +560,10 @@ int Engine::alloc_runtime(const Json& params) {
     tp_off_flags_ = b_part + b_recv;
     tp_off_pflags_ = tp_off_flags_ + 64;
     tp_pool_bytes_ = tp_off_pflags_ + 64;
-    tp_two_shot_ = params.get_int("tp_two_shot", 0) != 0 && !cfg_.falcon;
+    // prefill-sized forwards (>= tp_two_shot_min_rows rows): reduce-scatter + bf16 gather instead of every rank pulling every
+    // peer's full fp32 partial.  Default ON since round 2 (4 x B200, Llama-2-7B: TTFT 20.5 -> 11.2 ms at batch 1, 592 -> 262 ms
+    // at batch 32 — profiles/r02_bench_tp4_gpurun.json vs r02_tp_twoshot_n4.jsonl; parity: tests/test_tp_gpu.py two_shot)
+    tp_two_shot_ = params.get_int("tp_two_shot", 1) != 0 && !cfg_.falcon;
     tp_two_shot_min_rows_ = std::max(1, (int)params.get_int("tp_two_shot_min_rows", 64));
     if (tp_two_shot_) {  // opt-in: the default pool layout (and its size check in tp_connect) is unchanged
       tp_off_gather_ = tp_pool_bytes_;
