@@ -98,6 +98,7 @@ class Handler(BaseHTTPRequestHandler):
 
 
 def serve(model_dir: str, port: int, dtype: str = "bfloat16"):
+    State.ready, State.model = False, None  # a second server in one process must not answer with the previous model
     srv = ThreadingHTTPServer(("0.0.0.0", port), Handler)
     threading.Thread(target=load, args=(model_dir, dtype), daemon=True).start()
     return srv

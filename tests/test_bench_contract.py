@@ -125,9 +125,9 @@ def test_gpu_arm_control_flow_against_a_mock_engine(monkeypatch, capsys):
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["kernel"].startswith("decode_mega_kernel")
     d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-extras", "--engine-params", '{"fail32": 1}'])
     assert d["value"] > 0 and "boom" in d["batch32"]["error"] and d["config"]["engine_params"] == {"fail32": 1}
-    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--batch", "32"])
+    d = run(["--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-extras", "--batch", "32"])
     assert d["config"]["batch"] == 32 and "batch32" not in d and d["roofline"]["kernel"].startswith("gate/up")
-    d = run(["--steps", "25", "--warmup", "1", "--no-cpu-baseline", "--no-batch32"])
+    d = run(["--steps", "25", "--warmup", "1", "--no-cpu-baseline", "--no-batch32", "--no-extras"])
     assert d["ttft_samples"] == 25
 
 
