@@ -692,6 +692,10 @@ int Engine::alloc_runtime(const Json& params) {
       } else {
         tune_rounds_left_ = 0;
       }
+      if (params.get_int("mega_head_flags", 1) != 0) {
+        TRY(dmalloc(&mega_head_done_, (size_t)Hl_ + 2 * KVHl_ + 32));
+        CK(cudaMemset(mega_head_done_, 0, ((size_t)Hl_ + 2 * KVHl_ + 32) * sizeof(unsigned)));
+      }
       TRY(dmalloc(&mega_bar_, 1024));  // [0] barrier counter, [1] exit counter, [32 + 32 g] group counters of the tree-barrier experiment
       CK(cudaMemset(mega_bar_, 0, 1024 * sizeof(unsigned)));
     }
@@ -1478,6 +1482,7 @@ int Engine::forward_mega(int B) {
   // GQA groups of 8: CTA-tile attention when the K/V tile fits the activation staging area (params "mega_attn_tile": 0 = off)
   a.sm_weight = sm_weight_;
   a.cta_weight = cta_weight_;
+  a.head_done = mega_head_done_;
   a.tune_out = tune_rounds_left_ > 0 ? tune_out_ : nullptr;
   a.attn_coop = (a.attn_g < 8 && mega_attn_tile_ &&
                  (size_t)(B == 1 ? 1 : (B == 2 ? 2 : 4)) * mega_k_max_ * sizeof(bf16) >= mega_attn_coop_bytes(D, a.attn_g)) ? 1 : 0;

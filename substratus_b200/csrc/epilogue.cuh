@@ -157,6 +157,46 @@ SSB_DEVINL void gemv_epilogue_pre(const GemvArgs& a, int pair, int m, float v0, 
 // store; out_bf16 may alias resid, so the compiler cannot hoist the next token's loads above the previous store and
 // the tile epilogue degenerates into ~TN serialized L2 round trips (measured: 20 us per 128x32 tile).  Here all loads of
 // the eight tokens are issued first.
+// QKV + RoPE + KV-append for eight tokens of one row pair with the token-dependent inputs (position, KV block of that
+// position) already staged in shared memory by the caller (tc_gemm_kernel stages them once per token tile while the MMAs of
+// the tile run).  The generic form below re-reads row_pos -> {rope table, row_slot -> block_table} per thread: three
+// dependent L2 round trips per eight tokens, which made the prefill QKV GEMM take longer than gate/up for 56 % of its
+// FLOPs (profiles/r02_ncu_summary.txt).  Here only the rope-table read remains, all eight issued at once.
+SSB_DEVINL void tc_epilogue8_qkv_staged(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, const int* __restrict__ s_blk,
+                                        const float (&v0)[8], const float (&v1)[8]) {
+  const int hd = a.head_dim, half = hd >> 1;
+  const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+  const bool is_q = pair < q_pairs, is_k = !is_q && pair < q_pairs + k_pairs;
+  if (is_q || is_k) {
+    const int pp = is_q ? pair : pair - q_pairs;
+    const int head = pp / half, jj = pp - head * half;
+    uint32_t cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = (m0 + j < a.M) ? a.rope_cs[(size_t)s_pos[j] * half + jj] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (m0 + j >= a.M) continue;
+      const float c = bf_lo(cs[j]), s = bf_hi(cs[j]);
+      const float x0 = bf16r(v0[j]), x1 = bf16r(v1[j]);
+      const float y0 = bf16r(bf16r(x0 * c) + bf16r(-x1 * s));
+      const float y1 = bf16r(bf16r(x1 * c) + bf16r(x0 * s));
+      bf16* dst = is_q ? a.q_out + (size_t)(m0 + j) * a.q_rows + head * hd + jj
+                       : a.kcache + (((size_t)s_blk[j] * a.kvh + head) * a.block_size + (s_pos[j] % a.block_size)) * hd + jj;
+      dst[0] = __float2bfloat16_rn(y0);
+      dst[half] = __float2bfloat16_rn(y1);
+    }
+  } else {
+    const int e = 2 * (pair - q_pairs - k_pairs);
+    const int head = e / hd, jj = e - head * hd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (m0 + j >= a.M) continue;
+      bf16* v = a.vcache + (((size_t)s_blk[j] * a.kvh + head) * a.block_size + (s_pos[j] % a.block_size)) * hd + jj;
+      *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0[j], v1[j]);
+    }
+  }
+}
+
 template <int EPI>
 SSB_DEVINL void tc_epilogue8(const GemvArgs& a, int pair, int m0, const float (&v0)[8], const float (&v1)[8]) {
   if constexpr (EPI == EPI_RESID || EPI == EPI_RESID2) {

@@ -370,6 +370,32 @@ SSB_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// ---------------------------------------------------------------- QKV -> attention dependency by head (no grid barrier)
+SSB_DEVINL int qkv_head_slot(const MegaArgs& ma, int pair) {
+  const int half = ma.head_dim >> 1, q_pairs = ma.q_rows >> 1, k_pairs = ma.kv_rows >> 1;
+  if (pair < q_pairs) return pair / half;
+  if (pair < q_pairs + k_pairs) return ma.n_heads + (pair - q_pairs) / half;
+  return ma.n_heads + ma.kvh + (pair - q_pairs - k_pairs) / half;
+}
+// called by every lane of the warp after the epilogue of `pair` (all batch rows): the lanes' stores, ordered before lane 0 by
+// the warp barrier, are released at gpu scope together with the count
+SSB_DEVINL void qkv_head_signal(const MegaArgs& ma, int pair, bool valid, int lane) {
+  __syncwarp();
+  if (valid && lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ma.head_done + qkv_head_slot(ma, pair)) : "memory");
+}
+// the CTA is about to read q heads [h0, h0 + nh) and the new K / V row of KV head kvh of layer `layer`: thread i polls one
+// counter until all head_dim/2 pairs of that head have been produced in every layer up to this one, then the CTA barrier
+// hands the observed writes on to the other threads (same pattern as grid_sync)
+SSB_DEVINL void qkv_head_wait(const MegaArgs& ma, int layer, int h0, int nh, int kvh, int tid) {
+  const unsigned target = (unsigned)(layer + 1) * (unsigned)(ma.head_dim >> 1);
+  if (tid < nh + 2) {
+    const int slot = tid < nh ? h0 + tid : (tid == nh ? ma.n_heads + kvh : ma.n_heads + ma.kvh + kvh);
+    SpinGuard sg;
+    while (ld_acquire_gpu(ma.head_done + slot) < target) sg.poll();
+  }
+  named_bar_sync(1, MG_CW * 32);
+}
+
 #if MG_MMA
 // One projection on the tensor pipe.  A stage = 16 weight rows x 1024 k; warp w multiplies ALL 16 rows by the k slice
 // [128 w, 128 w + 128) of the chunk (8 k-steps of m16n8k16: A = ldmatrix.x4 of the padded stage, B = the staged activations,
@@ -380,7 +406,7 @@ SSB_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t
 // activation fragment is zero there (the ring is zero-filled at kernel start, so stale weights are finite).
 template <int BT, int EPI>
 SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        int warp, int lane, float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr) {
+                        int warp, int lane, float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr, [[maybe_unused]] const MegaArgs* hf = nullptr) {
   static_assert(MG_CW == 8 && MG_KC == 1024, "8 k slices of 128");
   const int K = a.K;
   const int P = a.N >> 1;
@@ -471,12 +497,16 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
         gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
       }
     }
+    if constexpr (EPI == EPI_QKV_ROPE) {
+      if (hf) qkv_head_signal(*hf, pair, valid, lane);
+    }
   }
 }
 #else
 template <int BT, int EPI>
 SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, uint64_t* full, uint64_t* empty, int n_stages, Ring& r,
-                        int warp, int lane, [[maybe_unused]] float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr) {
+                        int warp, int lane, [[maybe_unused]] float* red_s, [[maybe_unused]] const LlCtx* ll = nullptr,
+                        [[maybe_unused]] const MegaArgs* hf = nullptr) {
   const int K = a.K;
   const int P = a.N >> 1;
   int p0, p1;
@@ -534,6 +564,9 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
       } else {
         if (lane < BT && lane < a.M) gemv_epilogue<BT, EPI>(a, pair, lane, v0, v1);
       }
+    }
+    if constexpr (EPI == EPI_QKV_ROPE) {
+      if (hf) qkv_head_signal(*hf, pair, valid, lane);
     }
   }
 }
@@ -721,7 +754,7 @@ SSB_DEVINL void attention_phase(const MegaArgs& a, const bf16* kcache, const bf1
 // 9.9 us after its first — the merge tail — and the barrier behind it waited 6.4 us.
 template <int D, int G>
 SSB_DEVINL void attention_phase_coop(const MegaArgs& a, const bf16* kcache, const bf16* vcache, float* sm, int* sm_flag, int tid, int warp,
-                                     int lane) {
+                                     int lane, int flag_layer) {
   constexpr int LPR = D / 8, RPW = 32 / LPR;
   // load batch of a warp: 20 tokens at G = 1 / D = 128, so that a 512..640-token context cut into 4 splits x 8 warps
   // (18-20 tokens per warp) is ONE batch of loads, i.e. one memory latency
@@ -752,6 +785,7 @@ SSB_DEVINL void attention_phase_coop(const MegaArgs& a, const bf16* kcache, cons
       const int kvh = (hu * G) / a.group;
       const int t_begin = sp * slen + warp * wlen;
       const int t_end = min(ctx, t_begin + wlen);
+      if (flag_layer >= 0) qkv_head_wait(a, flag_layer, hu * G, G, kvh, tid);
       float q[G][8];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -911,7 +945,7 @@ SSB_DEVINL void attention_phase_coop(const MegaArgs& a, const bf16* kcache, cons
 constexpr int MG_ATT_TILE = 32;  // tokens staged per pass: 2 x 32 x D bf16 = 16 KiB at D = 128
 template <int D>
 SSB_DEVINL void attention_phase_cta(const MegaArgs& a, const bf16* kcache, const bf16* vcache, bf16* tile, int* sm_flag, int tid, int warp,
-                                    int lane) {
+                                    int lane, int flag_layer) {
   constexpr int G = 8, LPR = D / 8, RPW = 32 / LPR, T = MG_ATT_TILE;
   static_assert(MG_CW == 8 || MG_CW == 12, "one consumer warp per query head of the group");
   bf16(*sK)[D] = reinterpret_cast<bf16(*)[D]>(tile);
@@ -936,6 +970,7 @@ SSB_DEVINL void attention_phase_cta(const MegaArgs& a, const bf16* kcache, const
       const int hu = u / n_active, sp = u - hu * n_active;
       const int kvh = (hu * G) / a.group;
       const int t_begin = sp * chunk, t_end = min(ctx, t_begin + chunk);
+      if (flag_layer >= 0) qkv_head_wait(a, flag_layer, hu * G, G, kvh, tid);
       const bool head_on = warp < G;
       float q[8];
       {
@@ -1258,6 +1293,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     *a.step += 1;
     if (a.fwd_counter) *a.fwd_counter += 1;
   }
+  // QKV -> attention by per-head counters instead of a grid barrier: only with the CTA-level attention forms (uniform per launch)
+  const bool head_flags = a.head_done != nullptr && ((G == 8 && a.attn_cta_tile) || (G < 8 && a.attn_coop));
+  if (head_flags && blockIdx.x == 0)
+    for (int i = tid; i < a.n_heads + 2 * a.kvh; i += MG_CW * 32) a.head_done[i] = 0u;  // visible to all through the first grid barrier
   if (weighted && tid == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1321,20 +1360,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     g.vcache = w.vcache;
     MG_STAMP();  // 1: x staged
     MG_TUNE_BEGIN();
-    consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s);
+    consume<BT, EPI_QKV_ROPE>(g, tiles, xs, full, empty, a.n_stages, r, warp, lane, red_s, nullptr, head_flags ? &a : nullptr);
     MG_TUNE_END();
     MG_STAMP();  // 2: qkv consumed
-    grid_sync(a.grid_bar, n_sync, n_ctas);
+    if (!head_flags) grid_sync(a.grid_bar, n_sync, n_ctas);  // else: the attention units wait for the heads they read
     MG_STAMP();  // 3
     // ---- attention
     if constexpr (G == 8) {
       if (a.attn_cta_tile)
-        attention_phase_cta<D>(a, w.kcache, w.vcache, xs, reinterpret_cast<int*>(red + 16), tid, warp, lane);
+        attention_phase_cta<D>(a, w.kcache, w.vcache, xs, reinterpret_cast<int*>(red + 16), tid, warp, lane, head_flags ? l : -1);
       else
         attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
     } else {
       if (a.attn_coop)
-        attention_phase_coop<D, G>(a, w.kcache, w.vcache, reinterpret_cast<float*>(xs), reinterpret_cast<int*>(red + 16), tid, warp, lane);
+        attention_phase_coop<D, G>(a, w.kcache, w.vcache, reinterpret_cast<float*>(xs), reinterpret_cast<int*>(red + 16), tid, warp, lane,
+                                   head_flags ? l : -1);
       else
         attention_phase<D, G>(a, w.kcache, w.vcache, warp, lane);
     }

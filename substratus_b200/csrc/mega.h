@@ -62,6 +62,10 @@ struct MegaArgs {
   const float* sm_weight;            // [256] relative streaming speed of each SM (by %smid), null = equal row shares
   float* cta_weight;                 // [n_ctas] scratch: the weight of the SM each CTA of THIS launch runs on
   float* tune_out;                   // [n_ctas][4] or null: per-CTA time spent in the weight phases (self-tuning of sm_weight)
+  // QKV -> attention without a grid barrier ("mega_head_flags", default on with the CTA-level attention forms): head_done[slot]
+  // counts the row pairs of q head / k head / v head `slot` whose epilogue has run in this launch (slots: n_heads q, kvh k, kvh v;
+  // head_dim/2 pairs each per layer); an attention unit waits only for the heads it reads.  Zeroed by the kernel at entry.
+  unsigned* head_done;
 };
 
 size_t mega_smem_bytes(int bt, int k_max, int n_stages);

@@ -77,7 +77,7 @@ struct TcCfg {
   static constexpr int BUDGET = TN <= 64 ? TC_SK_SMEM_BUDGET : 200 * 1024;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * TN <= 32) ? 32 : (2 * TN <= 64) ? 64 : (2 * TN <= 128) ? 128 : (2 * TN <= 256) ? 256 : 512;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*per-token pos / KV block of a tile*/;
 };
 
 template <int TN, int EPI>
@@ -92,6 +92,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + Cfg::STAGES;   // [2]
   uint64_t* tempty = tfull + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  [[maybe_unused]] int* s_pos = reinterpret_cast<int*>(bars) + 64;  // [TN] position of each token of the current tile (QKV epilogue)
+  [[maybe_unused]] int* s_blk = s_pos + TN;                        // [TN] KV block holding that position
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ntiles = (a.N + TC_BM - 1) / TC_BM;
@@ -183,6 +185,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = tile % n_mtiles, nt = tile / n_mtiles;  // token tiles fastest: CTAs running together share a weight tile (one HBM read)
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        // stage the tile's per-token position and KV block while its MMAs run (two dependent loads, once per token)
+        named_bar_sync(2, 128);  // the previous tile's epilogue no longer reads s_pos / s_blk
+        for (int t = threadIdx.x - 64; t < TN; t += 128) {
+          const int m = mt * TN + t;
+          int pos = 0, blk = 0;
+          if (m < a.M) {
+            pos = __ldcg(a.row_pos + m);
+            blk = a.block_table[(size_t)a.row_slot[m] * a.bt_stride + pos / a.block_size];
+          }
+          s_pos[t] = pos;
+          s_blk[t] = blk;
+        }
+        named_bar_sync(2, 128);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = nt * TC_BM + quad * 32 + lane;  // physical weight row (even = first of a pair)
@@ -199,7 +216,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mine[j] = __uint_as_float(v[j]);
           other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
         }
-        if (!(lane & 1) && row < a.N) tc_epilogue8<EPI>(a, row >> 1, mt * TN + c, mine, other);
+        if constexpr (EPI == EPI_QKV_ROPE) {
+          if (!(lane & 1) && row < a.N) tc_epilogue8_qkv_staged(a, row >> 1, mt * TN + c, s_pos + c, s_blk + c, mine, other);
+        } else {
+          if (!(lane & 1) && row < a.N) tc_epilogue8<EPI>(a, row >> 1, mt * TN + c, mine, other);
+        }
       }
       tc_fence_before();
       __syncwarp();
