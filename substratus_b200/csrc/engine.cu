@@ -692,7 +692,7 @@ int Engine::alloc_runtime(const Json& params) {
       } else {
         tune_rounds_left_ = 0;
       }
-      if (params.get_int("mega_head_flags", 1) != 0) {
+      if (params.get_int("mega_head_flags", 0) != 0) {  // needs a library built with -DMG_HEAD_FLAGS=1; measured slower (mega.cu)
         TRY(dmalloc(&mega_head_done_, (size_t)Hl_ + 2 * KVHl_ + 32));
         CK(cudaMemset(mega_head_done_, 0, ((size_t)Hl_ + 2 * KVHl_ + 32) * sizeof(unsigned)));
       }

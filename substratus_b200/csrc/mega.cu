@@ -371,6 +371,12 @@ SSB_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t
 }
 
 // ---------------------------------------------------------------- QKV -> attention dependency by head (no grid barrier)
+// MG_HEAD_FLAGS = 1 compiles this in (and params "mega_head_flags" then selects it per engine).  Compiled OUT by default:
+// measured on B200, Llama-2-7B batch 1 (run 11): 355.7 tok/s with the flags vs 369.3 with the grid barrier in the same build
+// (372.6 without the code) — 48 release-reductions per CTA and layer plus the polling cost more than the barrier they replace.
+#ifndef MG_HEAD_FLAGS
+#define MG_HEAD_FLAGS 0
+#endif
 SSB_DEVINL int qkv_head_slot(const MegaArgs& ma, int pair) {
   const int half = ma.head_dim >> 1, q_pairs = ma.q_rows >> 1, k_pairs = ma.kv_rows >> 1;
   if (pair < q_pairs) return pair / half;
@@ -1294,7 +1300,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     if (a.fwd_counter) *a.fwd_counter += 1;
   }
   // QKV -> attention by per-head counters instead of a grid barrier: only with the CTA-level attention forms (uniform per launch)
+#if MG_HEAD_FLAGS
   const bool head_flags = a.head_done != nullptr && ((G == 8 && a.attn_cta_tile) || (G < 8 && a.attn_coop));
+#else
+  constexpr bool head_flags = false;
+#endif
   if (head_flags && blockIdx.x == 0)
     for (int i = tid; i < a.n_heads + 2 * a.kvh; i += MG_CW * 32) a.head_done[i] = 0u;  // visible to all through the first grid barrier
   if (weighted && tid == 0) {
