@@ -1726,7 +1726,12 @@ int Engine::bench_kernel(const char* which, int rows, int ctx, int iters, double
       g.out_f32 = logits_;
       g.ld_out = cfg_.vocab;
       bytes = 2LL * g.N * g.K;
-      CK(launch_gemv(g, EPI_F32_BF16R, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
+      if (btc) {  // mirror forward(): batched decode runs lm_head on the tensor cores (norm kernel + stream-K GEMM)
+        CK(launch_rmsnorm(h_, final_norm_, xn_, rows, h, cfg_.eps, lc(true)));
+        CK(launch_tc_gemm(tm_lm_head_, btm_xn, btn, g, EPI_F32_BF16R, lc(true)));
+      } else {
+        CK(launch_gemv(g, EPI_F32_BF16R, cfg_.falcon ? NORM_LN : NORM_RMS, lc(true)));
+      }
     } else if (w == "attn") {
       AttnArgs a = {};
       a.q = q_;
