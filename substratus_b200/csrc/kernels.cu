@@ -16,6 +16,8 @@
 #include "kernels.h"
 #include <cstring>
 
+#include "gemv_core.cuh"
+
 // =====================================================================================================================
 // proj_rows_kernel
 // =====================================================================================================================
@@ -25,11 +27,20 @@ constexpr int GV_PW = 4;                        // producer warps: the compiler 
 constexpr int GV_THREADS = (GV_CW + GV_PW) * 32;
 constexpr int GV_ROWS = 2 * GV_CW;              // weight rows per stage (each consumer warp owns one row pair)
 constexpr int GV_KC = 1024;                     // K elements per stage
-constexpr int GV_STAGES = 3;                    // 3 x 32 KiB in flight per SM
-constexpr int GV_TILE_BYTES = GV_STAGES * GV_ROWS * GV_KC * 2;
+constexpr int GV_MAX_STAGES = 6;                // up to 6 x 32 KiB in flight per SM (as many as fit beside the staged activations)
+constexpr int GV_RS = GEMV_RS;                  // stage row stride (padded for ldmatrix, gemv_core.cuh)
+constexpr int GV_STAGE_ELEMS = GV_ROWS * GV_RS;
+constexpr int GV_RED_FLOATS = 2 * GV_CW * 16 * 4;  // cross-warp sum of the k slices, double-buffered by pass
 
 int gemv_pick_bt(int M, int K);
-static size_t gemv_smem_bytes(int bt, int K) { return (size_t)GV_TILE_BYTES + (size_t)bt * K * 2 + 2 * GV_STAGES * 8 + 64; }
+static size_t gemv_smem_bytes(int bt, int K, int stages) {
+  return (size_t)stages * GV_STAGE_ELEMS * 2 + (size_t)bt * K * 2 + 2 * (size_t)stages * 8 + 128 + (size_t)GV_RED_FLOATS * 4;
+}
+static int gemv_pick_stages(int bt, int K) {
+  int s = GV_MAX_STAGES;
+  while (s > 2 && gemv_smem_bytes(bt, K, s) > 225 * 1024) --s;
+  return s;
+}
 
 int gemv_grid_ctas(int M, int N, int K, int n_sm) {
   const int bt = gemv_pick_bt(M, K), P = N / 2;
@@ -38,21 +49,22 @@ int gemv_grid_ctas(int M, int N, int K, int n_sm) {
 
 int gemv_pick_bt(int M, int K) {
   int bt = M >= 4 ? 4 : (M >= 2 ? 2 : 1);
-  while (bt > 1 && gemv_smem_bytes(bt, K) > 220 * 1024) bt >>= 1;
+  while (bt > 1 && gemv_smem_bytes(bt, K, 2) > 225 * 1024) bt >>= 1;
   return bt;
 }
 
 #include "epilogue.cuh"
-#include "gemv_core.cuh"
 
 template <int BT, int EPI, int NORM>
 __global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  bf16* tiles = reinterpret_cast<bf16*>(smem_raw);            // [STAGES][ROWS][KC]
-  bf16* xs = tiles + GV_STAGES * GV_ROWS * GV_KC;             // [BT][K]
+  const int n_stages = a.n_stages;
+  bf16* tiles = reinterpret_cast<bf16*>(smem_raw);            // [n_stages][ROWS][RS]
+  bf16* xs = tiles + (size_t)n_stages * GV_STAGE_ELEMS;       // [BT][K]
   uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t)BT * a.K);
-  uint64_t* empty = full + GV_STAGES;
-  float* red = reinterpret_cast<float*>(empty + GV_STAGES);   // [GV_CW]
+  uint64_t* empty = full + n_stages;
+  float* red = reinterpret_cast<float*>(empty + n_stages);    // [32]
+  float* red_s = red + 32;                                    // [2][GV_CW][16][4] k-slice partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K;
@@ -62,8 +74,10 @@ __global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs
   const int m0 = blockIdx.y * BT;
   const int nk = (K + GV_KC - 1) / GV_KC;
 
+  for (size_t i = tid; i < (size_t)n_stages * GV_STAGE_ELEMS / 8; i += GV_THREADS)
+    reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);  // k tails multiply stale ring contents by zero: keep them finite
   if (tid == 0) {
-    for (int s = 0; s < GV_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], GV_PW);
       mbar_init(&empty[s], GV_CW);
     }
@@ -91,9 +105,9 @@ __global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs
         if (lane == 0) mbar_expect_tx(&full[stage], (uint32_t)(mine * len * 2));
         __syncwarp();
         if (lane < mine)
-          bulk_g2s_hint(tiles + ((size_t)stage * GV_ROWS + r0 + lane) * GV_KC, a.W + (size_t)(2 * ps + r0 + lane) * K + k0,
+          bulk_g2s_hint(tiles + ((size_t)stage * GV_ROWS + r0 + lane) * GV_RS, a.W + (size_t)(2 * ps + r0 + lane) * K + k0,
                         (uint32_t)(len * 2), &full[stage], pol);
-        if (++stage == GV_STAGES) {
+        if (++stage == n_stages) {
           stage = 0;
           phase ^= 1;
         }
@@ -203,14 +217,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs
     }
     named_bar_sync(1, GV_CW * 32);
 
+    // tensor-pipe consumers (gemv_core.cuh: mma_chunk): warp w multiplies all 16 rows of a stage by its 128-wide k slice; the 8
+    // slices are summed through shared memory per pass and warp w runs the epilogue of pair ps + w, lane b = batch row m0 + b
     int stage = 0;
     uint32_t phase = 0;
-    for (int ps = p0; ps < p1; ps += GV_CW) {
+    int pass = 0;
+    for (int ps = p0; ps < p1; ps += GV_CW, ++pass) {
       const int pair = ps + warp;
       const bool valid = pair < p1;
-      float acc0[BT], acc1[BT];
-#pragma unroll
-      for (int b = 0; b < BT; ++b) acc0[b] = acc1[b] = 0.f;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
       // the epilogue's dependent global reads, issued now and hidden by the K loop (epilogue.cuh: EpiPre)
       [[maybe_unused]] EpiPre pre = {0u, 0, 0, 0u};
       if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
@@ -220,33 +235,28 @@ __global__ void __launch_bounds__(GV_THREADS, 1) proj_rows_kernel(const GemvArgs
         const int k0 = kc * GV_KC;
         const int len = min(GV_KC, K - k0);
         mbar_wait(&full[stage], phase);
-        if (valid) {
-          const bf16* w0 = tiles + ((size_t)stage * GV_ROWS + 2 * warp) * GV_KC;
-          const bf16* w1 = w0 + GV_KC;
-          gemv_chunk<BT>(w0, w1, xs, K, k0, len, lane, acc0, acc1);
-        }
+        mma_chunk<BT>(tiles + (size_t)stage * GV_STAGE_ELEMS, xs, K, k0, len, warp, lane, c);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == GV_STAGES) {
+        if (++stage == n_stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      if (valid) {
+      float* rb = red_s + (size_t)(pass & 1) * (GV_CW * 64);
+      mma_store_partial<BT>(rb + warp * 64, lane, c);
+      named_bar_sync(1, GV_CW * 32);
+      if (valid && lane < BT && m0 + lane < a.M) {
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float s0 = warp_sum(acc0[b]);
-          const float s1 = warp_sum(acc1[b]);
-          if (lane == b) {
-            v0 = s0;
-            v1 = s1;
-          }
+        for (int w = 0; w < GV_CW; ++w) {  // fixed order: deterministic
+          v0 += rb[w * 64 + (2 * warp) * 4 + lane];
+          v1 += rb[w * 64 + (2 * warp + 1) * 4 + lane];
         }
         if constexpr (EPI == EPI_RESID || EPI == EPI_QKV_ROPE) {
-          if (lane < BT && m0 + lane < a.M) gemv_epilogue_pre<BT, EPI>(a, pair, m0 + lane, v0, v1, pre);
+          gemv_epilogue_pre<BT, EPI>(a, pair, m0 + lane, v0, v1, pre);
         } else {
-          if (lane < BT && m0 + lane < a.M) gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
+          gemv_epilogue<BT, EPI>(a, pair, m0 + lane, v0, v1);
         }
       }
     }
@@ -278,8 +288,10 @@ static cudaError_t launch_ex(KernelT kernel, dim3 grid, dim3 block, size_t smem,
 }
 
 template <int BT, int EPI, int NORM>
-static cudaError_t launch_gemv_t(const GemvArgs& a, const LaunchCfg& lc) {
-  const size_t smem = gemv_smem_bytes(BT, a.K);
+static cudaError_t launch_gemv_t(const GemvArgs& a_in, const LaunchCfg& lc) {
+  GemvArgs a = a_in;
+  a.n_stages = gemv_pick_stages(BT, a.K);
+  const size_t smem = gemv_smem_bytes(BT, a.K, a.n_stages);
   static unsigned long long attr_mask = 0;  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(proj_rows_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

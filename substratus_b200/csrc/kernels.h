@@ -57,6 +57,7 @@ struct GemvArgs {
   unsigned long long* const* push_flags;  // [push_n] peer-mapped arrival counters, [push_n] entries each (one per source)
   long long push_off;                     // element offset of (parity, this rank)'s slot inside a receive buffer
   int push_n, push_rank;
+  int n_stages;  // set by launch_gemv: ring stages that fit beside the staged activations (2..6)
 };
 
 struct AttnArgs {

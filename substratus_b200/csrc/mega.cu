@@ -34,7 +34,7 @@ constexpr int MG_KC = 1024;
 #ifndef MG_MMA
 #define MG_MMA 1  // default since round 2 (run 7, Llama-2-7B): 371.6 vs 360.9 tok/s at 1 row, 628 vs 591 at 2, 997 vs 893 at 4
 #endif
-constexpr int MG_RS = MG_MMA ? MG_KC + 8 : MG_KC;   // row stride inside a stage (elements)
+constexpr int MG_RS = MG_MMA ? GEMV_RS : MG_KC;     // row stride inside a stage (elements; gemv_core.cuh)
 constexpr int MG_STAGE_ELEMS = MG_ROWS * MG_RS;     // 32 KiB of bf16 (+ 256 B of padding with MG_MMA)
 constexpr int MG_RED_FLOATS = MG_MMA ? 2 * MG_CW * 16 * 4 : 0;  // cross-warp reduction of the K slices, double-buffered by pass
 
@@ -361,15 +361,6 @@ SSB_DEVINL uint4 ld_relaxed_sys_v4(const uint4* p) {
   return v;
 }
 
-SSB_DEVINL void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
-}
-SSB_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 // ---------------------------------------------------------------- QKV -> attention dependency by head (no grid barrier)
 // MG_HEAD_FLAGS = 1 compiles this in (and params "mega_head_flags" then selects it per engine).  Compiled OUT by default:
 // measured on B200, Llama-2-7B batch 1 (run 11): 355.7 tok/s with the flags vs 369.3 with the grid barrier in the same build
@@ -419,9 +410,6 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
   int p0, p1;
   part_range(P, p0, p1);
   const int nk = (K + MG_KC - 1) / MG_KC;
-  const int kw0 = warp * (MG_KC / MG_CW);
-  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lko = (lane >> 4) * 8;  // ldmatrix source row / k offset of this lane
-  const int bn = lane >> 2, bk = (lane & 3) * 2;                               // B fragment: batch row, k pair
   int pass = 0;
   for (int ps = p0; ps < p1; ps += MG_CW, ++pass) {
     const int pair = ps + warp;
@@ -435,32 +423,7 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
       const int k0 = kc * MG_KC;
       const int len = min(MG_KC, K - k0);
       mbar_wait(&full[r.stage], r.phase);
-      const uint32_t st = smem_u32(tiles + (size_t)r.stage * MG_STAGE_ELEMS) + (uint32_t)(lrow * MG_RS + kw0 + lko) * 2u;
-      const bf16* xrow = xs + (size_t)(bn < BT ? bn : 0) * K + k0 + kw0 + bk;
-      if (len == MG_KC) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
-          ldmatrix_x4(a0, a1, a2, a3, st + (uint32_t)ks * 32u);
-          if (bn < BT) {
-            b0 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16);
-            b1 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16 + 8);
-          }
-          mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
-        }
-      } else {
-        for (int ks = 0; ks < 8; ++ks) {
-          const int kk = kw0 + ks * 16;
-          if (kk >= len) break;  // warp-uniform
-          uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
-          ldmatrix_x4(a0, a1, a2, a3, st + (uint32_t)ks * 32u);
-          if (bn < BT) {
-            if (kk + bk < len) b0 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16);
-            if (kk + bk + 8 < len) b1 = *reinterpret_cast<const uint32_t*>(xrow + ks * 16 + 8);
-          }
-          mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
-        }
-      }
+      mma_chunk<BT>(tiles + (size_t)r.stage * MG_STAGE_ELEMS, xs, K, k0, len, warp, lane, c);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[r.stage]);
       if (++r.stage == n_stages) {
@@ -469,18 +432,7 @@ SSB_DEVINL void consume(const GemvArgs& a, const bf16* tiles, const bf16* xs, ui
       }
     }
     // ---- sum the 8 k slices: fragment element (row, col) lives in lane 4*(row % 8) + col/2, register (row/8)*2 + col%2
-    float* rs = red_s + (size_t)(pass & 1) * (MG_CW * 16 * 4) + (size_t)warp * 64;
-    {
-      const int col = (lane & 3) * 2, row = lane >> 2;
-      if (col < BT) {
-        rs[row * 4 + col] = c[0];
-        rs[(row + 8) * 4 + col] = c[2];
-      }
-      if (col + 1 < BT) {
-        rs[row * 4 + col + 1] = c[1];
-        rs[(row + 8) * 4 + col + 1] = c[3];
-      }
-    }
+    mma_store_partial<BT>(red_s + (size_t)(pass & 1) * (MG_CW * 16 * 4) + (size_t)warp * 64, lane, c);
     named_bar_sync(1, MG_CW * 32);
     if (valid && lane < BT && lane < a.M) {
       const float* rb = red_s + (size_t)(pass & 1) * (MG_CW * 16 * 4);
