@@ -762,6 +762,7 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
     else
       RET(SSB_EINVAL, "params.gemm_path must be auto|gemv|tc");
     mega_attn_tile_ = params.get_int("mega_attn_tile", 1) != 0;
+    mega_max_batch_ = (int)params.get_int("mega_max_batch", 1);
     tc_tn_prefill_ = (int)params.get_int("tc_tn_prefill", 0);  // 0 = per-projection heuristic; 128 | 256 force (tests, A/B)
     if (tc_tn_prefill_ != 0 && tc_tn_prefill_ != 128 && tc_tn_prefill_ != 256) RET(SSB_EINVAL, "params.tc_tn_prefill must be 0, 128 or 256");
     const int h = cfg_.hidden, D = cfg_.head_dim, br = tc_weight_box_rows();
@@ -1547,7 +1548,10 @@ int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int ns
   CK(cudaMemcpyAsync(row_pos_, pos.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
   CK(cudaMemsetAsync(step_, 0xFF, sizeof(int), stream_));  // -1: the embed kernel pre-increments
   timing_.h2d_bytes += 3LL * nseq * sizeof(int);
-  const bool mega = use_mega_ && !taps_ && nseq <= 4 && nseq < tc_min_rows_ && mega_pick_stages(nseq == 1 ? 1 : (nseq == 2 ? 2 : 4), mega_k_max_) > 0;
+  // persistent kernel for batch <= mega_max_batch_ (default 1): since proj_rows_kernel moved to the tensor pipe with a 6-deep
+  // ring the graph + PDL multi-kernel step is as fast at 1 row (372.6 vs 373.4 tok/s, Llama-2-7B) and faster at 2 and 4 rows
+  // (679 vs 624, 1124 vs 997) — profiles/r02_mega_vs_multikernel.txt
+  const bool mega = use_mega_ && !taps_ && nseq <= mega_max_batch_ && nseq <= 4 && nseq < tc_min_rows_ && mega_pick_stages(nseq == 1 ? 1 : (nseq == 2 ? 2 : 4), mega_k_max_) > 0;
   const bool graph = use_graph_ && !taps_ && !mega;
   if (graph && !graphs_.count(nseq)) {
     CK(cudaStreamSynchronize(stream_));

@@ -94,6 +94,7 @@ class Engine {
   unsigned long long* mega_prof_ = nullptr;
   bool mega_prof_all_ = false;
   bool mega_attn_tile_ = true;
+  int mega_max_batch_ = 1;  // params "mega_max_batch": largest batch the persistent kernel serves (above: graph of per-projection kernels)
   unsigned* mega_head_done_ = nullptr;  // per-head QKV completion counters (mega.h: head_done), null = grid barrier
   float* sm_weight_ = nullptr;   // [256] per-SM streaming speed (calibrate_sm_weights), null = equal shares
   float* cta_weight_ = nullptr;  // [n_sm] scratch of the persistent kernel

@@ -48,7 +48,7 @@ int gemv_grid_ctas(int M, int N, int K, int n_sm) {
 }
 
 int gemv_pick_bt(int M, int K) {
-  int bt = M >= 4 ? 4 : (M >= 2 ? 2 : 1);
+  int bt = M >= 3 ? 4 : (M >= 2 ? 2 : 1);  // 3 rows ride a 4-row tile: two passes of a 2-row tile would stream the weights twice
   while (bt > 1 && gemv_smem_bytes(bt, K, 2) > 225 * 1024) bt >>= 1;
   return bt;
 }
