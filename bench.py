@@ -237,11 +237,13 @@ def hf_cpu_measure(cfg, steps, warmup, prompt_len, tok_cap, batch=1, dtype="floa
             tokens(T)
         step_s = [tokens(T) for _ in range(max(1, steps))]
     del m, past
-    tok_s = batch * T * len(step_s) / sum(step_s)
+    # the host is shared (128 cores, other tenants): a burst in one step moved the MEAN by 30 % between driver runs, so the
+    # reported rate is tokens per step over the MEDIAN step time
+    tok_s = batch * T / statistics.median(step_s)
     return {"decode_tok_s": tok_s, "ttft_s": ttft, "threads": threads, "cores": os.cpu_count(), "build_s": build_s, "dtype": dtype,
             "tokens_per_step": T, "step_ms": [s * 1e3 for s in step_s], "n_params": n_params,
             "sample": f"one full-depth ({cfg.get('num_hidden_layers')} layers, {n_params / 1e9:.2f} G params) request: {batch}x {prompt_len}-token seeded prompt "
-                      f"prefilled once, then {len(step_s)} timed steps (+{max(0, warmup)} warm-up) of {T} greedy decode tokens each on the growing context; "
+                      f"prefilled once, then {len(step_s)} timed steps (+{max(0, warmup)} warm-up) of {T} greedy decode tokens each on the growing context (rate from the median step); "
                       f"HF transformers {dtype} eager (HF's CPU default dtype), {threads} host threads"}
 
 
@@ -259,7 +261,7 @@ def run_reference(args, rank, world):
                               cpu_baseline={"value": None, "unit": "tokens/s", "cores": _host_threads(), "kind": "reference", "sample": str(ex)})), flush=True)
         return
     v = r["decode_tok_s"]
-    line = dict(base, value=v, ms_per_step=statistics.mean(r["step_ms"]), tokens_per_step=r["tokens_per_step"],
+    line = dict(base, value=v, ms_per_step=statistics.median(r["step_ms"]), ms_per_step_mean=statistics.mean(r["step_ms"]), tokens_per_step=r["tokens_per_step"],
                 config={"workload": f"{args.workload} decode, batch {args.batch}, {args.ref_prompt_len}-token prompt, CPU reference path", "sample": r["sample"]},
                 ttft_ms_p50=r["ttft_s"] * 1e3, model_build_s=r["build_s"],
                 cpu_baseline={"value": v, "unit": "tokens/s", "cores": r["threads"], "kind": "reference", "sample": r["sample"]},

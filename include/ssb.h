@@ -66,7 +66,7 @@ typedef struct ssb_timing {
  *   "weights": "file" | "synthetic" (seeded hash weights at config.json's shapes; "seed"),
  *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank),
  *   "use_pdl" (1), "use_graph" (1), "use_mega" (1: persistent single-kernel decode step at batch <= 4),
- *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (8), "tc_streamk" (1), "prefill_chunk" (1024),
+ *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (5), "tc_streamk" (1), "prefill_chunk" (1024),
  *   "tc_tn_prefill" (0 = per-projection heuristic | 128 | 256: token-tile width of the prefill GEMMs),
  *   "attn_splits" (0 = heuristic; context splits of the decode attention kernels, a sweep knob),
  *   "mega_attn_tile" (1: CTA-tile attention for GQA groups of 8 inside the persistent kernel),

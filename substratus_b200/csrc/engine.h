@@ -108,7 +108,7 @@ class Engine {
   int calibrate_sm_weights(const Json& params);
   int mega_max_chunks_ = 0, mega_k_max_ = 0;
   int tc_tn_prefill_ = 0;  // params "tc_tn_prefill": force the prefill token-tile width (0 = heuristic)
-  int tc_min_rows_ = 8;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)
+  int tc_min_rows_ = 5;  // forwards with >= this many token rows run the projections on the tensor cores (tcgen05)
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 
