@@ -304,6 +304,7 @@ static GenResult generate(const std::vector<int32_t>& prompt, int max_new, int c
     r.tokens = rq.tokens;
     if (r.hit_eos) r.tokens.resize(kept);
     r.error = rq.error;
+    r.fatal = rq.error_code == SSB_ECUDA;  // the device is gone for every later request too: the caller exits for a restart
     r.ttft_ms = rq.ttft_ms;
     r.decode_ms = rq.total_ms - rq.ttft_ms;
     return r;
@@ -514,7 +515,17 @@ static void handle(int fd) {
              "ssb_generated_tokens_total %lld\n# TYPE ssb_errors_total counter\nssb_errors_total %lld\n"
              "# TYPE ssb_ttft_ms_sum counter\nssb_ttft_ms_sum %.3f\n# TYPE ssb_decode_ms_sum counter\nssb_decode_ms_sum %.3f\n",
              g_requests.load(), g_tokens.load(), g_errors.load(), g_ttft_us_sum.load() / 1e3, g_decode_us_sum.load() / 1e3);
-    respond(fd, 200, "OK", m, "text/plain; version=0.0.4");
+    std::string ms = m;
+    if (g_sched) {  // continuous batching: how full the shared steps are and how often admission waited for KV blocks
+      snprintf(m, sizeof m,
+               "# TYPE ssb_sched_decode_calls_total counter\nssb_sched_decode_calls_total %lld\n"
+               "# TYPE ssb_sched_step_rows_total counter\nssb_sched_step_rows_total %lld\n"
+               "# TYPE ssb_sched_max_rows gauge\nssb_sched_max_rows %d\n"
+               "# TYPE ssb_sched_kv_deferred_total counter\nssb_sched_kv_deferred_total %lld\n",
+               g_sched->steps(), g_sched->step_rows(), g_sched->max_rows_seen(), g_sched->deferred());
+      ms += m;
+    }
+    respond(fd, 200, "OK", ms, "text/plain; version=0.0.4");
   } else if (method == "POST" && (path == "/generate" || path == "/v1/completions")) {
     if (g_ready.load() != 1) {
       respond(fd, 503, "Service Unavailable", err_json("model is not loaded yet"));
@@ -740,8 +751,12 @@ int main(int argc, char** argv) {
       }
       if (pj.get_int("batching", 0) != 0 && g_peers.empty()) {
         g_abi.e = g_engine;
-        g_sched = new ssbhost::BatchScheduler<AbiEngine>(&g_abi, g_info.max_batch, (int)pj.get_int("batch_tick", 8));
-        fprintf(stderr, "serve: continuous batching on (max_batch %d)\n", g_info.max_batch);
+        int kv_total = 0, kv_free = 0;
+        if (ssb_kv_blocks(g_engine, &kv_total, &kv_free) != SSB_OK) kv_total = 0;  // no accounting: ENOMEM is the limit
+        g_sched = new ssbhost::BatchScheduler<AbiEngine>(&g_abi, g_info.max_batch, (int)pj.get_int("batch_tick", 8), kv_total,
+                                                         g_info.kv_block_size);
+        fprintf(stderr, "serve: continuous batching on (max_batch %d, %d KV blocks of %d tokens)\n", g_info.max_batch, kv_total,
+                g_info.kv_block_size);
       }
     } catch (std::exception&) {
     }

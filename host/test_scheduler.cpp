@@ -14,6 +14,7 @@ struct FakeEngine {
   std::mutex mu;
   std::map<int, int> len;  // sid -> cached length
   int next_sid = 0, max_slots = 8;
+  int kv_budget = 1 << 30;  // total cached tokens the fake "KV pool" holds: calls that would exceed it fail with -4, state untouched
   std::string err;
   std::atomic<int> decode_calls{0};
   int seq_create(int* sid) {
@@ -30,8 +31,19 @@ struct FakeEngine {
     std::lock_guard<std::mutex> lk(mu);
     return len.erase(sid) ? 0 : -1;
   }
+  int total() {
+    int t = 0;
+    for (auto& kv : len) t += kv.second;
+    return t;
+  }
   int prefill(const int* sids, const int32_t* toks, const int* lens, int nseq, int32_t* next) {
     std::lock_guard<std::mutex> lk(mu);
+    int add = 0;
+    for (int i = 0; i < nseq; ++i) add += lens[i];
+    if (total() + add > kv_budget) {
+      err = "KV block pool exhausted";
+      return -4;
+    }
     for (int i = 0, o = 0; i < nseq; o += lens[i], ++i) {
       len[sids[i]] += lens[i];
       next[i] = step(toks[o + lens[i] - 1], len[sids[i]]);
@@ -42,6 +54,10 @@ struct FakeEngine {
   int decode(const int* sids, const int32_t* last, int nseq, int nsteps, int32_t* out) {
     std::lock_guard<std::mutex> lk(mu);
     ++decode_calls;
+    if (total() + nseq * nsteps > kv_budget) {
+      err = "KV block pool exhausted";
+      return -4;
+    }
     for (int i = 0; i < nseq; ++i) {
       int32_t t = last[i];
       for (int s = 0; s < nsteps; ++s) {
@@ -116,6 +132,72 @@ int main() {
   if (!eng.len.empty()) {
     printf("FAIL %zu sequence slots leaked\n", eng.len.size());
     ++failures;
+  }
+  {
+    // resource exhaustion must fail ONE request, not its batch mates: budget for ~3 of 6 long requests
+    FakeEngine small;
+    small.kv_budget = 200;
+    ssbhost::BatchScheduler<FakeEngine> sched(&small, 8, 4);
+    const int kClients = 6;
+    std::vector<ssbhost::Request> reqs(kClients);
+    std::vector<std::thread> th;
+    for (int c = 0; c < kClients; ++c) {
+      reqs[c].prompt.assign(30, (int32_t)(c + 1));
+      reqs[c].max_new = 30;
+    }
+    for (int c = 0; c < kClients; ++c) th.emplace_back([&, c] { sched.submit(&reqs[c]); });
+    for (auto& t : th) t.join();
+    int okc = 0, failed = 0;
+    for (int c = 0; c < kClients; ++c) {
+      if (reqs[c].error.empty()) {
+        ++okc;
+        if (reqs[c].tokens != alone(reqs[c].prompt, reqs[c].max_new)) {
+          printf("FAIL survivor %d got wrong ids\n", c);
+          ++failures;
+        }
+      } else {
+        ++failed;
+        if (reqs[c].error.find("exhausted") == std::string::npos) {
+          printf("FAIL unexpected error '%s'\n", reqs[c].error.c_str());
+          ++failures;
+        }
+      }
+    }
+    printf("KV budget test: %d served, %d refused\n", okc, failed);
+    if (okc < 2 || failed < 1) {
+      printf("FAIL exhaustion should refuse some requests and serve the rest (served %d, refused %d)\n", okc, failed);
+      ++failures;
+    }
+    if (!small.len.empty()) {
+      printf("FAIL slots leaked after exhaustion\n");
+      ++failures;
+    }
+  }
+  {
+    // same pool, but the scheduler knows its size (ssb_kv_blocks): requests queue for blocks instead of failing
+    FakeEngine small;
+    small.kv_budget = 200;
+    ssbhost::BatchScheduler<FakeEngine> sched(&small, 8, 4, /*kv_total_blocks=*/12, /*kv_block_size=*/16);
+    const int kClients = 6;
+    std::vector<ssbhost::Request> reqs(kClients);
+    std::vector<std::thread> th;
+    for (int c = 0; c < kClients; ++c) {
+      reqs[c].prompt.assign(30, (int32_t)(c + 1));
+      reqs[c].max_new = 30;  // 60 tokens -> 4 blocks: three requests fit at a time
+    }
+    for (int c = 0; c < kClients; ++c) th.emplace_back([&, c] { sched.submit(&reqs[c]); });
+    for (auto& t : th) t.join();
+    for (int c = 0; c < kClients; ++c) {
+      if (!reqs[c].error.empty() || reqs[c].tokens != alone(reqs[c].prompt, reqs[c].max_new)) {
+        printf("FAIL admission-controlled request %d: '%s'\n", c, reqs[c].error.c_str());
+        ++failures;
+      }
+    }
+    printf("KV admission test: max rows %d, deferred passes %lld\n", sched.max_rows_seen(), sched.deferred());
+    if (sched.max_rows_seen() > 3 || sched.deferred() < 1) {
+      printf("FAIL admission should cap the batch at 3 rows and defer the rest\n");
+      ++failures;
+    }
   }
   printf(failures ? "SCHEDULER TEST FAILED\n" : "SCHEDULER TEST OK\n");
   return failures ? 1 : 0;

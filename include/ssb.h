@@ -105,6 +105,13 @@ int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int n
 /* Current cached length of a sequence (tokens in its KV cache). */
 int ssb_seq_len(ssb_engine* e, int seq_id, int* len);
 
+/* KV block pool of this engine: *total blocks of ssb_info.kv_block_size tokens, *free_now of them unassigned.  A sequence
+ * of n cached tokens holds ceil(n / kv_block_size) blocks until ssb_seq_free; ssb_prefill / ssb_decode return SSB_ENOMEM
+ * (state untouched) when the pool cannot cover the tokens they would add.  The host scheduler admits a request only when
+ * prompt + max_new_tokens blocks are available (host/scheduler.h) — the reference has no such limit to mirror: its
+ * container serves one request at a time (internal/controller/server_controller.go:115). */
+int ssb_kv_blocks(ssb_engine* e, int* total, int* free_now);
+
 int ssb_last_timing(ssb_engine* e, ssb_timing* out);
 int ssb_timing_reset(ssb_engine* e);
 

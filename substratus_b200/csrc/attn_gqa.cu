@@ -373,7 +373,7 @@ int attn_prefill_tile_rows() { return PF_Q; }
 cudaError_t launch_attn_prefill(const AttnArgs& a, const LaunchCfg& lc) {
   if (a.n_tiles <= 0) return cudaSuccess;
   const size_t smem = (size_t)(PF_Q + 2 * PF_K) * a.head_dim * 2;
-  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  static std::atomic<unsigned long long> attr_mask{0};  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (PF_Q + 2 * PF_K) * 128 * 2);
   }

@@ -834,8 +834,9 @@ int Engine::ensure_blocks(int slot, int new_len) {
   if (new_len > max_seq_) RET(SSB_EINVAL, "sequence would exceed max_seq_len");
   SeqSlot& s = slots_[slot];
   const int need = (new_len + block_size_ - 1) / block_size_;
+  // all or nothing per sequence: a refused call leaves the pool as it found it (the host retires ONE request and retries)
+  if (need - (int)s.blocks.size() > (int)free_blocks_.size()) RET(SSB_ENOMEM, "KV block pool exhausted");
   while ((int)s.blocks.size() < need) {
-    if (free_blocks_.empty()) RET(SSB_ENOMEM, "KV block pool exhausted");
     const int b = free_blocks_.back();
     free_blocks_.pop_back();
     host_bt_[(size_t)slot * max_blocks_per_seq_ + s.blocks.size()] = b;
@@ -2049,6 +2050,12 @@ int ssb_seq_free(ssb_engine* e, int seq_id) {
 int ssb_seq_len(ssb_engine* e, int seq_id, int* len) {
   GUARD(e);
   return len ? e->impl.seq_len(seq_id, len) : SSB_EINVAL;
+}
+int ssb_kv_blocks(ssb_engine* e, int* total, int* free_now) {
+  GUARD(e);
+  if (!total || !free_now) return SSB_EINVAL;
+  e->impl.kv_blocks(total, free_now);
+  return SSB_OK;
 }
 int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok,
                 float* logits_opt) {

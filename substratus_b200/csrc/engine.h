@@ -46,6 +46,10 @@ class Engine {
   int seq_create(int* id);
   int seq_free(int id);
   int seq_len(int id, int* len) const;
+  void kv_blocks(int* total, int* free_now) const {
+    *total = n_blocks_;
+    *free_now = (int)free_blocks_.size();
+  }
   int prefill(const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits);
   int decode(const int* seq_ids, const int32_t* last_tok, int nseq, int nsteps, int32_t* out_tok, float* logits);
   int last_timing(ssb_timing* t) const;

@@ -292,7 +292,7 @@ static cudaError_t launch_gemv_t(const GemvArgs& a_in, const LaunchCfg& lc) {
   GemvArgs a = a_in;
   a.n_stages = gemv_pick_stages(BT, a.K);
   const size_t smem = gemv_smem_bytes(BT, a.K, a.n_stages);
-  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  static std::atomic<unsigned long long> attr_mask{0};  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(proj_rows_kernel<BT, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(128, 1) sm_calib_kernel(const uint8_t* __restr
 }
 
 cudaError_t launch_sm_calib(const void* src, size_t bytes_per_cta, int n_ctas, unsigned long long* out, cudaStream_t s) {
-  static unsigned long long attr_mask = 0;
+  static std::atomic<unsigned long long> attr_mask{0};
   const int smem = 6 * 32 * 1024 + 64;  // the ring: also keeps it to one CTA per SM
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(sm_calib_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -1,5 +1,6 @@
 // kernels.h — host-visible launch API of the sm_100a decode kernels (plain structs, no torch).
 #pragma once
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -90,13 +91,14 @@ struct LaunchCfg {
   int sk_slots = 0;
 };
 
-// cudaFuncSetAttribute is per device: returns true the first time it is called for `mask` on the current device
-inline bool first_launch_on_device(unsigned long long& mask) {
+// cudaFuncSetAttribute is per device: returns true the first time it is called for `mask` on the current device.  TP rank
+// threads (one per device) reach the same static mask concurrently, hence the atomic read-modify-write.
+inline bool first_launch_on_device(std::atomic<unsigned long long>& mask) {
   int d = 0;
   cudaGetDevice(&d);
-  if ((mask >> d) & 1ull) return false;
-  mask |= 1ull << d;
-  return true;
+  const unsigned long long bit = 1ull << d;
+  if (mask.load(std::memory_order_acquire) & bit) return false;
+  return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
 }
 
 cudaError_t launch_gemv(const GemvArgs& a, int epi, int norm, const LaunchCfg& lc);

@@ -1506,7 +1506,7 @@ int mega_pick_stages(int bt, int k_max) {
 template <int BT, int D, int G, bool TP = false>
 static cudaError_t launch_mega_t(const MegaArgs& a, const LaunchCfg& lc) {
   const size_t smem = mega_smem_bytes(BT, a.k_max, a.n_stages);
-  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  static std::atomic<unsigned long long> attr_mask{0};  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<BT, D, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);  // + ~1.7 KiB static <= 227 KiB
     if (e != cudaSuccess) return e;

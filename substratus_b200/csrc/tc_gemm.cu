@@ -521,7 +521,7 @@ int tc_weight_box_rows() { return TC_BM; }
 template <int TN, int EPI>
 static cudaError_t launch_tc_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
   using Cfg = TcCfg<TN>;
-  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  static std::atomic<unsigned long long> attr_mask{0};  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
@@ -556,7 +556,7 @@ static cudaError_t launch_tc_e(int tn, const TcTensorMap& tmA, const TcTensorMap
 template <int TN, int EPI>
 static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, const GemvArgs& a, const LaunchCfg& lc) {
   using Cfg = TcCfg<TN>;
-  static unsigned long long attr_mask = 0;  // per instantiation, per device
+  static std::atomic<unsigned long long> attr_mask{0};  // per instantiation, per device
   if (first_launch_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_sk_kernel<TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;

@@ -44,6 +44,7 @@ class SsbTiming(C.Structure):
 
 EXPORTS = [
     "ssb_engine_create", "ssb_engine_destroy", "ssb_engine_info", "ssb_seq_create", "ssb_seq_free", "ssb_seq_len",
+    "ssb_kv_blocks",
     "ssb_prefill", "ssb_decode", "ssb_last_timing", "ssb_timing_reset", "ssb_tp_handle_size", "ssb_tp_export",
     "ssb_tp_connect", "ssb_bench_kernel", "ssb_debug_profile", "ssb_debug_read", "ssb_debug_dequant", "ssb_synth_fill_host", "ssb_last_error", "ssb_version", "ssb_tok_load", "ssb_tok_free", "ssb_tok_encode",
     "ssb_tok_decode", "ssb_model_read_tensor",
@@ -72,6 +73,7 @@ def load_library(path: str | None = None):
     lib.ssb_seq_create.argtypes = [vp, ip]
     lib.ssb_seq_free.argtypes = [vp, C.c_int]
     lib.ssb_seq_len.argtypes = [vp, C.c_int, ip]
+    lib.ssb_kv_blocks.argtypes = [vp, ip, ip]
     lib.ssb_prefill.argtypes = [vp, ip, i32p, ip, C.c_int, i32p, fp]
     lib.ssb_decode.argtypes = [vp, ip, i32p, C.c_int, C.c_int, i32p, fp]
     lib.ssb_last_timing.argtypes = [vp, C.POINTER(SsbTiming)]
@@ -154,6 +156,12 @@ class Engine:
         n = C.c_int()
         _check(self._lib, self._lib.ssb_seq_len(self._h, sid, C.byref(n)))
         return n.value
+
+    def kv_blocks(self) -> tuple[int, int]:
+        """(total, free) blocks of the KV pool; a block holds info.kv_block_size tokens."""
+        t, f = C.c_int(), C.c_int()
+        _check(self._lib, self._lib.ssb_kv_blocks(self._h, C.byref(t), C.byref(f)))
+        return t.value, f.value
 
     # ---- compute
     def prefill(self, seq_ids: Sequence[int], prompts: Sequence[Sequence[int]], want_logits: bool = False):

@@ -39,6 +39,7 @@ static void fake_logits(uint64_t s, int vocab, float* out) {
 struct ssb_engine {
   int vocab = 1000, max_batch = 32, max_seq_len = 4096, tp_size = 1, tp_rank = 0;
   int fail_code = SSB_ECUDA;  // "fake_fail_code": what the failing decode returns (SSB_ECUDA = the device is gone)
+  int kv_blocks = 1 << 20;  // "fake_kv_blocks": pool of 16-token blocks; prefill / decode beyond it return SSB_ENOMEM
   int step_us = 0, fail_after = -1;  // "fake_step_us": sleep per decode step; "fake_fail_after": decode calls before an error
   bool connected = false;
   std::mutex mu;
@@ -46,6 +47,18 @@ struct ssb_engine {
   int next_id = 0;
   long long decode_calls = 0, max_rows = 0;
 };
+constexpr int kFakeBlock = 16;
+// blocks the sequences hold, with `extra[i]` more tokens on the listed ones (caller holds e->mu)
+static int fake_blocks_used(ssb_engine* e, const int* ids, const int* extra, int n, int extra_all) {
+  int used = 0;
+  for (auto& kv : e->seqs) {
+    int len = kv.second.second;
+    for (int i = 0; i < n; ++i)
+      if (ids[i] == kv.first) len += extra ? extra[i] : extra_all;
+    used += (len + kFakeBlock - 1) / kFakeBlock;
+  }
+  return used;
+}
 struct ssb_tokenizer {
   ssb::Tokenizer impl;
 };
@@ -66,6 +79,7 @@ int ssb_engine_create(const char* model_dir, const char* params_json, ssb_engine
     e->step_us = (int)pj.get_int("fake_step_us", 0);
     e->fail_after = (int)pj.get_int("fake_fail_after", -1);
     e->fail_code = (int)pj.get_int("fake_fail_code", SSB_ECUDA);
+    e->kv_blocks = (int)pj.get_int("fake_kv_blocks", 1 << 20);
     const int load_ms = (int)pj.get_int("fake_load_ms", 0);
     if (load_ms > 0) std::this_thread::sleep_for(std::chrono::milliseconds(load_ms));
     if (pj.get_int("fake_load_error", 0) != 0) {
@@ -91,6 +105,7 @@ int ssb_engine_info(ssb_engine* e, ssb_info* out) {
   out->tp_size = e->tp_size;
   out->tp_rank = e->tp_rank;
   out->n_layers = 2;
+  out->kv_block_size = kFakeBlock;
   snprintf(out->model_type, sizeof out->model_type, "fake");
   snprintf(out->dtype, sizeof out->dtype, "u64");
   return SSB_OK;
@@ -111,6 +126,13 @@ int ssb_seq_free(ssb_engine* e, int seq_id) {
   std::lock_guard<std::mutex> lk(e->mu);
   return e->seqs.erase(seq_id) ? SSB_OK : SSB_EINVAL;
 }
+int ssb_kv_blocks(ssb_engine* e, int* total, int* free_now) {
+  if (!e || !total || !free_now) return SSB_EINVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  *total = e->kv_blocks;
+  *free_now = e->kv_blocks - fake_blocks_used(e, nullptr, nullptr, 0, 0);
+  return SSB_OK;
+}
 int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const int* lens, int nseq, int32_t* next_tok, float* logits) {
   if (!e || !seq_ids || !tokens || !lens || !next_tok || nseq < 1) return SSB_EINVAL;
   if (e->tp_size > 1 && !e->connected) {
@@ -118,6 +140,10 @@ int ssb_prefill(ssb_engine* e, const int* seq_ids, const int32_t* tokens, const 
     return SSB_ESTATE;
   }
   std::lock_guard<std::mutex> lk(e->mu);
+  if (fake_blocks_used(e, seq_ids, lens, nseq, 0) > e->kv_blocks) {
+    g_err = "KV block pool exhausted";
+    return SSB_ENOMEM;
+  }
   size_t off = 0;
   for (int i = 0; i < nseq; ++i) {
     auto it = e->seqs.find(seq_ids[i]);
@@ -139,6 +165,10 @@ int ssb_decode(ssb_engine* e, const int* seq_ids, const int32_t* last_tok, int n
   if (e->fail_after >= 0 && e->decode_calls >= e->fail_after) {
     g_err = "fake: decode failure requested";
     return e->fail_code;
+  }
+  if (fake_blocks_used(e, seq_ids, nullptr, nseq, nsteps) > e->kv_blocks) {
+    g_err = "KV block pool exhausted";
+    return SSB_ENOMEM;
   }
   ++e->decode_calls;
   for (int i = 0; i < nseq; ++i) {

@@ -309,12 +309,28 @@ def test_errors_and_slot_reuse(Engine, tmp_path):
             e.prefill([a], [list(range(40))])  # > max_seq_len
         with pytest.raises(SsbError):
             e.prefill([a], [[cfg["vocab_size"]]])  # token out of range
-        e.prefill([a], [list(range(30))])  # 2 blocks
+        assert e.kv_blocks() == (3, 3)
+        ta, _ = e.prefill([a], [list(range(30))])  # 2 blocks
+        assert e.kv_blocks() == (3, 1)
         with pytest.raises(SsbError) as ei:
             e.prefill([b], [list(range(20))])  # needs 2 more, 1 left
         assert ei.value.code == -4
-        e.seq_free(a)
+        # a refused call leaves the engine as it was (host/scheduler.h retires one request and retries the others)
+        assert e.kv_blocks() == (3, 1) and e.seq_len(a) == 30 and e.seq_len(b) == 0
+        tb, _ = e.prefill([b], [list(range(10))])  # the last block
+        assert e.kv_blocks() == (3, 0)
+        out, _ = e.decode([a, b], [int(ta[0]), int(tb[0])], 2)  # 32 and 12 tokens: nobody needs a new block
+        with pytest.raises(SsbError) as ei:
+            e.decode([b], [int(out[1, -1])], 5)  # 17 tokens: a second block, none left
+        assert ei.value.code == -4 and e.seq_len(b) == 12 and e.seq_len(a) == 32
+        e.seq_free(a)  # what the scheduler does: retire one request ...
+        out2, _ = e.decode([b], [int(out[1, -1])], 5)  # ... and the other carries on
+        assert e.seq_len(b) == 17 and e.kv_blocks() == (3, 1)
+        # and its ids are what an undisturbed run produces
         e.seq_free(b)
+        ref, _ = e.generate([list(range(10))], 8)
+        assert list(ref[0]) == [int(tb[0])] + [int(x) for x in out[1]] + [int(x) for x in out2[0]]
+        assert e.kv_blocks() == (3, 3)
         c = e.seq_create()
         t, _ = e.prefill([c], [list(range(20))])
         assert e.seq_len(c) == 20

@@ -220,7 +220,7 @@ def test_decode_failure_is_reported(serve_fake, tmp_path):
         assert _req(s.port, "/")[0] == 200 and s.p.poll() is None
 
 
-@pytest.mark.parametrize("params", [{}, {"tp_size": 2}])
+@pytest.mark.parametrize("params", [{}, {"tp_size": 2}, {"batching": 1}])
 def test_device_failure_answers_then_exits_nonzero(serve_fake, tmp_path, params):
     """a sticky device error (SSB_ECUDA) must not leave a ready-looking pod behind: the request is answered with
     the error, then the process exits non-zero so the Deployment restarts it (server_controller.go:280-296).  Same with
@@ -280,6 +280,27 @@ def test_continuous_batching_keeps_every_request_its_own_ids(serve_fake, tmp_pat
 
         with cf.ThreadPoolExecutor(10) as ex:  # more clients than slots: the rest wait their turn
             assert all(ex.map(one, range(10)))
+
+
+def test_batching_admits_by_kv_blocks_instead_of_failing_the_batch(serve_fake, tmp_path):
+    """ADVICE r1 (scheduler.h): the pool holds 8 blocks of 16 tokens; each request needs 3 (8 + 40 tokens), so two run at a
+    time and the others queue — nobody gets a 500 for somebody else's appetite.  A request larger than the whole pool is
+    the one that fails, alone."""
+    with Server(serve_fake, tmp_path, {"fake_vocab": 999, "batching": 1, "batch_tick": 4, "max_batch": 8, "fake_kv_blocks": 8,
+                                      "fake_step_us": 500}) as s:
+        s.wait_ready()
+
+        def one(i):
+            prompt = [i + 1] * 8
+            n = 300 if i == 3 else 40
+            code, r = _req(s.port, "/generate", {"tokens": prompt, "max_new_tokens": n})
+            if i == 3:
+                return code == 500 and "exhausted" in r["error"]
+            return code == 200 and r["tokens"] == fake_generate(prompt, n, 999)
+
+        with cf.ThreadPoolExecutor(8) as ex:
+            assert all(ex.map(one, range(8)))
+        assert _req(s.port, "/")[0] == 200 and s.p.poll() is None
 
 
 def test_tensor_parallel_ranks_in_one_container(serve_fake, tmp_path):
