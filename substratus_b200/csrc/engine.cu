@@ -645,6 +645,10 @@ int Engine::alloc_runtime(const Json& params) {
       TRY(dmalloc(&sk_part_, (size_t)sk_slots_ * 64 * 128));
       TRY(dmalloc(&sk_flags_, (size_t)sk_slots_));
       CK(cudaMemset(sk_flags_, 0, sk_slots_ * sizeof(unsigned)));
+      if (params.get_int("sk_prof", 0)) {
+        TRY(dmalloc(&sk_prof_, (size_t)n_sm_ * 8));
+        CK(cudaMemset(sk_prof_, 0, (size_t)n_sm_ * 8 * sizeof(unsigned long long)));
+      }
     }
   }
   // persistent decode kernel (mega.cu): per-layer pointer table, attention chunk partials, grid barrier
@@ -842,6 +846,19 @@ int Engine::ensure_blocks(int slot, int new_len) {
     host_bt_[(size_t)slot * max_blocks_per_seq_ + s.blocks.size()] = b;
     s.blocks.push_back(b);
   }
+  return SSB_OK;
+}
+
+// the blocks of several sequences in one step: checks every length and the pool first, then grants — nothing changes on error
+int Engine::ensure_blocks_all(const int* slot_ids, const int* new_lens, int n) {
+  long long need = 0;
+  for (int i = 0; i < n; ++i) {
+    if (new_lens[i] > max_seq_) RET(SSB_EINVAL, "sequence would exceed max_seq_len");
+    const int want = (new_lens[i] + block_size_ - 1) / block_size_ - (int)slots_[slot_ids[i]].blocks.size();
+    if (want > 0) need += want;
+  }
+  if (need > (long long)free_blocks_.size()) RET(SSB_ENOMEM, "KV block pool exhausted");
+  for (int i = 0; i < n; ++i) TRY(ensure_blocks(slot_ids[i], new_lens[i]));
   return SSB_OK;
 }
 
@@ -1154,12 +1171,17 @@ int Engine::prefill(const int* seq_ids, const int32_t* tokens, const int* lens, 
     if (lens[i] < 1) RET(SSB_EINVAL, "empty prompt");
     for (int j = 0; j < i; ++j)
       if (seq_ids[j] == s) RET(SSB_EINVAL, "duplicate seq_id");
-    TRY(ensure_blocks(s, slots_[s].len + lens[i]));
     total += lens[i];
   }
   for (int i = 0, o = 0; i < nseq; o += lens[i], ++i)
     for (int t = 0; t < lens[i]; ++t)
       if (tokens[o + t] < 0 || tokens[o + t] >= cfg_.vocab) RET(SSB_EINVAL, "token id out of range");
+  // blocks last, and for the whole call or not at all: a refused call leaves the pool as it found it
+  {
+    std::vector<int> new_len(nseq);
+    for (int i = 0; i < nseq; ++i) new_len[i] = slots_[seq_ids[i]].len + lens[i];
+    TRY(ensure_blocks_all(seq_ids, new_len.data(), nseq));
+  }
   TRY(upload_block_rows(slots));
   // flatten rows
   std::vector<int> r_tok(total), r_slot(total), r_pos(total), r_last(total, -1);
@@ -1542,8 +1564,12 @@ int Engine::decode(const int* seq_ids, const int32_t* last_tok, int nseq, int ns
     for (int j = 0; j < i; ++j)
       if (seq_ids[j] == s) RET(SSB_EINVAL, "duplicate seq_id");
     if (last_tok[i] < 0 || last_tok[i] >= cfg_.vocab) RET(SSB_EINVAL, "token id out of range");
-    TRY(ensure_blocks(s, slots_[s].len + nsteps));
     pos[i] = slots_[s].len;
+  }
+  {
+    std::vector<int> new_len(nseq);
+    for (int i = 0; i < nseq; ++i) new_len[i] = pos[i] + nsteps;
+    TRY(ensure_blocks_all(seq_ids, new_len.data(), nseq));
   }
   TRY(upload_block_rows(slots));
   CK(cudaMemcpyAsync(row_tok_, last_tok, nseq * sizeof(int), cudaMemcpyHostToDevice, stream_));
@@ -1925,6 +1951,22 @@ int Engine::debug_read(const char* name, float* dst, int64_t n, int* rows, int* 
       for (int i = 0; i < 256; ++i) dst[i] = 1.0f;
     *rows = 1;
     *cols = 256;
+    return SSB_OK;
+  }
+  if (nm == "sk_prof") {  // [n_sm][8] stamps of the last stream-K projection launch, us from the earliest (0 = not stamped)
+    if (!sk_prof_) RET(SSB_ESTATE, "engine was not created with params.sk_prof=1");
+    if (n < (int64_t)n_sm_ * 8) RET(SSB_EINVAL, "destination too small");
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    std::vector<unsigned long long> t((size_t)n_sm_ * 8);
+    CK(cudaMemcpy(t.data(), sk_prof_, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < t.size(); ++i)
+      if (i % 8 != 7 && t[i] && t[i] < t0) t0 = t[i];
+    for (size_t i = 0; i < t.size(); ++i)  // column 7 is a count (segments of the CTA's range), not a time
+      dst[i] = i % 8 == 7 ? (float)t[i] : (t[i] ? (float)((double)(t[i] - t0) * 1e-3) : -1.0f);
+    *rows = n_sm_;
+    *cols = 8;
     return SSB_OK;
   }
   if (nm == "mega_prof_all") {  // [n_ctas][1024]: per-CTA phase stamps of the LAST step in us from the earliest one; column 1023 = %smid

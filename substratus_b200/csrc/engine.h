@@ -69,6 +69,7 @@ class Engine {
   int dmalloc(T** p, size_t n);
   // run
   int ensure_blocks(int slot, int new_len);
+  int ensure_blocks_all(const int* slot_ids, const int* new_lens, int n);
   int upload_block_rows(const std::vector<int>& slots);
   int forward(int M, int n_logit_rows, bool decode_mode);  // enqueue one forward over the staged rows
   int build_graph(int B);
@@ -79,11 +80,13 @@ class Engine {
     c.sk_part = sk_part_;
     c.sk_flags = sk_flags_;
     c.sk_slots = sk_slots_;
+    c.sk_prof = sk_prof_;
     return c;
   }
   float* sk_part_ = nullptr;  // stream-K workspace of the tensor-core decode projections
   unsigned* sk_flags_ = nullptr;
   int sk_slots_ = 0;
+  unsigned long long* sk_prof_ = nullptr;  // params "sk_prof": 1 (needs the skprof variant library to be written)
 
   ModelCfg cfg_;
   int tp_size_ = 1, tp_rank_ = 0, device_ = 0, n_sm_ = 148;

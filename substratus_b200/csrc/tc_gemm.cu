@@ -247,7 +247,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 struct SkWs {
   float* part;      // [slots][TN/8][128][8] fp32
   unsigned* flags;  // [slots], zero on entry and on exit
+  unsigned long long* prof;  // [grid][8] globaltimer stamps (TC_SK_PROF builds), may be null
 };
+#ifndef TC_SK_PROF
+#define TC_SK_PROF 0
+#endif
+// phase stamps of one stream-K launch, per CTA: 0 entry, 1 setup done (barriers, TMEM), 2 first weight tile landed,
+// 3 last MMA committed, 4 epilogue saw the last accumulator, 5 epilogue done, 6 exit, 7 = number of segments
+SSB_DEVINL void sk_stamp(const SkWs& ws, int i) {
+#if TC_SK_PROF
+  if (ws.prof) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ws.prof[(size_t)blockIdx.x * 8 + i] = t;
+  }
+#endif
+}
 
 #ifndef TC_SK_PREFETCH_RING
 #define TC_SK_PREFETCH_RING 0
@@ -273,6 +288,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const long long u0 = (long long)blockIdx.x * U / G, u1 = (long long)(blockIdx.x + 1) * U / G;
 
   if (threadIdx.x == 0) {
+    sk_stamp(ws, 0);
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -294,6 +310,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) sk_stamp(ws, 1);
   pdl_launch_dependents();
 
   if (warp == 0) {
@@ -360,6 +377,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
+          if (TC_SK_PROF && u == u0 && kb == kb0) sk_stamp(ws, 2);
           const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
           const uint64_t ad = umma_desc_k_sw128(sa);
           const uint64_t bd = umma_desc_k_sw128(sa + Cfg::A_BYTES);
@@ -368,6 +386,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_mma_bf16(tmem_base + acc * TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > kb0) || k != 0);
           tc_commit(&empty[stage]);
           if (kb == kb1 - 1) tc_commit(&tfull[acc]);
+          if (TC_SK_PROF && u + (kb1 - kb0) >= u1 && kb == kb1 - 1) sk_stamp(ws, 3);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) {
@@ -391,6 +410,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool is_first_seg = (u == u0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (TC_SK_PROF && warp == 2 && lane == 0 && u + (kb1 - kb0) >= u1) sk_stamp(ws, 4);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN;
       const int row = nt * TC_BM + erow;
       if (kb0 != 0) {
@@ -462,9 +482,14 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       u += kb1 - kb0;
     }
+    if (TC_SK_PROF && warp == 2 && lane == 0) {
+      sk_stamp(ws, 5);
+      if (ws.prof) ws.prof[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)it;
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (TC_SK_PROF && threadIdx.x == 0) sk_stamp(ws, 6);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
@@ -567,7 +592,7 @@ static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, c
   long long gmax = U / min_units;
   int grid = (int)(gmax < 1 ? 1 : (gmax < lc.n_sm ? gmax : lc.n_sm));
   if (grid * 2 > lc.sk_slots) return cudaErrorInvalidValue;
-  const SkWs ws = {lc.sk_part, lc.sk_flags};
+  const SkWs ws = {lc.sk_part, lc.sk_flags, lc.sk_prof};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
