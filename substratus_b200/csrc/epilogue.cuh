@@ -162,17 +162,15 @@ SSB_DEVINL void gemv_epilogue_pre(const GemvArgs& a, int pair, int m, float v0, 
 // the tile run).  The generic form below re-reads row_pos -> {rope table, row_slot -> block_table} per thread: three
 // dependent L2 round trips per eight tokens, which made the prefill QKV GEMM take longer than gate/up for 56 % of its
 // FLOPs (profiles/r02_ncu_summary.txt).  Here only the rope-table read remains, all eight issued at once.
-SSB_DEVINL void tc_epilogue8_qkv_staged(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, const int* __restrict__ s_blk,
-                                        const float (&v0)[8], const float (&v1)[8]) {
+SSB_DEVINL void tc_epilogue8_qkv_cs(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, const int* __restrict__ s_blk,
+                                    const uint32_t* cs, const float (&v0)[8], const float (&v1)[8]) {
+  // cs[j] = packed cos | sin of (token m0 + j, this pair), already loaded by the caller (unused for V rows)
   const int hd = a.head_dim, half = hd >> 1;
   const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
   const bool is_q = pair < q_pairs, is_k = !is_q && pair < q_pairs + k_pairs;
   if (is_q || is_k) {
     const int pp = is_q ? pair : pair - q_pairs;
     const int head = pp / half, jj = pp - head * half;
-    uint32_t cs[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cs[j] = (m0 + j < a.M) ? a.rope_cs[(size_t)s_pos[j] * half + jj] : 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (m0 + j >= a.M) continue;
@@ -195,6 +193,19 @@ SSB_DEVINL void tc_epilogue8_qkv_staged(const GemvArgs& a, int pair, int m0, con
       *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0[j], v1[j]);
     }
   }
+}
+SSB_DEVINL void tc_epilogue8_qkv_staged(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, const int* __restrict__ s_blk,
+                                        const float (&v0)[8], const float (&v1)[8]) {
+  const int half = a.head_dim >> 1;
+  const int q_pairs = a.q_rows >> 1, k_pairs = a.kv_rows >> 1;
+  uint32_t cs[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  if (pair < q_pairs + k_pairs) {
+    const int pp = pair < q_pairs ? pair : pair - q_pairs;
+    const int jj = pp % half;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = (m0 + j < a.M) ? a.rope_cs[(size_t)s_pos[j] * half + jj] : 0u;
+  }
+  tc_epilogue8_qkv_cs(a, pair, m0, s_pos, s_blk, cs, v0, v1);
 }
 
 template <int EPI>

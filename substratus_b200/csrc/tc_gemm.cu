@@ -48,6 +48,11 @@ SSB_DEVINL void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+SSB_DEVINL void tc_ld8p(uint32_t taddr, uint32_t* v) {  // same, into v[0..7] of a larger register array
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 SSB_DEVINL void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row groups of 128 B rows, groups 1024 B apart
@@ -252,6 +257,9 @@ struct SkWs {
 #ifndef TC_SK_PROF
 #define TC_SK_PROF 0
 #endif
+#ifndef TC_SK_EPI_V2
+#define TC_SK_EPI_V2 1  // batched owner epilogue (0 = the first version, kept for the A/B: variant library "skepi1")
+#endif
 // phase stamps of one stream-K launch, per CTA: 0 entry, 1 setup done (barriers, TMEM), 2 first weight tile landed,
 // 3 last MMA committed, 4 epilogue saw the last accumulator, 5 epilogue done, 6 exit, 7 = number of segments
 SSB_DEVINL void sk_stamp(const SkWs& ws, int i) {
@@ -283,9 +291,13 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ntiles = (a.N + TC_BM - 1) / TC_BM;
   const int nkb = (a.K + TC_BK - 1) / TC_BK;
-  const long long U = (long long)n_ntiles * nkb;
-  const long long G = gridDim.x;
-  const long long u0 = (long long)blockIdx.x * U / G, u1 = (long long)(blockIdx.x + 1) * U / G;
+  // 32-bit unit arithmetic (the launcher checks U * grid < 2^31): the 64-bit divisions of the first version were software
+  // routines on the critical path of every segment and of the owner's contributor search
+  const int U = n_ntiles * nkb;
+  const int G = (int)gridDim.x;
+  const int u0 = (int)((unsigned)blockIdx.x * (unsigned)U / (unsigned)G), u1 = (int)((unsigned)(blockIdx.x + 1) * (unsigned)U / (unsigned)G);
+  [[maybe_unused]] int* s_pos = reinterpret_cast<int*>(bars) + 64;  // [TN] position of each token (QKV epilogue), staged once
+  [[maybe_unused]] int* s_blk = s_pos + TN;                        // [TN] KV block holding that position
 
   if (threadIdx.x == 0) {
     sk_stamp(ws, 0);
@@ -320,22 +332,22 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool waited = false;
-      long long ustart = u0;
+      int ustart = u0;
 #if TC_SK_PREFETCH_RING
       // compile-time experiment for round 2 (never run on hardware): put the weight tiles of the first ring-full of
       // units in flight before the dependency wait instead of only the first one, so the HBM stream of this projection
       // ramps up while the previous kernel drains; the activation tiles follow after the wait on the same barriers.
       {
-        const long long upre = min(u1, u0 + (long long)Cfg::STAGES);
+        const int upre = min(u1, u0 + Cfg::STAGES);
         int st = 0;
-        for (long long u = u0; u < upre; ++u, ++st) {  // the ring starts empty: no empty-wait in the first pass
+        for (int u = u0; u < upre; ++u, ++st) {  // the ring starts empty: no empty-wait in the first pass
           mbar_expect_tx(&full[st], Cfg::A_BYTES + Cfg::B_BYTES);
           tma_load_2d(smem + (size_t)st * Cfg::STAGE_BYTES, &tmA, (int)(u % nkb) * TC_BK, (int)(u / nkb) * TC_BM, &full[st]);
         }
         pdl_wait();
         waited = true;
         st = 0;
-        for (long long u = u0; u < upre; ++u, ++st)
+        for (int u = u0; u < upre; ++u, ++st)
           tma_load_2d(smem + (size_t)st * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (int)(u % nkb) * TC_BK, 0, &full[st]);
         const int n = (int)(upre - u0);
         stage = n % Cfg::STAGES;
@@ -343,8 +355,8 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ustart = upre;
       }
 #endif
-      for (long long u = ustart; u < u1; ++u) {
-        const int nt = (int)(u / nkb), kb = (int)(u % nkb);
+      for (int u = ustart; u < u1; ++u) {
+        const int nt = u / nkb, kb = u - nt * nkb;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
@@ -366,9 +378,9 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (long long u = u0; u < u1; ++it) {
-      const int kb0 = (int)(u % nkb);
-      const int kb1 = (int)min((long long)nkb, kb0 + (u1 - u));
+    for (int u = u0; u < u1; ++it) {
+      const int kb0 = u % nkb;
+      const int kb1 = min(nkb, kb0 + (u1 - u));
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -401,10 +413,23 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     pdl_wait();  // residuals / positions written by the previous kernel
     const int quad = warp & 3;
     const int erow = quad * 32 + lane;  // row inside the 128-row tile
+    if constexpr (EPI == EPI_QKV_ROPE && TC_SK_EPI_V2) {
+      // per-token position and KV block, once per CTA (two dependent loads) instead of per thread and 8-token chunk
+      for (int t = threadIdx.x - 64; t < TN; t += 128) {
+        int pos = 0, blk = 0;
+        if (t < a.M) {
+          pos = __ldcg(a.row_pos + t);
+          blk = a.block_table[(size_t)a.row_slot[t] * a.bt_stride + pos / a.block_size];
+        }
+        s_pos[t] = pos;
+        s_blk[t] = blk;
+      }
+      named_bar_sync(2, 128);
+    }
     int it = 0;
-    for (long long u = u0; u < u1; ++it) {
-      const int nt = (int)(u / nkb), kb0 = (int)(u % nkb);
-      const int kb1 = (int)min((long long)nkb, kb0 + (u1 - u));
+    for (int u = u0; u < u1; ++it) {
+      const int nt = u / nkb, kb0 = u - nt * nkb;
+      const int kb1 = min(nkb, kb0 + (u1 - u));
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const bool is_first_seg = (u == u0);
@@ -427,7 +452,10 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
         }
         tc_fence_before();
+#if !TC_SK_EPI_V2
         __threadfence();
+#endif
+        // the barrier orders the 128 threads' stores before warp 2's release store (release is cumulative at gpu scope)
         named_bar_sync(2, 128);
         if (warp == 2 && lane == 0) {
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.flags + slot), "r"(1u) : "memory");
@@ -436,16 +464,127 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive(&tempty[acc]);
         }
       } else {
-        // owner: the part starting at k = 0.  Contributors = the CTAs whose ranges cover the rest of this tile.
-        const long long t_end = (long long)(nt + 1) * nkb;          // first unit after this tile
-        long long cu = u + (kb1 - kb0);                               // first unit not covered by this CTA
+        // owner: the part starting at k = 0.  Contributors = the CTAs whose ranges cover the rest of this tile: the next
+        // n_contrib CTAs (every CTA has a non-empty range: grid <= U), each with its FIRST segment.
+#if TC_SK_EPI_V2
+        // Version 2.  The first version spent ~11 us here per owner (profiles/r02_sk_phase_stamps_v1.txt) in 12-16 SERIAL L2
+        // round trips: flag by flag, then per 8-token chunk the partials, then the residual / RoPE inputs.  Now every load
+        // that does not depend on another is issued together: epilogue inputs first (they depend on nothing computed
+        // here), all flags in one batch, partials of 32 tokens x 2 contributors in flight at a time.
+        const int t_end = (nt + 1) * nkb;  // first unit after this tile
+        int n_contrib = 0;
+        for (int cu = u + (kb1 - kb0); cu < t_end && n_contrib < 12; ++n_contrib)
+          cu = (int)((unsigned)(blockIdx.x + n_contrib + 2) * (unsigned)U / (unsigned)G);
+        const int slot0 = (blockIdx.x + 1) * 2;  // contributor i dumped into slot0 + 2 i
+        constexpr int CG = TN < 32 ? TN : 32;    // tokens per pass
+        const bool epi_lane = !(lane & 1) && row < a.N;
+        const int pair = row >> 1;
+        bool polled = false;
+#pragma unroll 1
+        for (int g0 = 0; g0 < TN; g0 += CG) {
+          if (g0 >= a.M) break;  // warp-uniform
+          uint32_t v[CG];
+#pragma unroll
+          for (int q = 0; q < CG / 8; ++q) tc_ld8p(taddr + g0 + 8 * q, &v[8 * q]);
+          // ---- epilogue inputs of these tokens
+          [[maybe_unused]] uint32_t w[CG];
+          if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+            for (int j = 0; j < CG; ++j)
+              w[j] = (epi_lane && g0 + j < a.M) ? __ldcg(reinterpret_cast<const uint32_t*>(a.resid + (size_t)(g0 + j) * a.ld_out + 2 * pair)) : 0u;
+          } else if constexpr (EPI == EPI_QKV_ROPE) {
+            const int half = a.head_dim >> 1, qk_pairs = (a.q_rows + a.kv_rows) >> 1;
+            const int pp = pair < (a.q_rows >> 1) ? pair : pair - (a.q_rows >> 1);
+            const int jj = pp % half;
+#pragma unroll
+            for (int j = 0; j < CG; ++j)
+              w[j] = (epi_lane && pair < qk_pairs && g0 + j < a.M) ? a.rope_cs[(size_t)s_pos[g0 + j] * half + jj] : 0u;
+          }
+          // ---- all contributors' flags in one round trip (they are normally up long before the owner gets here)
+          if (!polled) {
+            polled = true;
+            for (;;) {
+              unsigned ok = 1u;
+#pragma unroll
+              for (int i = 0; i < 12; ++i) {
+                unsigned f = 1u;
+                if (i < n_contrib) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(ws.flags + slot0 + 2 * i) : "memory");
+                ok &= (f != 0u) ? 1u : 0u;
+              }
+              if (ok) break;
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire: the contributors' partials are visible to this thread
+          }
+          tc_wait_ld();
+          float f[CG];
+#pragma unroll
+          for (int j = 0; j < CG; ++j) f[j] = __uint_as_float(v[j]);
+          const float* pbase = ws.part + (size_t)slot0 * (TN * 128) + ((size_t)(g0 / 8) * 128 + erow) * 8;
+#pragma unroll 1
+          for (int i = 0; i < n_contrib; i += 2) {
+            const bool two = i + 1 < n_contrib;
+            const float* p0 = pbase + (size_t)(2 * i) * (TN * 128);
+            const float* p1 = p0 + (size_t)2 * (TN * 128);
+            float4 x[CG / 4], y[CG / 4];
+#pragma unroll
+            for (int q = 0; q < CG / 8; ++q) {
+              x[2 * q] = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)q * 128 * 8));
+              x[2 * q + 1] = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)q * 128 * 8) + 1);
+            }
+#pragma unroll
+            for (int q = 0; q < CG / 8; ++q) {
+              y[2 * q] = two ? __ldcg(reinterpret_cast<const float4*>(p1 + (size_t)q * 128 * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              y[2 * q + 1] = two ? __ldcg(reinterpret_cast<const float4*>(p1 + (size_t)q * 128 * 8) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // same order of additions as the first version: contributor i, then i + 1
+#pragma unroll
+            for (int q = 0; q < CG / 4; ++q) {
+              f[4 * q] += x[q].x; f[4 * q + 1] += x[q].y; f[4 * q + 2] += x[q].z; f[4 * q + 3] += x[q].w;
+            }
+#pragma unroll
+            for (int q = 0; q < CG / 4; ++q) {
+              f[4 * q] += y[q].x; f[4 * q + 1] += y[q].y; f[4 * q + 2] += y[q].z; f[4 * q + 3] += y[q].w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CG; c += 8) {
+            if (g0 + c < a.M) {  // warp-uniform
+              float mine[8], other[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                mine[j] = f[c + j];
+                other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
+              }
+              if (epi_lane) {
+                if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (g0 + c + j < a.M)
+                      *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)(g0 + c + j) * a.ld_out + 2 * pair) =
+                          pack_bf16(bf16r(mine[j]) + bf_lo(w[c + j]), bf16r(other[j]) + bf_hi(w[c + j]));
+                } else if constexpr (EPI == EPI_QKV_ROPE) {
+                  tc_epilogue8_qkv_cs(a, pair, g0 + c, s_pos + g0 + c, s_blk + g0 + c, &w[c], mine, other);
+                } else {
+                  tc_epilogue8<EPI>(a, pair, g0 + c, mine, other);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(2, 128);  // every epilogue thread has consumed the partials
+        if (warp == 2 && lane < n_contrib) ws.flags[slot0 + 2 * lane] = 0;  // clean for the next launch
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+#else
+        const int t_end = (nt + 1) * nkb;                     // first unit after this tile
+        int cu = u + (kb1 - kb0);                              // first unit not covered by this CTA
         int n_contrib = 0;
         int cslot[12];  // the launcher sizes the grid so that a tile is never split over more than 10 CTAs
-        for (long long c = blockIdx.x + 1; cu < t_end && c < G && n_contrib < 12; ++c) {
-          const long long c0 = c * U / G, c1 = (c + 1) * U / G;
+        for (int c = blockIdx.x + 1; cu < t_end && c < G && n_contrib < 12; ++c) {
+          const int c0 = (int)((unsigned)c * (unsigned)U / (unsigned)G), c1 = (int)((unsigned)(c + 1) * (unsigned)U / (unsigned)G);
           if (c1 <= c0) continue;
           // CTA c's segment inside this tile starts at max(c0, cu) == c0 (ranges are contiguous) and is its FIRST segment
-          cslot[n_contrib++] = (int)c * 2 + 0;
+          cslot[n_contrib++] = c * 2 + 0;
           cu = c1;
         }
         for (int i = 0; i < n_contrib; ++i) {
@@ -479,6 +618,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (warp == 2 && lane == 0)
           for (int i = 0; i < n_contrib; ++i) ws.flags[cslot[i]] = 0;  // clean for the next launch
         if (lane == 0) mbar_arrive(&tempty[acc]);
+#endif
       }
       u += kb1 - kb0;
     }
@@ -591,7 +731,7 @@ static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, c
   const long long min_units = (nkb + 7) / 8;  // >= nkb/8 units per CTA: a tile spans at most 8 full + 2 partial ranges
   long long gmax = U / min_units;
   int grid = (int)(gmax < 1 ? 1 : (gmax < lc.n_sm ? gmax : lc.n_sm));
-  if (grid * 2 > lc.sk_slots) return cudaErrorInvalidValue;
+  if (grid * 2 > lc.sk_slots || U * (grid + 1) >= (1ll << 31)) return cudaErrorInvalidValue;
   const SkWs ws = {lc.sk_part, lc.sk_flags, lc.sk_prof};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
