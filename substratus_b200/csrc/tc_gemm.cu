@@ -85,6 +85,70 @@ struct TcCfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * TN * 4 /*per-token pos / KV block of a tile*/;
 };
 
+#ifndef TC_EPI_V2
+#define TC_EPI_V2 1  // prefill epilogue in passes of 32 tokens with the next pass's inputs prefetched (0 = 8 tokens at a time; variant "tcepi1")
+#endif
+// Epilogue inputs of CG consecutive tokens of one row pair — residual words (EPI_RESID) or packed RoPE cos|sin
+// (EPI_QKV_ROPE, positions staged in shared memory).  They do not depend on the accumulator, so a caller can have them in
+// flight while the MMAs of the tile (or the previous pass's stores) run; `on` = this lane runs the epilogue of a real row.
+template <int EPI, int CG>
+SSB_DEVINL void tc_epi_inputs(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, bool on, uint32_t (&w)[CG]) {
+  if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+    for (int j = 0; j < CG; ++j)
+      w[j] = (on && m0 + j < a.M) ? __ldcg(reinterpret_cast<const uint32_t*>(a.resid + (size_t)(m0 + j) * a.ld_out + 2 * pair)) : 0u;
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    const int half = a.head_dim >> 1, q_pairs = a.q_rows >> 1, qk_pairs = (a.q_rows + a.kv_rows) >> 1;
+    const int pp = pair < q_pairs ? pair : pair - q_pairs;
+    const int jj = pp % half;
+#pragma unroll
+    for (int j = 0; j < CG; ++j) w[j] = (on && pair < qk_pairs && m0 + j < a.M) ? a.rope_cs[(size_t)s_pos[j] * half + jj] : 0u;
+  }
+}
+// eight tokens of one row pair with their inputs already loaded (w = the eight words tc_epi_inputs produced for them)
+template <int EPI>
+SSB_DEVINL void tc_epi_store8(const GemvArgs& a, int pair, int m0, const int* __restrict__ s_pos, const int* __restrict__ s_blk,
+                              const uint32_t* w, const float (&mine)[8], const float (&other)[8]) {
+  if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (m0 + j < a.M)
+        *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)(m0 + j) * a.ld_out + 2 * pair) =
+            pack_bf16(bf16r(mine[j]) + bf_lo(w[j]), bf16r(other[j]) + bf_hi(w[j]));
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    tc_epilogue8_qkv_cs(a, pair, m0, s_pos, s_blk, w, mine, other);
+  } else {
+    tc_epilogue8<EPI>(a, pair, m0, mine, other);
+  }
+}
+
+// One pass of the fused epilogue: CG tokens of one row PAIR, split between the pair's two lanes.  Each lane holds its own
+// row's CG accumulators f[]; the even lane finishes tokens [0, CG/2) of the pass, the odd lane tokens [CG/2, CG), after
+// swapping the halves the partner needs.  (The first version let the even lane do all tokens while the odd lane idled: with
+// one epilogue warp per scheduler the epilogue is a dependent-issue chain, so instructions per warp are what it costs —
+// the split halves them.)  w = the inputs of THIS lane's CG/2 tokens (tc_epi_inputs at token m_base + off).  Must be
+// called by all 32 lanes (shuffles).  s_pos / s_blk point at the pass's first token inside the staged tile.
+template <int EPI, int CG>
+SSB_DEVINL void tc_epi_pass(const GemvArgs& a, int pair, bool on, int odd, int m_base, const int* __restrict__ s_pos,
+                            const int* __restrict__ s_blk, const float (&f)[CG], const uint32_t (&w)[CG / 2]) {
+  constexpr int H = CG / 2;
+  float recv[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) recv[j] = __shfl_xor_sync(0xffffffffu, odd ? f[j] : f[H + j], 1);
+  const int off = odd ? H : 0;
+#pragma unroll
+  for (int c = 0; c < H; c += 8) {
+    float v0[8], v1[8];  // even row (gate / first of the RoPE pair), odd row
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float own = odd ? f[H + c + j] : f[c + j];
+      v0[j] = odd ? recv[c + j] : own;
+      v1[j] = odd ? own : recv[c + j];
+    }
+    if (on && m_base + off + c < a.M) tc_epi_store8<EPI>(a, pair, m_base + off + c, s_pos + off + c, s_blk + off + c, &w[c], v0, v1);
+  }
+}
+
 template <int TN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemvArgs a) {
@@ -205,10 +269,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         named_bar_sync(2, 128);
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = nt * TC_BM + quad * 32 + lane;  // physical weight row (even = first of a pair)
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN;
+#if TC_EPI_V2
+      // passes of CG tokens: one TMEM read and one batch of input loads per pass instead of per 8 tokens (each batch is a
+      // full L2 round trip, ~0.7 us; a 256-token tile used to pay 32 of them in sequence), and the inputs of pass p+1 are
+      // requested before pass p is converted and stored.  The first batch flies while the tile's MMAs finish.
+      constexpr int CG = TN < 32 ? TN : 32;
+      constexpr int H = CG / 2;  // tokens per lane and pass (tc_epi_pass)
+      const bool on = row < a.N;
+      const int pair = row >> 1, odd = lane & 1, off = odd ? H : 0;
+      uint32_t w[H], wn[H];
+      tc_epi_inputs<EPI, H>(a, pair, mt * TN + off, s_pos + off, on, w);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g0 = 0; g0 < TN; g0 += CG) {
+        if (mt * TN + g0 >= a.M) break;  // warp-uniform
+        uint32_t v[CG];
+#pragma unroll
+        for (int q = 0; q < CG / 8; ++q) tc_ld8p(taddr + g0 + 8 * q, &v[8 * q]);
+        if (g0 + CG < TN && mt * TN + g0 + CG < a.M)
+          tc_epi_inputs<EPI, H>(a, pair, mt * TN + g0 + CG + off, s_pos + g0 + CG + off, on, wn);
+        tc_wait_ld();
+        float f[CG];
+#pragma unroll
+        for (int j = 0; j < CG; ++j) f[j] = __uint_as_float(v[j]);
+        tc_epi_pass<EPI, CG>(a, pair, on, odd, mt * TN + g0, s_pos + g0, s_blk + g0, f, w);
+#pragma unroll
+        for (int j = 0; j < H; ++j) w[j] = wn[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+#else
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < TN; c += 8) {
         if (mt * TN + c >= a.M) break;  // warp-uniform
@@ -230,6 +326,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+#endif
     }
   }
   tc_fence_before();
@@ -477,8 +574,9 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           cu = (int)((unsigned)(blockIdx.x + n_contrib + 2) * (unsigned)U / (unsigned)G);
         const int slot0 = (blockIdx.x + 1) * 2;  // contributor i dumped into slot0 + 2 i
         constexpr int CG = TN < 32 ? TN : 32;    // tokens per pass
-        const bool epi_lane = !(lane & 1) && row < a.N;
-        const int pair = row >> 1;
+        constexpr int H = CG / 2;                // tokens per lane and pass (tc_epi_pass)
+        const bool on = row < a.N;
+        const int pair = row >> 1, odd = lane & 1, off = odd ? H : 0;
         bool polled = false;
 #pragma unroll 1
         for (int g0 = 0; g0 < TN; g0 += CG) {
@@ -486,20 +584,9 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t v[CG];
 #pragma unroll
           for (int q = 0; q < CG / 8; ++q) tc_ld8p(taddr + g0 + 8 * q, &v[8 * q]);
-          // ---- epilogue inputs of these tokens
-          [[maybe_unused]] uint32_t w[CG];
-          if constexpr (EPI == EPI_RESID) {
-#pragma unroll
-            for (int j = 0; j < CG; ++j)
-              w[j] = (epi_lane && g0 + j < a.M) ? __ldcg(reinterpret_cast<const uint32_t*>(a.resid + (size_t)(g0 + j) * a.ld_out + 2 * pair)) : 0u;
-          } else if constexpr (EPI == EPI_QKV_ROPE) {
-            const int half = a.head_dim >> 1, qk_pairs = (a.q_rows + a.kv_rows) >> 1;
-            const int pp = pair < (a.q_rows >> 1) ? pair : pair - (a.q_rows >> 1);
-            const int jj = pp % half;
-#pragma unroll
-            for (int j = 0; j < CG; ++j)
-              w[j] = (epi_lane && pair < qk_pairs && g0 + j < a.M) ? a.rope_cs[(size_t)s_pos[g0 + j] * half + jj] : 0u;
-          }
+          // ---- epilogue inputs of this lane's half of the pass
+          uint32_t w[H];
+          tc_epi_inputs<EPI, H>(a, pair, g0 + off, s_pos + g0 + off, on, w);
           // ---- all contributors' flags in one round trip (they are normally up long before the owner gets here)
           if (!polled) {
             polled = true;
@@ -541,35 +628,14 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int q = 0; q < CG / 4; ++q) {
               f[4 * q] += x[q].x; f[4 * q + 1] += x[q].y; f[4 * q + 2] += x[q].z; f[4 * q + 3] += x[q].w;
             }
+            if (two) {  // warp-uniform
 #pragma unroll
-            for (int q = 0; q < CG / 4; ++q) {
-              f[4 * q] += y[q].x; f[4 * q + 1] += y[q].y; f[4 * q + 2] += y[q].z; f[4 * q + 3] += y[q].w;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < CG; c += 8) {
-            if (g0 + c < a.M) {  // warp-uniform
-              float mine[8], other[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                mine[j] = f[c + j];
-                other[j] = __shfl_xor_sync(0xffffffffu, mine[j], 1);
-              }
-              if (epi_lane) {
-                if constexpr (EPI == EPI_RESID) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (g0 + c + j < a.M)
-                      *reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)(g0 + c + j) * a.ld_out + 2 * pair) =
-                          pack_bf16(bf16r(mine[j]) + bf_lo(w[c + j]), bf16r(other[j]) + bf_hi(w[c + j]));
-                } else if constexpr (EPI == EPI_QKV_ROPE) {
-                  tc_epilogue8_qkv_cs(a, pair, g0 + c, s_pos + g0 + c, s_blk + g0 + c, &w[c], mine, other);
-                } else {
-                  tc_epilogue8<EPI>(a, pair, g0 + c, mine, other);
-                }
+              for (int q = 0; q < CG / 4; ++q) {
+                f[4 * q] += y[q].x; f[4 * q + 1] += y[q].y; f[4 * q + 2] += y[q].z; f[4 * q + 3] += y[q].w;
               }
             }
           }
+          tc_epi_pass<EPI, CG>(a, pair, on, odd, g0, s_pos + g0, s_blk + g0, f, w);
         }
         tc_fence_before();
         named_bar_sync(2, 128);  // every epilogue thread has consumed the partials
