@@ -10,6 +10,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> fused RoPE/KV-append | SwiGLU | residual, same math as gemv_epilogue).
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "sk_partition.h"
 #include <cuda.h>
 
 #include "common.cuh"
@@ -392,7 +393,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // routines on the critical path of every segment and of the owner's contributor search
   const int U = n_ntiles * nkb;
   const int G = (int)gridDim.x;
-  const int u0 = (int)((unsigned)blockIdx.x * (unsigned)U / (unsigned)G), u1 = (int)((unsigned)(blockIdx.x + 1) * (unsigned)U / (unsigned)G);
+  const int u0 = sk_begin(blockIdx.x, U, G), u1 = sk_begin(blockIdx.x + 1, U, G);  // sk_partition.h (checked exhaustively on the host)
   [[maybe_unused]] int* s_pos = reinterpret_cast<int*>(bars) + 64;  // [TN] position of each token (QKV epilogue), staged once
   [[maybe_unused]] int* s_blk = s_pos + TN;                        // [TN] KV block holding that position
 
@@ -569,9 +570,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // that does not depend on another is issued together: epilogue inputs first (they depend on nothing computed
         // here), all flags in one batch, partials of 32 tokens x 2 contributors in flight at a time.
         const int t_end = (nt + 1) * nkb;  // first unit after this tile
-        int n_contrib = 0;
-        for (int cu = u + (kb1 - kb0); cu < t_end && n_contrib < 12; ++n_contrib)
-          cu = (int)((unsigned)(blockIdx.x + n_contrib + 2) * (unsigned)U / (unsigned)G);
+        const int n_contrib = sk_contributors(blockIdx.x, U, G, u + (kb1 - kb0), t_end);
         const int slot0 = (blockIdx.x + 1) * 2;  // contributor i dumped into slot0 + 2 i
         constexpr int CG = TN < 32 ? TN : 32;    // tokens per pass
         constexpr int H = CG / 2;                // tokens per lane and pass (tc_epi_pass)
@@ -593,7 +592,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (;;) {
               unsigned ok = 1u;
 #pragma unroll
-              for (int i = 0; i < 12; ++i) {
+              for (int i = 0; i < SK_MAX_CONTRIB; ++i) {
                 unsigned f = 1u;
                 if (i < n_contrib) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(ws.flags + slot0 + 2 * i) : "memory");
                 ok &= (f != 0u) ? 1u : 0u;
@@ -794,10 +793,8 @@ static cudaError_t launch_sk_t(const TcTensorMap& tmA, const TcTensorMap& tmB, c
   }
   const int nkb = (a.K + TC_BK - 1) / TC_BK;
   const long long U = (long long)((a.N + TC_BM - 1) / TC_BM) * nkb;
-  const long long min_units = (nkb + 7) / 8;  // >= nkb/8 units per CTA: a tile spans at most 8 full + 2 partial ranges
-  long long gmax = U / min_units;
-  int grid = (int)(gmax < 1 ? 1 : (gmax < lc.n_sm ? gmax : lc.n_sm));
-  if (grid * 2 > lc.sk_slots || U * (grid + 1) >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int grid = sk_grid(U, nkb, lc.n_sm);  // >= nkb/8 units per CTA: a tile spans at most 8 full + 2 partial ranges
+  if (grid * 2 > lc.sk_slots || !sk_fits(U, grid)) return cudaErrorInvalidValue;
   const SkWs ws = {lc.sk_part, lc.sk_flags, lc.sk_prof};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
