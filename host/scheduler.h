@@ -12,7 +12,8 @@
 //
 // Failure isolation: SSB_ENOMEM (a resource limit, engine state untouched) costs ONE request — newcomers are re-prefilled
 // one by one, a decode retires its most recently admitted sequence and retries the rest; any other engine error fails the
-// batch and carries its code to the host (SSB_ECUDA there means exit for a pod restart).  With the pool size known
+// batch only if it is SSB_ECUDA (the host then exits for a pod restart); an argument the engine rejects (validated before
+// any state changes) makes that tick run sequence by sequence so only the offender is retired.  With the pool size known
 // (ssb_kv_blocks) requests are admitted only while their prompt + max_new blocks are unreserved, so ENOMEM stays a backstop.
 //
 // Decode never overshoots a request (the step count is the minimum remaining), newcomers wait at most one tick, and
@@ -56,6 +57,8 @@ struct Request {
 //   std::string last_error();
 // SSB_ENOMEM of include/ssb.h: a per-call resource limit (sequence slots, KV blocks) — the engine's state is untouched
 constexpr int kPerSequenceError = -4;
+// SSB_ECUDA: the device (or a tensor-parallel peer) is gone — nothing can be retried, the host exits for a pod restart
+constexpr int kFatalError = -5;
 
 template <class EngineT>
 class BatchScheduler {
@@ -163,9 +166,9 @@ class BatchScheduler {
         if (!ok.empty()) {
           std::vector<int32_t> next(ok.size());
           int prc = eng_->prefill(sids.data(), toks.data(), lens.data(), (int)ok.size(), next.data());
-          if (prc == kPerSequenceError && ok.size() > 1) {
-            // a resource limit (e.g. the KV block pool) hit by the joint call must not fail every newcomer: the engine
-            // rejects before it touches any state, so prefill them one by one and fail only those that do not fit
+          if (prc != 0 && prc != kFatalError && ok.size() > 1) {
+            // a resource limit (e.g. the KV block pool) or a rejected argument of ONE prompt must not fail every newcomer:
+            // the engine rejects before it touches any state, so prefill them one by one and fail only the offenders
             prc = 0;
             std::vector<Request*> ok2;
             std::vector<int> sids2;
@@ -212,14 +215,46 @@ class BatchScheduler {
       // ---- one decode tick over all active sequences, never past the shortest remaining request
       int nsteps = tick_;
       for (auto& a : active) nsteps = std::min(nsteps, a.r->max_new - (int)a.r->tokens.size());
-      const int n = (int)active.size();
-      std::vector<int> sids(n);
-      std::vector<int32_t> last(n), out((size_t)n * nsteps);
-      for (int i = 0; i < n; ++i) {
+      std::vector<int> sids(active.size());
+      std::vector<int32_t> last(active.size()), out(active.size() * (size_t)nsteps);
+      for (size_t i = 0; i < active.size(); ++i) {
         sids[i] = active[i].sid;
         last[i] = active[i].last;
       }
-      const int drc = eng_->decode(sids.data(), last.data(), n, nsteps, out.data());
+      int n = (int)active.size();
+      int drc = eng_->decode(sids.data(), last.data(), n, nsteps, out.data());
+      if (drc != 0 && drc != kPerSequenceError && drc != kFatalError && n > 1) {
+        // a rejected argument of ONE sequence (the engine validates everything before it touches any) must not fail its
+        // batch mates: run this tick sequence by sequence, retire the ones the engine refuses, carry on with the others
+        std::vector<Active> keep;
+        std::vector<int32_t> out2, one((size_t)nsteps);
+        drc = 0;
+        for (int i = 0; i < n && drc != kFatalError; ++i) {
+          const int rc1 = eng_->decode(&sids[i], &last[i], 1, nsteps, one.data());
+          if (rc1 == 0) {
+            keep.push_back(active[i]);
+            out2.insert(out2.end(), one.begin(), one.end());
+          } else if (rc1 == kFatalError) {
+            drc = rc1;  // the device is gone: everybody fails below
+          } else {
+            const std::string e = eng_->last_error();
+            eng_->seq_free(active[i].sid);
+            finish(active[i].r, e, rc1);
+            active[i].r = nullptr;
+          }
+        }
+        if (drc == kFatalError) {
+          std::vector<Active> left;
+          for (auto& a : active)
+            if (a.r) left.push_back(a);
+          active.swap(left);
+        } else {
+          active.swap(keep);
+          out.swap(out2);
+          n = (int)active.size();
+          if (n == 0) continue;
+        }
+      }
       if (drc == kPerSequenceError && n > 1) {
         // resource limit (KV blocks for the next steps): the engine refused before changing any sequence.  Retire the most
         // recently admitted request with the error and retry the others on the next pass instead of failing the whole batch.

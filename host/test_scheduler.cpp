@@ -14,6 +14,7 @@ struct FakeEngine {
   std::mutex mu;
   std::map<int, int> len;  // sid -> cached length
   int next_sid = 0, max_slots = 8;
+  int max_len = 1 << 30;    // a sequence that would grow past it makes the call fail with -1 ("bad argument"), state untouched
   int kv_budget = 1 << 30;  // total cached tokens the fake "KV pool" holds: calls that would exceed it fail with -4, state untouched
   std::string err;
   std::atomic<int> decode_calls{0};
@@ -44,6 +45,11 @@ struct FakeEngine {
       err = "KV block pool exhausted";
       return -4;
     }
+    for (int i = 0, o = 0; i < nseq; o += lens[i], ++i)
+      if (toks[o] == 666 || len[sids[i]] + lens[i] > max_len) {  // validation first, like the engine
+        err = "bad prompt";
+        return -1;
+      }
     for (int i = 0, o = 0; i < nseq; o += lens[i], ++i) {
       len[sids[i]] += lens[i];
       next[i] = step(toks[o + lens[i] - 1], len[sids[i]]);
@@ -58,6 +64,11 @@ struct FakeEngine {
       err = "KV block pool exhausted";
       return -4;
     }
+    for (int i = 0; i < nseq; ++i)
+      if (len[sids[i]] + nsteps > max_len) {
+        err = "sequence would exceed max_seq_len";
+        return -1;
+      }
     for (int i = 0; i < nseq; ++i) {
       int32_t t = last[i];
       for (int s = 0; s < nsteps; ++s) {
@@ -172,6 +183,40 @@ int main() {
       printf("FAIL slots leaked after exhaustion\n");
       ++failures;
     }
+  }
+  {
+    // an argument the engine rejects for ONE sequence (a poisoned prompt at prefill, a sequence that outgrows max_len in
+    // decode) costs that request only: the others finish with the ids they would get alone
+    FakeEngine picky;
+    picky.max_len = 50;
+    ssbhost::BatchScheduler<FakeEngine> sched(&picky, 8, 4);
+    const int kClients = 7;
+    std::vector<ssbhost::Request> reqs(kClients);
+    std::vector<std::thread> th;
+    for (int c = 0; c < kClients; ++c) {
+      reqs[c].prompt.assign(10 + c, (int32_t)(c + 1));
+      reqs[c].max_new = 20;
+    }
+    reqs[2].prompt[0] = 666;  // rejected at prefill
+    reqs[5].max_new = 60;     // 15 + 60 > 50: rejected by a decode call some ticks in
+    for (int c = 0; c < kClients; ++c) th.emplace_back([&, c] { sched.submit(&reqs[c]); });
+    for (auto& t : th) t.join();
+    for (int c = 0; c < kClients; ++c) {
+      const bool should_fail = c == 2 || c == 5;
+      if (should_fail != !reqs[c].error.empty() || (should_fail && reqs[c].error_code != -1)) {
+        printf("FAIL isolation: request %d error '%s' code %d\n", c, reqs[c].error.c_str(), reqs[c].error_code);
+        ++failures;
+      }
+      if (!should_fail && reqs[c].tokens != alone(reqs[c].prompt, reqs[c].max_new)) {
+        printf("FAIL isolation: survivor %d got wrong ids\n", c);
+        ++failures;
+      }
+    }
+    if (!picky.len.empty()) {
+      printf("FAIL slots leaked after per-sequence errors\n");
+      ++failures;
+    }
+    printf("argument-error isolation test done\n");
   }
   {
     // same pool, but the scheduler knows its size (ssb_kv_blocks): requests queue for blocks instead of failing
