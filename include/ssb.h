@@ -65,6 +65,8 @@ typedef struct ssb_timing {
  *   "max_batch" (32), "max_seq_len" (config's), "kv_block_size" (16), "kv_blocks" (auto),
  *   "weights": "file" | "synthetic" (seeded hash weights at config.json's shapes; "seed"),
  *   "tp_size", "tp_rank" (1, 0), "device" (tp_rank),
+ *   "tp_presharded" (1: with tp_size N > 1, if <model_dir>/ssb_tp<N>/rank<tp_rank>.safetensors exists — written by
+ *   tools/tp_shard.py: this rank's slices of the projections + the replicated tensors — the rank loads that file alone),
  *   "use_pdl" (1), "use_graph" (1), "use_mega" (1: persistent single-kernel decode step at batch <= 4),
  *   "gemm_path": "auto" | "gemv" | "tc", "tc_min_rows" (5), "tc_streamk" (1), "prefill_chunk" (1024),
  *   "tc_tn_prefill" (0 = per-projection heuristic | 128 | 256: token-tile width of the prefill GEMMs),

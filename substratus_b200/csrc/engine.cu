@@ -5,6 +5,7 @@
 // Forward structure = HF LlamaModel.forward / LlamaDecoderLayer.forward (HF:models/llama/modeling_llama.py:292-332,
 // 355-500); greedy loop = HF:generation/utils.py:2658-2800.  No CPU fallback anywhere: init() fails with
 // SSB_ENODEV when there is no sm_100 device.
+#include <sys/stat.h>
 #include "engine.h"
 #include "tokenizer.h"
 
@@ -189,7 +190,11 @@ struct FillJob {
 
 int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed, bool validate_only) {
   const int h = cfg_.hidden, D = cfg_.head_dim, half = D / 2;
-  const int h0 = tp_rank_ * Hl_, kv0 = tp_rank_ * KVHl_, i0 = tp_rank_ * Il_;
+  // a pre-sharded artifact holds this rank's slices only: the same jobs with every offset zero and the row-parallel
+  // matrices as wide as the slice (the device-side gather / interleave is unchanged)
+  const bool pre = tp_presharded_ && !synthetic;
+  const int h0 = pre ? 0 : tp_rank_ * Hl_, kv0 = pre ? 0 : tp_rank_ * KVHl_, i0 = pre ? 0 : tp_rank_ * Il_;
+  const int64_t o_cols = pre ? (int64_t)Hl_ * cfg_.head_dim : (int64_t)cfg_.heads * cfg_.head_dim, down_cols = pre ? Il_ : cfg_.inter;
   std::vector<FillJob> jobs;
   auto ident = [](int start, int n) {
     std::vector<int> v(n);
@@ -237,9 +242,9 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed, 
       jobs.push_back({w.wqkv, h, q_rows(), Hl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
       jobs.push_back({w.wqkv + (size_t)Hl_ * D * h, h, k_rows(), KVHl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
       jobs.push_back({w.wqkv + (size_t)(Hl_ + KVHl_) * D * h, h, v_rows(), KVHl_ * D, 0, h, h, qkv, t + 11, kWAmp, 0.f});
-      jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, (int64_t)cfg_.heads * D, p + "self_attention.dense.weight", t + K_O, kWAmp, 0.f});
+      jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, o_cols, p + "self_attention.dense.weight", t + K_O, kWAmp, 0.f});
       jobs.push_back({w.wgu, h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.dense_h_to_4h.weight", t + 9, kWAmp, 0.f});
-      jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, cfg_.inter, p + "mlp.dense_4h_to_h.weight", t + 10, kWAmp, 0.f});
+      jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, down_cols, p + "mlp.dense_4h_to_h.weight", t + 10, kWAmp, 0.f});
       jobs.push_back({w.ln1, h, {}, 1, 0, h, h, p + "ln_attn.weight", t + K_LN1, kNormAmp, 1.f});
       jobs.push_back({w.ln1_b, h, {}, 1, 0, h, h, p + "ln_attn.bias", t + 12, kNormAmp, 0.f});
       jobs.push_back({w.ln2, h, {}, 1, 0, h, h, p + "ln_mlp.weight", t + K_LN2, kNormAmp, 1.f});
@@ -257,11 +262,11 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed, 
     jobs.push_back({w.wqkv, h, rope_rows(h0, Hl_), Hl_ * D, 0, h, h, p + "self_attn.q_proj.weight", t + K_Q, kWAmp, 0.f});
     jobs.push_back({w.wqkv + (size_t)Hl_ * D * h, h, rope_rows(kv0, KVHl_), KVHl_ * D, 0, h, h, p + "self_attn.k_proj.weight", t + K_K, kWAmp, 0.f});
     jobs.push_back({w.wqkv + (size_t)(Hl_ + KVHl_) * D * h, h, ident(kv0 * D, KVHl_ * D), KVHl_ * D, 0, h, h, p + "self_attn.v_proj.weight", t + K_V, kWAmp, 0.f});
-    jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, (int64_t)cfg_.heads * D, p + "self_attn.o_proj.weight", t + K_O, kWAmp, 0.f});
+    jobs.push_back({w.wo, (int64_t)Hl_ * D, {}, h, h0 * D, Hl_ * D, o_cols, p + "self_attn.o_proj.weight", t + K_O, kWAmp, 0.f});
     // gate/up interleaved row-wise: physical row 2i = gate_i, 2i+1 = up_i (SwiGLU partners adjacent)
     jobs.push_back({w.wgu, 2 * (int64_t)h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.gate_proj.weight", t + K_GATE, kWAmp, 0.f});
     jobs.push_back({w.wgu + h, 2 * (int64_t)h, ident(i0, Il_), Il_, 0, h, h, p + "mlp.up_proj.weight", t + K_UP, kWAmp, 0.f});
-    jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, cfg_.inter, p + "mlp.down_proj.weight", t + K_DOWN, kWAmp, 0.f});
+    jobs.push_back({w.wdown, Il_, {}, h, i0, Il_, down_cols, p + "mlp.down_proj.weight", t + K_DOWN, kWAmp, 0.f});
     jobs.push_back({w.ln1, h, {}, 1, 0, h, h, p + "input_layernorm.weight", t + K_LN1, kNormAmp, 1.f});
     jobs.push_back({w.ln2, h, {}, 1, 0, h, h, p + "post_attention_layernorm.weight", t + K_LN2, kNormAmp, 1.f});
   }
@@ -316,6 +321,7 @@ int Engine::fill_weights(const std::string& dir, bool synthetic, uint64_t seed, 
       int64_t max_row = j.rows.empty() ? j.n_rows - 1 : 0;
       for (int r : j.rows) max_row = std::max<int64_t>(max_row, r);
       if (max_row >= tv->rows()) RET(SSB_EINVAL, "tensor " + j.name + " has too few rows for this config");
+      if (pre && files.is_gguf()) RET(SSB_EINVAL, "a pre-sharded artifact cannot be GGUF");
       max_src = std::max(max_src, tv->nbytes);
       if (tv->dtype >= DT_Q4_0) {
         int64_t n = 1;
@@ -721,7 +727,26 @@ int Engine::init(const std::string& model_dir, const std::string& params_json) {
   if (wmode != "file" && wmode != "synthetic") RET(SSB_EINVAL, "params.weights must be 'file' or 'synthetic'");
   if (wmode == "file") {
     std::string err;
-    if (!files_.open(model_dir, &err)) RET(SSB_EIO, err);
+    // A tensor-parallel rank prefers its pre-sharded artifact (written by tools/tp_shard.py): ONE safetensors
+    // file with exactly this rank's slices of the projections plus the replicated tensors, so a rank reads ~1/N of the
+    // checkpoint at pod start instead of mapping all of it.  "tp_presharded": 0 ignores it.
+    const long long tps = params.get_int("tp_size", 1), tpr = params.get_int("tp_rank", 0);
+    const std::string shard = std::string(model_dir) + "/ssb_tp" + std::to_string(tps) + "/rank" + std::to_string(tpr) + ".safetensors";
+    struct stat st;
+    if (tps > 1 && params.get_int("tp_presharded", 1) != 0 && stat(shard.c_str(), &st) == 0) {
+      if (!files_.open_file(shard, &err)) RET(SSB_EIO, err);
+      const auto& md = files_.metadata();
+      auto get = [&](const char* k) {
+        auto it = md.find(k);
+        return it == md.end() ? std::string() : it->second;
+      };
+      if (get("format") != "ssb-tp" || get("tp_size") != std::to_string(tps) || get("tp_rank") != std::to_string(tpr))
+        RET(SSB_EINVAL, shard + " is not the pre-sharded artifact of rank " + std::to_string(tpr) + " of " + std::to_string(tps) +
+                            " (metadata format / tp_size / tp_rank)");
+      tp_presharded_ = true;
+    } else if (!files_.open(model_dir, &err)) {
+      RET(SSB_EIO, err);
+    }
   }
   TRY(load_config(model_dir, params));
   if (tp_size_ > 8) RET(SSB_EINVAL, "tp_size > 8 is not supported (one NVSwitch domain)");

@@ -86,6 +86,7 @@ class Engine {
   float* sk_part_ = nullptr;  // stream-K workspace of the tensor-core decode projections
   unsigned* sk_flags_ = nullptr;
   int sk_slots_ = 0;
+  bool tp_presharded_ = false;  // weights come from <model_dir>/ssb_tp<N>/rank<r>.safetensors (this rank's slices only)
   unsigned long long* sk_prof_ = nullptr;  // params "sk_prof": 1 (needs the skprof variant library to be written)
 
   ModelCfg cfg_;

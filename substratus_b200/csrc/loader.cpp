@@ -124,7 +124,12 @@ bool ModelFiles::open_safetensors(const std::string& path, std::string* err) {
   const uint8_t* base = f->data() + 8 + hlen;
   const size_t avail = f->size() - 8 - (size_t)hlen;
   for (auto& kv : hdr.obj) {
-    if (kv.first == "__metadata__") continue;
+    if (kv.first == "__metadata__") {
+      if (kv.second.kind == Json::Obj)
+        for (auto& m : kv.second.obj)
+          if (m.second.kind == Json::Str) metadata_[m.first] = m.second.str;
+      continue;
+    }
     const Json& t = kv.second;
     TensorView v;
     v.name = kv.first;

@@ -43,6 +43,10 @@ class ModelFiles {
   // Opens every *.safetensors — else every pytorch_model*.bin (torch.save zip, torch_zip.cpp) — else the single
   // *.gguf / model.bin GGUF under dir.  Returns false + err on failure.
   bool open(const std::string& dir, std::string* err);
+  // One safetensors file (a tensor-parallel rank's pre-sharded artifact, <dir>/ssb_tp<N>/rank<r>.safetensors).
+  bool open_file(const std::string& path, std::string* err) { return open_safetensors(path, err); }
+  // string entries of the safetensors "__metadata__" objects seen so far (later files override earlier ones)
+  const std::map<std::string, std::string>& metadata() const { return metadata_; }
   const TensorView* find(const std::string& name) const;
   bool is_gguf() const { return is_gguf_; }
   const Json& gguf_meta() const { return gguf_meta_; }  // GGUF key/values as a JSON object (numbers/strings/arrays)
@@ -55,6 +59,7 @@ class ModelFiles {
   bool open_torch_zip(const std::string& path, std::string* err);
   std::vector<std::unique_ptr<MappedFile>> files_;
   std::map<std::string, TensorView> tensors_;
+  std::map<std::string, std::string> metadata_;
   bool is_gguf_ = false;
   Json gguf_meta_;
 };

@@ -394,3 +394,58 @@ def test_pathological_json_is_an_error_not_a_crash(tmp_path, lib):
         h = C.c_void_p()
         assert L.ssb_engine_create(str(tmp_path).encode(), payload, C.byref(h)) == EINVAL
         assert b"json" in L.ssb_last_error() or b"params" in L.ssb_last_error()
+
+
+@pytest.mark.parametrize("family", ["llama", "falcon"])
+def test_tp_presharded_artifact(tmp_path, no_gpu, lib, family):
+    """tools/tp_shard.py writes one safetensors file per tensor-parallel rank; an engine created with that
+    tp_size reads ONLY that file (the original shards may be gone), its inventory passes the host-side validation and
+    creation gets as far as the device check.  The slices are a partition of the original tensors."""
+    import sys
+
+    from safetensors import safe_open
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import tp_shard
+
+    if family == "llama":
+        cfg = dict(synth.TINY_GQA, num_attention_heads=8, num_key_value_heads=4, hidden_size=1024, intermediate_size=2752)
+        sd = synth.llama_state_dict(cfg, 3)
+    else:
+        from oracle import falcon_ref as fr
+
+        cfg = dict(fr.TINY_FALCON, hidden_size=512, num_attention_heads=8, num_kv_heads=4)
+        sd = fr.falcon_state_dict(cfg, 3)
+    llama_ref.write_hf_dir(str(tmp_path), cfg, sd, shards=2)
+    files = tp_shard.shard(str(tmp_path), 2, quiet=True)
+    assert [os.path.basename(f) for f in files] == ["rank0.safetensors", "rank1.safetensors"]
+    # a partition: concatenating the rank slices along the sharded axis gives the original tensor back; replicated
+    # tensors are whole in every rank file
+    parts = [safe_open(f, framework="pt") for f in files]
+    assert parts[1].metadata() == {"format": "ssb-tp", "tp_size": "2", "tp_rank": "1", "source": os.path.basename(str(tmp_path))}
+    sharded_bytes = 0
+    for name, full in sd.items():
+        a, b = parts[0].get_tensor(name), parts[1].get_tensor(name)
+        if a.shape == full.shape:
+            assert torch.equal(a, full) and torch.equal(b, full)
+        else:
+            axis = 0 if a.shape[0] != full.shape[0] else 1
+            assert torch.equal(torch.cat([a, b], dim=axis), full), name
+            sharded_bytes += full.numel() * 2
+    assert sharded_bytes > 0.5 * sum(t.numel() * 2 for t in sd.values())  # most of the checkpoint IS sharded
+    # the engine takes the rank file (validated on the host, then stops at the device check) ...
+    for r in (0, 1):
+        e = _create(tmp_path, {"tp_size": 2, "tp_rank": r})
+        assert e.code == ENODEV, str(e)
+    # ... and only the rank file: without the original shards the pre-sharded ranks still load, a full load does not
+    for f in os.listdir(tmp_path):
+        if f.endswith(".safetensors") or f.endswith(".index.json"):
+            os.remove(tmp_path / f)
+    assert _create(tmp_path, {"tp_size": 2, "tp_rank": 1}).code == ENODEV
+    e = _create(tmp_path, {"tp_size": 2, "tp_rank": 1, "tp_presharded": 0})
+    assert e.code == EIO and "safetensors" in str(e)
+    assert _create(tmp_path).code == EIO  # tp_size 1 never looks at ssb_tp*
+    # a rank file in the wrong place is refused by its metadata, a foreign safetensors file too
+    os.replace(tmp_path / "ssb_tp2" / "rank1.safetensors", tmp_path / "ssb_tp2" / "rank0.safetensors")
+    e = _create(tmp_path, {"tp_size": 2, "tp_rank": 0})
+    assert e.code == EINVAL and "pre-sharded" in str(e)

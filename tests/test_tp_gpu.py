@@ -135,3 +135,52 @@ def test_falcon_tp_matches_tp1_and_oracle(tmp_path, world, mode):
     ref32 = fr.FalconRef(cfg, sd, torch.float32).forward(torch.tensor([prompts[1]]))[0, -1].numpy()
     refbf = fr.FalconRef(cfg, sd, torch.bfloat16).forward(torch.tensor([prompts[1]]))[0, -1].float().numpy()
     assert rel_err(ltp[0, 1], ref32) <= 1.5 * rel_err(refbf, ref32) + 1e-3
+
+
+@pytest.mark.parametrize("family", ["llama", "falcon"])
+def test_presharded_ranks_reproduce_the_full_checkpoint(tmp_path, family):
+    """ranks that load their pre-sharded artifact (tools/tp_shard.py -> ssb_tp2/rank<r>.safetensors, the full
+    shards deleted) hold the same weights as ranks that slice the full checkpoint themselves: same ids, same logits.
+    (The host side of this — inventory, metadata, partition — runs on CPU in tests/test_loader_cpu.py.)"""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import shutil
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import tp_shard
+
+    if family == "llama":
+        cfg = dict(synth.TINY_GQA, num_attention_heads=8, num_key_value_heads=4, hidden_size=1024, intermediate_size=2752)
+        sd = synth.llama_state_dict(cfg, 17)
+    else:
+        from oracle import falcon_ref as fr
+
+        cfg = dict(fr.TINY_FALCON, hidden_size=512, num_attention_heads=8, num_kv_heads=4)
+        sd = fr.falcon_state_dict(cfg, 29)
+    full, pre = tmp_path / "full", tmp_path / "pre"
+    llama_ref.write_hf_dir(str(full), cfg, sd)
+    shutil.copytree(full, pre)
+    tp_shard.shard(str(pre), world, quiet=True)
+    for f in os.listdir(pre):
+        if f.endswith(".safetensors"):
+            os.remove(pre / f)  # only config.json + ssb_tp2/ are left
+    gen = torch.Generator().manual_seed(5)
+    prompts = [torch.randint(0, cfg["vocab_size"], (n,), generator=gen).tolist() for n in (19, 40)]
+    out = {}
+    for tag, d in (("full", full), ("pre", pre)):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        ps = [ctx.Process(target=_worker, args=(r, world, port, str(d), prompts, 6, {}, q)) for r in range(world)]
+        for p in ps:
+            p.start()
+        res = sorted([q.get(timeout=240) for _ in ps], key=lambda x: x[0])
+        for p in ps:
+            p.join(timeout=60)
+        for r, toks, _ in res:
+            assert not isinstance(toks, str), f"{tag} rank {r}: {toks}"
+        out[tag] = res[0]
+    assert np.array_equal(out["full"][1], out["pre"][1])
+    assert rel_err(out["pre"][2][0], out["full"][2][0]) < 1e-3  # identical weights; only exchange timing may differ
