@@ -10,11 +10,11 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> fused RoPE/KV-append | SwiGLU | residual, same math as gemv_epilogue).
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include "sk_partition.h"
 #include <cuda.h>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sk_partition.h"
 #include "tc_gemm.h"
 
 #include "epilogue.cuh"
