@@ -449,3 +449,38 @@ def test_tp_presharded_artifact(tmp_path, no_gpu, lib, family):
     os.replace(tmp_path / "ssb_tp2" / "rank1.safetensors", tmp_path / "ssb_tp2" / "rank0.safetensors")
     e = _create(tmp_path, {"tp_size": 2, "tp_rank": 0})
     assert e.code == EINVAL and "pre-sharded" in str(e)
+
+
+def test_tp_shard_plan_covers_the_baseline_models():
+    """tools/tp_shard.py's partition at the BASELINE shapes (no tensors needed): for every TP size the engine accepts, the
+    per-rank row / column ranges of each projection are contiguous, equal-sized and tile the full dimension."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import tp_shard
+    from oracle import falcon_ref as fr
+
+    for cfg, names in ((synth.LLAMA2_7B, "llama"), (synth.LLAMA2_13B, "llama"), (synth.LLAMA2_70B, "llama"), (fr.FALCON_40B, "falcon")):
+        heads = cfg["num_attention_heads"]
+        d = cfg["hidden_size"] // heads
+        if names == "llama":
+            kvh, inter = cfg.get("num_key_value_heads", heads), cfg["intermediate_size"]
+            dims = {"model.layers.0.self_attn.q_proj.weight": ("rows", heads * d), "model.layers.0.self_attn.k_proj.weight": ("rows", kvh * d),
+                    "model.layers.0.self_attn.v_proj.weight": ("rows", kvh * d), "model.layers.0.self_attn.o_proj.weight": ("cols", heads * d),
+                    "model.layers.0.mlp.gate_proj.weight": ("rows", inter), "model.layers.0.mlp.up_proj.weight": ("rows", inter),
+                    "model.layers.0.mlp.down_proj.weight": ("cols", inter), "model.norm.weight": ("full", 0), "lm_head.weight": ("full", 0)}
+        else:
+            kvh, inter = cfg["num_kv_heads"], cfg.get("ffn_hidden_size", 4 * cfg["hidden_size"])
+            dims = {"transformer.h.0.self_attention.query_key_value.weight": ("rows", (heads + 2 * kvh) * d),
+                    "transformer.h.0.self_attention.dense.weight": ("cols", heads * d), "transformer.h.0.mlp.dense_h_to_4h.weight": ("rows", inter),
+                    "transformer.h.0.mlp.dense_4h_to_h.weight": ("cols", inter), "transformer.ln_f.weight": ("full", 0)}
+        for tp in (2, 4, 8):
+            if kvh % tp:
+                continue
+            rules = [tp_shard.plan(cfg, tp)(r) for r in range(tp)]
+            for name, (kind, full) in dims.items():
+                got = [rule(name) for rule in rules]
+                assert all(g[0] == kind for g in got), (name, got)
+                if kind != "full":
+                    assert got[0][1] == 0 and got[-1][2] == full and all(got[i][2] == got[i + 1][1] for i in range(tp - 1)), (name, tp, got)
+                    assert len({g[2] - g[1] for g in got}) == 1
