@@ -1,7 +1,8 @@
 """Where a batched-decode stream-K projection spends its time: per-CTA globaltimer stamps of the LAST launch of
 `bench_kernel(<class>, rows=32)` on Llama-2-7B shapes.  Needs the stamped library: SSB_LIB_VARIANT=skprof python tools/sk_prof.py
 Columns (us from the earliest CTA's entry, median [min..max] over CTAs): entry, setup done, first weight tile landed,
-last MMA committed, epilogue saw the last accumulator, epilogue done, exit."""
+last MMA committed, epilogue saw the last accumulator, epilogue done, "exit" (thread 0 after the final barrier — in practice
+the time the producer lane ARRIVED there: the timer read issues before the warp blocks; do not read it as the exit time)."""
 import json, os, sys, tempfile
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
